@@ -1,0 +1,26 @@
+#!/bin/bash
+# Builds dextractor_b200/libdexb200.so for sm_100a (B200).  nvcc cross-compiles without a GPU.
+set -e
+cd "$(dirname "$0")"
+OUT=../libdexb200.so
+NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
+FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC,-Wall,-Wno-unused-function -I../../include -I."
+mkdir -p build
+objs=""
+for f in dx_frame.cu dx_qv_stats.cu dx_qv_encode.cu dx_qv_decode.cu dx_pack.cu; do
+  o=build/${f%.cu}.o
+  if [ ! -f $o ] || [ $f -nt $o ] || [ dx_common.cuh -nt $o ] || [ dx_internal.h -nt $o ] || [ ../../include/dexb200.h -nt $o ]; then
+    $NVCC $FLAGS ${PTXAS_V:+-Xptxas -v} -c $f -o $o &
+  fi
+  objs="$objs $o"
+done
+for f in dx_api.cpp dx_coding.cpp; do
+  o=build/${f%.cpp}.o
+  if [ ! -f $o ] || [ $f -nt $o ] || [ dx_internal.h -nt $o ] || [ ../../include/dexb200.h -nt $o ]; then
+    $NVCC $FLAGS -x cu -c $f -o $o &
+  fi
+  objs="$objs $o"
+done
+wait
+$NVCC -shared -gencode arch=compute_100a,code=sm_100a -o $OUT $objs -lcudart_static -lpthread -ldl -lrt
+echo "built $OUT"

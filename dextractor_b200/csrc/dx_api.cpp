@@ -1,0 +1,1121 @@
+// dx_api.cpp -- the C ABI of libdexb200.so (include/dexb200.h): context, device scratch arena,
+// and the host-side orchestration of the kernels.  The host does only what the reference does
+// once per file (prefix, coding header, code-length assignment) or what costs O(#entries)
+// integer work (header text lengths, chain verification); every per-symbol loop is a kernel.
+//
+// There is no CPU implementation of the codecs in this library: without a CUDA device dx_open
+// fails with DX_E_NOGPU and nothing else can be called.
+
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+#include "dx_internal.h"
+
+// ================================================================================================
+//  errors, context, arena
+// ================================================================================================
+
+int dx_fail(dx_ctx *ctx, int code, const char *fmt, ...)
+{ if (ctx != NULL)
+    { va_list ap;
+      va_start(ap,fmt);
+      vsnprintf(ctx->err,sizeof(ctx->err),fmt,ap);
+      va_end(ap);
+    }
+  return code;
+}
+
+int dx_cuda_fail(dx_ctx *ctx, cudaError_t e, const char *what)
+{ return dx_fail(ctx,DX_E_CUDA,"CUDA error %d (%s) in %s",(int) e,cudaGetErrorString(e),what); }
+
+static size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+void dx_arena_reset(dx_ctx *ctx)
+{ if (ctx->nblk > 1)
+    { // the last call spilled over: consolidate into one block big enough for all of it
+      size_t total = 0;
+      for (int i = 0; i < ctx->nblk; i++)
+        { total += ctx->blk[i].cap;
+          cudaFree(ctx->blk[i].p);
+        }
+      ctx->nblk = 0;
+      uint8_t *p = NULL;
+      total = round_up(total + total/4,(size_t) 1 << 20);
+      if (cudaMalloc((void **) &p,total) == cudaSuccess)
+        { ctx->blk[0].p = p; ctx->blk[0].cap = total; ctx->blk[0].top = 0; ctx->nblk = 1; }
+      else
+        cudaGetLastError();
+    }
+  for (int i = 0; i < ctx->nblk; i++)
+    ctx->blk[i].top = 0;
+}
+
+void *dx_arena_get(dx_ctx *ctx, size_t bytes)
+{ bytes = round_up(bytes > 0 ? bytes : 1,256);
+  for (int i = 0; i < ctx->nblk; i++)
+    if (ctx->blk[i].top + bytes <= ctx->blk[i].cap)
+      { void *p = ctx->blk[i].p + ctx->blk[i].top;
+        ctx->blk[i].top += bytes;
+        return p;
+      }
+  if (ctx->nblk >= 32)
+    { dx_fail(ctx,DX_E_NOMEM,"scratch arena exhausted (32 blocks)");
+      return NULL;
+    }
+  size_t cap = round_up(bytes > ((size_t) 32 << 20) ? bytes : ((size_t) 32 << 20),(size_t) 1 << 20);
+  uint8_t *p = NULL;
+  cudaError_t e = cudaMalloc((void **) &p,cap);
+  if (e != cudaSuccess)
+    { dx_cuda_fail(ctx,e,"cudaMalloc(scratch)");
+      return NULL;
+    }
+  DxBlock &b = ctx->blk[ctx->nblk++];
+  b.p = p; b.cap = cap; b.top = bytes;
+  return p;
+}
+
+int dx_arena_reserve(dx_ctx *ctx, size_t bytes)
+{ void *p = dx_arena_get(ctx,bytes);
+  if (p == NULL) return DX_E_NOMEM;
+  dx_arena_reset(ctx);
+  return DX_OK;
+}
+
+extern "C" int dx_open(int device, dx_ctx **out)
+{ if (out == NULL) return DX_E_ARG;
+  *out = NULL;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
+    { cudaGetLastError();
+      return DX_E_NOGPU;
+    }
+  if (device < 0 || device >= ndev) return DX_E_ARG;
+  if (cudaSetDevice(device) != cudaSuccess) return DX_E_CUDA;
+  dx_ctx *ctx = (dx_ctx *) calloc(1,sizeof(dx_ctx));
+  if (ctx == NULL) return DX_E_NOMEM;
+  ctx->device = device;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop,device) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&ctx->stream,cudaStreamNonBlocking) != cudaSuccess)
+    { free(ctx);
+      return DX_E_CUDA;
+    }
+  ctx->sm_count = prop.multiProcessorCount;
+  *out = ctx;
+  return DX_OK;
+}
+
+extern "C" void dx_close(dx_ctx *ctx)
+{ if (ctx == NULL) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  for (int i = 0; i < ctx->nblk; i++) cudaFree(ctx->blk[i].p);
+  if (ctx->io_in)    cudaFree(ctx->io_in);
+  if (ctx->io_out)   cudaFree(ctx->io_out);
+  if (ctx->qv_store) cudaFree(ctx->qv_store);
+  cudaStreamDestroy(ctx->stream);
+  free(ctx);
+}
+
+extern "C" const char *dx_strerror(const dx_ctx *ctx) { return ctx ? ctx->err : "no context"; }
+extern "C" int64_t     dx_error_line(const dx_ctx *ctx) { return ctx ? ctx->err_line : 0; }
+extern "C" void       *dx_stream(dx_ctx *ctx) { return ctx ? (void *) ctx->stream : NULL; }
+
+extern "C" int dx_sync(dx_ctx *ctx)
+{ DX_CUDA(ctx,cudaStreamSynchronize(ctx->stream));
+  return DX_OK;
+}
+
+extern "C" uint64_t dx_launch_count(dx_ctx *ctx, int reset)
+{ uint64_t v = ctx->launches;
+  if (reset) ctx->launches = 0;
+  return v;
+}
+
+extern "C" void *dx_device_alloc(dx_ctx *ctx, size_t bytes)
+{ void *p = NULL;
+  cudaSetDevice(ctx->device);
+  cudaError_t e = cudaMalloc(&p,round_up(bytes + 64,256));
+  if (e != cudaSuccess) { dx_cuda_fail(ctx,e,"cudaMalloc"); return NULL; }
+  return p;
+}
+extern "C" void dx_device_free(dx_ctx *ctx, void *p) { (void) ctx; if (p) cudaFree(p); }
+
+extern "C" void *dx_pinned_alloc(dx_ctx *ctx, size_t bytes)
+{ void *p = NULL;
+  cudaError_t e = cudaHostAlloc(&p,bytes > 0 ? bytes : 1,cudaHostAllocDefault);
+  if (e != cudaSuccess) { dx_cuda_fail(ctx,e,"cudaHostAlloc"); return NULL; }
+  return p;
+}
+extern "C" void dx_pinned_free(dx_ctx *ctx, void *p) { (void) ctx; if (p) cudaFreeHost(p); }
+
+extern "C" int dx_h2d(dx_ctx *ctx, void *d, const void *h, size_t n)
+{ DX_CUDA(ctx,cudaMemcpyAsync(d,h,n,cudaMemcpyHostToDevice,ctx->stream)); return DX_OK; }
+extern "C" int dx_d2h(dx_ctx *ctx, void *h, const void *d, size_t n)
+{ DX_CUDA(ctx,cudaMemcpyAsync(h,d,n,cudaMemcpyDeviceToHost,ctx->stream)); return DX_OK; }
+
+// ---- small helpers ---------------------------------------------------------------------------
+
+static int check_buf(dx_ctx *ctx, const void *p, const char *what)
+{ if (p == NULL) return dx_fail(ctx,DX_E_ARG,"%s is NULL",what);
+  if (((uintptr_t) p & 15) != 0)
+    return dx_fail(ctx,DX_E_ARG,"%s must be 16-byte aligned device memory",what);
+  return DX_OK;
+}
+
+// copy [at, at+len) of a device image to the host (synchronous)
+static int peek(dx_ctx *ctx, const uint8_t *d, size_t n, size_t at, size_t len, std::vector<uint8_t> &h)
+{ if (at > n) at = n;
+  if (at + len > n) len = n - at;
+  h.resize(len);
+  if (len == 0) return DX_OK;
+  DX_CUDA(ctx,cudaMemcpyAsync(h.data(),d+at,len,cudaMemcpyDeviceToHost,ctx->stream));
+  DX_CUDA(ctx,cudaStreamSynchronize(ctx->stream));
+  return DX_OK;
+}
+
+template <class T>
+static int download(dx_ctx *ctx, const T *d, size_t count, std::vector<T> &h)
+{ h.resize(count);
+  if (count == 0) return DX_OK;
+  DX_CUDA(ctx,cudaMemcpyAsync(h.data(),d,count*sizeof(T),cudaMemcpyDeviceToHost,ctx->stream));
+  DX_CUDA(ctx,cudaStreamSynchronize(ctx->stream));
+  return DX_OK;
+}
+
+template <class T>
+static int upload(dx_ctx *ctx, T *d, const T *h, size_t count)
+{ if (count == 0) return DX_OK;
+  DX_CUDA(ctx,cudaMemcpyAsync(d,h,count*sizeof(T),cudaMemcpyHostToDevice,ctx->stream));
+  DX_CUDA(ctx,cudaStreamSynchronize(ctx->stream));     // h may be a temporary
+  return DX_OK;
+}
+
+static int ndigits(int32_t v)          // characters printf("%d") produces
+{ int n = (v < 0);
+  uint32_t u = (v < 0) ? (uint32_t) (-(int64_t) v) : (uint32_t) v;
+  do { n++; u /= 10; } while (u);
+  return n;
+}
+
+static int ensure_io(dx_ctx *ctx, uint8_t **buf, size_t *cap, size_t need)
+{ need = round_up(need + 64,256);
+  if (*cap >= need) return DX_OK;
+  if (*buf) cudaFree(*buf);
+  *buf = NULL; *cap = 0;
+  DX_CUDA(ctx,cudaMalloc((void **) buf,need));
+  *cap = need;
+  return DX_OK;
+}
+
+// ================================================================================================
+//  Chain of entries in a compressed image (.dexta / .dexar / .dexqv)
+//
+//  None of the three formats stores entry lengths; the reference finds entry k+1 only by
+//  finishing entry k.  Here: every offset whose bytes look like an entry's fixed fields is a
+//  CANDIDATE (dx_frame.cu); all candidates are walked in parallel to find where they would
+//  end; then the host accepts a candidate only if the previous accepted entry ends exactly at
+//  its well-delta bytes.  Exactness never depends on the candidate filter: a true entry the
+//  filter missed is walked on its own (slow path), a false candidate is never reached.
+// ================================================================================================
+
+struct ChainEntry
+{ int64_t start;        // first well-delta byte
+  int64_t q;            // first field byte
+  int64_t end;          // first byte after the entry
+  int64_t cand;         // candidate index, or -1 when found by the slow path
+  int32_t well;         // absolute well number
+  uint8_t field[16];
+};
+
+typedef int (*WalkOne)(dx_ctx *ctx, void *user, int64_t q, int64_t *end, int64_t *slot);
+
+static int resolve_chain(dx_ctx *ctx, const uint8_t *d_in, size_t n, size_t first, int fieldbytes,
+                         const std::vector<int64_t> &q, const std::vector<int64_t> &end,
+                         const std::vector<CandInfo> &info, WalkOne walk_one, void *user,
+                         std::vector<ChainEntry> &chain)
+{ int64_t cur = (int64_t) first;
+  int32_t well = 0;
+  size_t  i = 0;
+  const size_t nc = q.size();
+  chain.clear();
+  std::vector<uint8_t> win;
+  while (cur < (int64_t) n)
+    { while (i < nc && q[i] - 1 < cur) i++;                  // candidates inside accepted entries
+      // the entry at cur has its fields right after the run of 0xff bytes that starts at cur
+      // and the one byte that ends it: a candidate is that entry iff its q is exactly there
+      while (i < nc && info[i].last == 0xff && q[i] - 1 - cur <= info[i].ffrun)
+        i++;                                                  // candidate inside the 0xff run
+      bool ok = false;
+      if (i < nc && end[i] >= 0)
+        { const int64_t gap = q[i] - 1 - cur;                // must be all 0xff, then last != 0xff
+          ok = (gap <= info[i].ffrun && info[i].last != 0xff);
+        }
+      ChainEntry ce;
+      if (ok)
+        { ce.start = cur; ce.q = q[i]; ce.end = end[i]; ce.cand = (int64_t) i;
+          well += 255 * (int32_t) (q[i] - 1 - cur) + info[i].last;
+          memcpy(ce.field,info[i].field,16);
+          i++;
+        }
+      else
+        { // slow path: read the header bytes at cur and walk this one entry by itself
+          int64_t p = cur;
+          int32_t add = 0;
+          uint8_t byte = 0xff;
+          while (byte == 0xff)
+            { int rc = peek(ctx,d_in,n,(size_t) p,4096,win);
+              if (rc != DX_OK) return rc;
+              if (win.empty()) return dx_fail(ctx,DX_E_TRUNC,"compressed image ends inside an entry header");
+              size_t k = 0;
+              while (k < win.size() && win[k] == 0xff) { add += 255; k++; }
+              p += (int64_t) k;
+              if (k < win.size()) { byte = win[k]; add += byte; p += 1; }
+            }
+          int rc = peek(ctx,d_in,n,(size_t) p,16,win);
+          if (rc != DX_OK) return rc;
+          if ((int) win.size() < fieldbytes)
+            return dx_fail(ctx,DX_E_TRUNC,"compressed image ends inside an entry header");
+          memset(ce.field,0,16);
+          memcpy(ce.field,win.data(),(size_t) fieldbytes);
+          ce.start = cur; ce.q = p; ce.cand = -1;
+          int64_t e = -1, slot = -1;
+          rc = walk_one(ctx,user,p,&e,&slot);
+          if (rc != DX_OK) return rc;
+          ce.end = e;
+          ce.cand = -2 - slot;                                // slot in the walker's side table
+          well += add;
+        }
+      if (ce.end < 0 || ce.end > (int64_t) n || ce.end <= cur)
+        return dx_fail(ctx,DX_E_TRUNC,"compressed image ends inside an entry (offset %lld)",
+                       (long long) cur);
+      ce.well = well;
+      chain.push_back(ce);
+      cur = ce.end;
+    }
+  return DX_OK;
+}
+
+static inline int32_t le32(const uint8_t *p)
+{ return (int32_t) ((uint32_t) p[0] | ((uint32_t) p[1] << 8) | ((uint32_t) p[2] << 16) | ((uint32_t) p[3] << 24)); }
+
+// ================================================================================================
+//  2-bit codec
+// ================================================================================================
+
+struct PkWalkUser { int fieldbytes; const uint8_t *d_in; size_t n; };
+
+static int pk_walk_one(dx_ctx *ctx, void *user, int64_t q, int64_t *end, int64_t *slot)
+{ PkWalkUser *u = (PkWalkUser *) user;
+  std::vector<uint8_t> f;
+  int rc = peek(ctx,u->d_in,u->n,(size_t) q,8,f);
+  if (rc != DX_OK) return rc;
+  *slot = 0;
+  if (f.size() < 8) { *end = -1; return DX_OK; }
+  const int64_t rlen = (int64_t) le32(f.data()+4) - le32(f.data());
+  *end = (rlen < 0) ? -1 : q + u->fieldbytes + ((rlen + 3) >> 2);
+  return DX_OK;
+}
+
+extern "C" int dx_dexta_dev(dx_ctx *ctx, int kind, const uint8_t *d_text, size_t n,
+                            uint8_t *d_out, size_t cap, size_t *out_len)
+{ if (ctx == NULL || out_len == NULL || (kind != DX_FASTA && kind != DX_ARROW)) return DX_E_ARG;
+  *out_len = 0;
+  ctx->err_line = 0;
+  int rc;
+  if ((rc = check_buf(ctx,d_text,"text")) != DX_OK) return rc;
+  if (d_out == NULL) return dx_fail(ctx,DX_E_ARG,"output is NULL");
+  if (n == 0) return dx_fail(ctx,DX_E_FORMAT,"empty input");
+  cudaSetDevice(ctx->device);
+  dx_arena_reset(ctx);
+
+  // first header line: endian key + prefix (dexta.c:108-129)
+  std::vector<uint8_t> head;
+  if ((rc = peek(ctx,d_text,n,0,100000,head)) != DX_OK) return rc;
+  const uint8_t *nl = (const uint8_t *) memchr(head.data(),'\n',head.size());
+  if (nl == NULL || nl - head.data() > 99998)
+    { ctx->err_line = 1;
+      return dx_fail(ctx,DX_E_TOOLONG,"Line 1: %s line is too long (> 99998 chars)",
+                     kind == DX_FASTA ? "Fasta" : "Arrow");
+    }
+  if (head[0] != '>')
+    { ctx->err_line = 1;
+      return dx_fail(ctx,DX_E_FORMAT,"Line 1: First header in %s file is missing",
+                     kind == DX_FASTA ? "fasta" : "arrow");
+    }
+  const uint8_t *slash = (const uint8_t *) memchr(head.data(),'/',(size_t) (nl - head.data()));
+  if (slash == NULL) return dx_fail(ctx,DX_E_FORMAT,"Header line incorrectly formatted ?");
+  const int32_t plen = (int32_t) (slash - head.data());
+  const size_t  hbytes = 2 + 4 + (size_t) plen;
+
+  int64_t *d_hdr = NULL, nent = 0;
+  if ((rc = dxk_index_positions(ctx,DX_PRED_FASTA_HDR,d_text,n,0,&d_hdr,&nent)) != DX_OK) return rc;
+
+  FaEntries ent;
+  ent.n = nent;
+  const size_t N = (size_t) nent;
+  ent.hdr    = (int64_t *) dx_arena_get(ctx,N*8);
+  ent.seq    = (int64_t *) dx_arena_get(ctx,N*8);
+  ent.region = (int64_t *) dx_arena_get(ctx,N*8);
+  ent.off    = (int64_t *) dx_arena_get(ctx,(N+1)*8);
+  ent.rlen   = (int32_t *) dx_arena_get(ctx,N*4);
+  ent.width  = (int32_t *) dx_arena_get(ctx,N*4);
+  ent.well   = (int32_t *) dx_arena_get(ctx,N*4);
+  ent.beg    = (int32_t *) dx_arena_get(ctx,N*4);
+  ent.end    = (int32_t *) dx_arena_get(ctx,N*4);
+  ent.aux    = (int32_t *) dx_arena_get(ctx,N*8);
+  ent.flag   = (int32_t *) dx_arena_get(ctx,N*4);
+  ent.bytes  = (uint32_t *) dx_arena_get(ctx,N*4);
+  if (!ent.hdr || !ent.seq || !ent.region || !ent.off || !ent.rlen || !ent.width || !ent.well ||
+      !ent.beg || !ent.end || !ent.aux || !ent.flag || !ent.bytes) return DX_E_NOMEM;
+
+  if ((rc = dxk_fa_measure(ctx,kind,d_text,n,d_hdr,ent)) != DX_OK) return rc;
+
+  // entries the device could not settle: non-canonical headers go through the host's sscanf
+  std::vector<int32_t> flag;
+  if ((rc = download(ctx,ent.flag,N,flag)) != DX_OK) return rc;
+  for (size_t e = 0; e < N; e++)
+    { if (flag[e] & 4)
+        return dx_fail(ctx,DX_E_TOOLONG,"%s line is too long (> 99998 chars) or unterminated (entry %zu)",
+                       kind == DX_FASTA ? "Fasta" : "Arrow",e+1);
+      if (!(flag[e] & 1)) continue;
+      int64_t h0 = 0;
+      DX_CUDA(ctx,cudaMemcpyAsync(&h0,ent.hdr+e,8,cudaMemcpyDeviceToHost,ctx->stream));
+      DX_CUDA(ctx,cudaStreamSynchronize(ctx->stream));
+      std::vector<uint8_t> line;
+      if ((rc = peek(ctx,d_text,n,(size_t) h0,100000,line)) != DX_OK) return rc;
+      const uint8_t *e1 = (const uint8_t *) memchr(line.data(),'\n',line.size());
+      if (e1 == NULL) return dx_fail(ctx,DX_E_TOOLONG,"header line too long (entry %zu)",e+1);
+      std::vector<char> txt(line.begin(),line.begin() + (e1 - line.data()) + 1);
+      txt.push_back('\0');
+      char *sl = strchr(txt.data()+1,'/');
+      if (sl == NULL) return dx_fail(ctx,DX_E_FORMAT,"Header line incorrectly formatted ?");
+      int32_t well = 0, beg = 0, en = 0, aux[2] = { 0, 0 };
+      if (kind == DX_FASTA)
+        { int qv = 0;
+          int x = sscanf(sl+1,"%d/%d_%d RQ=0.%d\n",&well,&beg,&en,&qv);      // dexta.c:151
+          if (x < 3) return dx_fail(ctx,DX_E_FORMAT,"Header line incorrectly formatted ?");
+          aux[0] = (x == 3) ? 0 : qv;
+        }
+      else
+        { float snr[4];
+          int x = sscanf(sl+1,"%d/%d_%d SN=%f,%f,%f,%f\n",&well,&beg,&en,snr,snr+1,snr+2,snr+3);
+          if (x != 7) return dx_fail(ctx,DX_E_FORMAT,"Header line incorrectly formatted ?");
+          uint32_t c[4];
+          for (int k = 0; k < 4; k++)                                           // dexar.c:159-163
+            c[k] = (snr[k] > 99.99) ? 9999u : ((uint32_t) (snr[k]*100.) & 0xffffu);
+          aux[0] = (int32_t) (c[0] | (c[1] << 16));
+          aux[1] = (int32_t) (c[2] | (c[3] << 16));
+        }
+      if ((rc = upload(ctx,ent.well+e,&well,1)) != DX_OK) return rc;
+      if ((rc = upload(ctx,ent.beg+e,&beg,1)) != DX_OK) return rc;
+      if ((rc = upload(ctx,ent.end+e,&en,1)) != DX_OK) return rc;
+      if ((rc = upload(ctx,ent.aux+2*e,aux,2)) != DX_OK) return rc;
+    }
+
+  int64_t body = 0;
+  if ((rc = dxk_fa_offsets(ctx,kind,ent,0,&body)) != DX_OK) return rc;
+  if (hbytes + (size_t) body > cap)
+    return dx_fail(ctx,DX_E_CAP,"output needs %zu bytes, buffer has %zu",hbytes + (size_t) body,cap);
+
+  std::vector<uint8_t> fh(hbytes);
+  const uint16_t key = 0x55aa;
+  memcpy(fh.data(),&key,2);
+  memcpy(fh.data()+2,&plen,4);
+  memcpy(fh.data()+6,head.data(),(size_t) plen);
+  if ((rc = upload(ctx,d_out,fh.data(),hbytes)) != DX_OK) return rc;
+  if ((rc = dxk_fa_pack(ctx,kind,d_text,n,ent,0,d_out + hbytes)) != DX_OK) return rc;
+  DX_CUDA(ctx,cudaStreamSynchronize(ctx->stream));
+  *out_len = hbytes + (size_t) body;
+  return DX_OK;
+}
+
+// Everything undexta needs to know about a 2-bit image before the payload is touched.
+struct PkPlan
+{ std::vector<PkDecEntry> ent;
+  std::vector<char>       prefix;
+  size_t                  text_len;
+};
+
+static int plan_undexta(dx_ctx *ctx, int kind, const uint8_t *d_in, size_t n, int width, PkPlan &plan)
+{ int rc;
+  if (width <= 0) return dx_fail(ctx,DX_E_ARG,"line width must be positive");
+  std::vector<uint8_t> head;
+  if ((rc = peek(ctx,d_in,n,0,6,head)) != DX_OK) return rc;
+  if (head.size() < 6) return dx_fail(ctx,DX_E_TRUNC,"System error, read failed!");
+  uint16_t key; memcpy(&key,head.data(),2);
+  int32_t  plen; memcpy(&plen,head.data()+2,4);
+  const bool legacy = (kind == DX_FASTA && (key == 0x33cc || key == 0xcc33));
+  const bool flip   = (key == 0xaa55 || key == 0xcc33);
+  if (!(key == 0x55aa || key == 0xaa55 || legacy))
+    return dx_fail(ctx,DX_E_KEY,"Not a %s file, endian key invalid",kind == DX_FASTA ? ".dexta" : ".dexar");
+  if (flip) plen = (int32_t) __builtin_bswap32((uint32_t) plen);
+  if (plen < 0 || (size_t) plen + 6 > n) return dx_fail(ctx,DX_E_TRUNC,"System error, read failed!");
+  if ((rc = peek(ctx,d_in,n,6,(size_t) plen,head)) != DX_OK) return rc;
+  plan.prefix.assign(head.begin(),head.end());
+  const size_t first = 6 + (size_t) plen;
+  const int fieldbytes = (kind == DX_FASTA) ? 12 : 16;
+
+  struct Hdr { int64_t q; int32_t well, beg, end, aux[2]; };
+  std::vector<Hdr> hdrs;
+
+  if (legacy || flip)
+    { // old 16-bit layout or foreign byte order (undexta.c:140-155, 211-240): rare, so the
+      // header chain is hopped on the host over a copy of the image
+      std::vector<uint8_t> img;
+      if ((rc = peek(ctx,d_in,n,0,n,img)) != DX_OK) return rc;
+      size_t at = first;
+      int32_t well = 0;
+      while (at < n)
+        { uint8_t b = img[at++];
+          while (b == 255)
+            { well += 255;
+              if (at >= n) return dx_fail(ctx,DX_E_TRUNC,"System error, read failed!");
+              b = img[at++];
+            }
+          well += b;
+          Hdr h; h.well = well; h.aux[0] = h.aux[1] = 0;
+          if (legacy)
+            { if (at + 6 > n) return dx_fail(ctx,DX_E_TRUNC,"System error, read failed!");
+              uint16_t v[3]; memcpy(v,img.data()+at,6);
+              if (flip) for (int k = 0; k < 3; k++) v[k] = (uint16_t) ((v[k] >> 8) | (v[k] << 8));
+              h.beg = v[0]; h.end = v[1]; h.aux[0] = v[2];
+              at += 6;
+            }
+          else
+            { if (at + (size_t) fieldbytes > n) return dx_fail(ctx,DX_E_TRUNC,"System error, read failed!");
+              uint32_t v[2]; memcpy(v,img.data()+at,8);
+              h.beg = (int32_t) __builtin_bswap32(v[0]); h.end = (int32_t) __builtin_bswap32(v[1]);
+              if (kind == DX_FASTA)
+                { uint32_t qv; memcpy(&qv,img.data()+at+8,4); h.aux[0] = (int32_t) __builtin_bswap32(qv); }
+              else
+                { uint16_t c[4]; memcpy(c,img.data()+at+8,8);
+                  for (int k = 0; k < 4; k++) c[k] = (uint16_t) ((c[k] >> 8) | (c[k] << 8));
+                  h.aux[0] = (int32_t) (c[0] | ((uint32_t) c[1] << 16));
+                  h.aux[1] = (int32_t) (c[2] | ((uint32_t) c[3] << 16));
+                }
+              at += (size_t) fieldbytes;
+            }
+          h.q = (int64_t) at;                         // here: first payload byte
+          const int64_t rlen = (int64_t) h.end - h.beg;
+          if (rlen < 0) return dx_fail(ctx,DX_E_FORMAT,"negative read length in entry header");
+          at += (size_t) ((rlen + 3) >> 2);
+          if (at > n) return dx_fail(ctx,DX_E_TRUNC,"System error, read failed!");
+          hdrs.push_back(h);
+        }
+    }
+  else
+    { int64_t *d_q = NULL, nc = 0;
+      if ((rc = dxk_index_positions(ctx,kind == DX_FASTA ? DX_PRED_QVCAND : DX_PRED_ARCAND,
+                                    d_in,n,first + 1,&d_q,&nc)) != DX_OK) return rc;
+      int64_t  *d_end  = (int64_t *) dx_arena_get(ctx,(size_t) nc*8);
+      CandInfo *d_info = (CandInfo *) dx_arena_get(ctx,(size_t) nc*sizeof(CandInfo));
+      if (!d_end || !d_info) return DX_E_NOMEM;
+      if ((rc = dxk_pk_walk(ctx,fieldbytes,d_in,n,d_q,nc,d_end)) != DX_OK) return rc;
+      if ((rc = dxk_cand_context(ctx,d_in,n,first,d_q,nc,fieldbytes,d_info)) != DX_OK) return rc;
+      std::vector<int64_t> q, end;
+      std::vector<CandInfo> info;
+      if ((rc = download(ctx,d_q,(size_t) nc,q)) != DX_OK) return rc;
+      if ((rc = download(ctx,d_end,(size_t) nc,end)) != DX_OK) return rc;
+      if ((rc = download(ctx,d_info,(size_t) nc,info)) != DX_OK) return rc;
+      PkWalkUser user = { fieldbytes, d_in, n };
+      std::vector<ChainEntry> chain;
+      if ((rc = resolve_chain(ctx,d_in,n,first,fieldbytes,q,end,info,pk_walk_one,&user,chain)) != DX_OK)
+        return rc;
+      hdrs.reserve(chain.size());
+      for (const ChainEntry &c : chain)
+        { Hdr h; h.well = c.well;
+          h.beg = le32(c.field); h.end = le32(c.field+4);
+          h.aux[0] = le32(c.field+8);
+          h.aux[1] = (kind == DX_ARROW) ? le32(c.field+12) : 0;
+          h.q = c.q + fieldbytes;
+          hdrs.push_back(h);
+        }
+    }
+
+  // output layout: "%s/%d/%d_%d RQ=0.%d\n" + wrapped sequence (undexta.c:242-270)
+  size_t at = 0;
+  plan.ent.resize(hdrs.size());
+  for (size_t i = 0; i < hdrs.size(); i++)
+    { const Hdr &h = hdrs[i];
+      PkDecEntry &d = plan.ent[i];
+      d.bin_off = h.q; d.out_off = (int64_t) at;
+      d.well = h.well; d.beg = h.beg; d.end = h.end; d.aux[0] = h.aux[0]; d.aux[1] = h.aux[1];
+      size_t hl = plan.prefix.size() + 1 + ndigits(h.well) + 1 + ndigits(h.beg) + 1 + ndigits(h.end);
+      if (kind == DX_FASTA)
+        hl += 6 + ndigits(h.aux[0]) + 1;
+      else
+        { hl += 4;
+          for (int k = 0; k < 4; k++)
+            { const uint32_t c = ((uint32_t) h.aux[k >> 1] >> (16*(k & 1))) & 0xffffu;
+              hl += ndigits((int32_t) (c / 100)) + 3 + (k < 3);
+            }
+          hl += 1;
+        }
+      at += hl;
+      d.text_off = (int64_t) at;
+      const int64_t rlen = (int64_t) h.end - h.beg;
+      if (rlen > 0)
+        at += (size_t) (rlen + (rlen + width - 1) / width);
+    }
+  plan.text_len = at;
+  return DX_OK;
+}
+
+extern "C" int dx_undexta_dev(dx_ctx *ctx, int kind, const uint8_t *d_in, size_t n, int width,
+                              int upper, uint8_t *d_out, size_t cap, size_t *out_len)
+{ if (ctx == NULL || out_len == NULL || (kind != DX_FASTA && kind != DX_ARROW)) return DX_E_ARG;
+  *out_len = 0;
+  int rc;
+  if ((rc = check_buf(ctx,d_in,"image")) != DX_OK) return rc;
+  cudaSetDevice(ctx->device);
+  dx_arena_reset(ctx);
+  PkPlan plan;
+  if ((rc = plan_undexta(ctx,kind,d_in,n,width,plan)) != DX_OK) return rc;
+  if (plan.text_len > cap)
+    return dx_fail(ctx,DX_E_CAP,"output needs %zu bytes, buffer has %zu",plan.text_len,cap);
+  if (d_out == NULL && plan.text_len > 0) return dx_fail(ctx,DX_E_ARG,"output is NULL");
+  const size_t N = plan.ent.size();
+  PkDecEntry *d_ent = (PkDecEntry *) dx_arena_get(ctx,N*sizeof(PkDecEntry));
+  char *d_prefix = (char *) dx_arena_get(ctx,plan.prefix.size()+1);
+  if (!d_ent || !d_prefix) return DX_E_NOMEM;
+  if ((rc = upload(ctx,d_ent,plan.ent.data(),N)) != DX_OK) return rc;
+  if ((rc = upload(ctx,d_prefix,plan.prefix.data(),plan.prefix.size())) != DX_OK) return rc;
+  if ((rc = dxk_unpack(ctx,kind,upper,width,d_in,d_ent,(int64_t) N,d_prefix,(int) plan.prefix.size(),
+                       d_out)) != DX_OK) return rc;
+  DX_CUDA(ctx,cudaStreamSynchronize(ctx->stream));
+  *out_len = plan.text_len;
+  return DX_OK;
+}
+
+extern "C" int dx_compress_reads_dev(dx_ctx *ctx, int kind, const uint8_t *d_src,
+                                     const int64_t *d_src_off, const int32_t *d_len, int64_t nreads,
+                                     uint8_t *d_dst, const int64_t *d_dst_off)
+{ if (ctx == NULL || nreads < 0) return DX_E_ARG;
+  cudaSetDevice(ctx->device);
+  return dxk_compress_reads(ctx,kind,d_src,d_src_off,d_len,nreads,d_dst,d_dst_off);
+}
+
+extern "C" int dx_uncompress_reads_dev(dx_ctx *ctx, int kind, int upper, const uint8_t *d_src,
+                                       const int64_t *d_src_off, const int32_t *d_len,
+                                       int64_t nreads, uint8_t *d_dst, const int64_t *d_dst_off)
+{ if (ctx == NULL || nreads < 0) return DX_E_ARG;
+  cudaSetDevice(ctx->device);
+  return dxk_uncompress_reads(ctx,kind,upper,d_src,d_src_off,d_len,nreads,d_dst,d_dst_off);
+}
+
+// ================================================================================================
+//  QV coder: scan
+// ================================================================================================
+
+static int qv_frame(dx_ctx *ctx, const uint8_t *d_text, size_t n, uint64_t *totchar)
+{ int rc;
+  ctx->qv_text = NULL; ctx->qv_n = 0; ctx->qv_ent.n = 0;
+  *totchar = 0;
+  if (n == 0) { ctx->qv_text = d_text; return DX_OK; }
+
+  int64_t *d_nl = NULL, nlines = 0;
+  if ((rc = dxk_index_positions(ctx,DX_PRED_NEWLINE,d_text,n,0,&d_nl,&nlines)) != DX_OK) return rc;
+  int64_t last = -1;
+  if (nlines > 0)
+    { DX_CUDA(ctx,cudaMemcpyAsync(&last,d_nl+nlines-1,8,cudaMemcpyDeviceToHost,ctx->stream));
+      DX_CUDA(ctx,cudaStreamSynchronize(ctx->stream));
+    }
+  if (last != (int64_t) n - 1)
+    { ctx->err_line = nlines + 1;
+      return dx_fail(ctx,DX_E_FORMAT,"Line %lld: Last line does not end with a newline !",
+                     (long long) nlines + 1);
+    }
+  if (nlines % 6 != 0)
+    { ctx->err_line = nlines + 1;
+      return dx_fail(ctx,DX_E_FORMAT,"Line %lld: incomplete last entry of .quiv file",
+                     (long long) nlines + 1);
+    }
+  const int64_t nent = nlines / 6;
+  const size_t need = round_up((size_t) nent*8,256)*2 + round_up((size_t) nent*4,256)*6 + 256;
+  if (ctx->qv_store_cap < need)
+    { if (ctx->qv_store) cudaFree(ctx->qv_store);
+      ctx->qv_store = NULL; ctx->qv_store_cap = 0;
+      DX_CUDA(ctx,cudaMalloc((void **) &ctx->qv_store,need));
+      ctx->qv_store_cap = need;
+    }
+  QvEntries ent;
+  uint8_t *p = ctx->qv_store;
+  ent.n = nent;
+  ent.hdr   = (int64_t *) p; p += round_up((size_t) nent*8,256);
+  ent.line0 = (int64_t *) p; p += round_up((size_t) nent*8,256);
+  ent.rlen  = (int32_t *) p; p += round_up((size_t) nent*4,256);
+  ent.well  = (int32_t *) p; p += round_up((size_t) nent*4,256);
+  ent.beg   = (int32_t *) p; p += round_up((size_t) nent*4,256);
+  ent.end   = (int32_t *) p; p += round_up((size_t) nent*4,256);
+  ent.qv    = (int32_t *) p; p += round_up((size_t) nent*4,256);
+  ent.flag  = (int32_t *) p;
+
+  int32_t err[2];
+  if ((rc = dxk_qv_entries(ctx,d_text,n,d_nl,nlines,ent,err,totchar)) != DX_OK) return rc;
+  if (err[0] != 0)
+    { ctx->err_line = err[1];
+      if (err[0] == 5)
+        return dx_fail(ctx,DX_E_LINELEN,"Line %d: Lines for an entry are not the same length",err[1]);
+      if (err[0] == 6)
+        return dx_fail(ctx,DX_E_TOOLONG,"Line %d: entry longer than 2^24 symbols",err[1]);
+      return dx_fail(ctx,DX_E_FORMAT,"Line %d: Header in quiva file is missing",err[1]);
+    }
+
+  // headers the device parser did not recognise as canonical: the host's sscanf decides
+  std::vector<int32_t> flag;
+  if ((rc = download(ctx,ent.flag,(size_t) nent,flag)) != DX_OK) return rc;
+  for (int64_t e = 0; e < nent; e++)
+    { if (!flag[e]) continue;
+      int64_t h0 = 0;
+      DX_CUDA(ctx,cudaMemcpyAsync(&h0,ent.hdr+e,8,cudaMemcpyDeviceToHost,ctx->stream));
+      DX_CUDA(ctx,cudaStreamSynchronize(ctx->stream));
+      std::vector<uint8_t> line;
+      if ((rc = peek(ctx,d_text,n,(size_t) h0,4096,line)) != DX_OK) return rc;
+      std::vector<char> txt(line.begin(),line.end());
+      txt.push_back('\0');
+      char *e1 = (char *) memchr(txt.data(),'\n',line.size());
+      if (e1 != NULL) e1[1] = '\0';
+      char *sl = strchr(txt.data()+1,'/');
+      int well, beg, en, qv;
+      if (sl == NULL || sscanf(sl+1,"%d/%d_%d RQ=0.%d\n",&well,&beg,&en,&qv) != 4)   // QV.c:958-968
+        { ctx->err_line = 6*e + 1;
+          return dx_fail(ctx,DX_E_FORMAT,"Line %lld: Header line incorrectly formatted ?",
+                         (long long) (6*e + 1));
+        }
+      if ((rc = upload(ctx,ent.well+e,&well,1)) != DX_OK) return rc;
+      if ((rc = upload(ctx,ent.beg+e,&beg,1)) != DX_OK) return rc;
+      if ((rc = upload(ctx,ent.end+e,&en,1)) != DX_OK) return rc;
+      if ((rc = upload(ctx,ent.qv+e,&qv,1)) != DX_OK) return rc;
+    }
+  ctx->qv_text = d_text; ctx->qv_n = n; ctx->qv_ent = ent;
+  return DX_OK;
+}
+
+extern "C" int dx_qv_scan_dev(dx_ctx *ctx, const uint8_t *d_text, size_t n, const dx_qv_carry *carry,
+                              dx_qv_stats *stats)
+{ if (ctx == NULL || stats == NULL) return DX_E_ARG;
+  int rc;
+  ctx->err_line = 0;
+  if ((rc = check_buf(ctx,d_text,"text")) != DX_OK) return rc;
+  cudaSetDevice(ctx->device);
+  dx_arena_reset(ctx);
+  dx_qv_carry zero;
+  if (carry == NULL)
+    { memset(&zero,0,sizeof(zero));
+      zero.delchar = zero.subchar = -1;
+      carry = &zero;
+    }
+  memset(stats,0,sizeof(*stats));
+  uint64_t tot = 0;
+  if ((rc = qv_frame(ctx,d_text,n,&tot)) != DX_OK) return rc;
+  QvProbe probe;
+  if ((rc = dxk_qv_probe(ctx,d_text,ctx->qv_ent,carry,&probe)) != DX_OK) return rc;
+  if ((rc = dxk_qv_hist(ctx,d_text,ctx->qv_ent,&probe,&stats->hist[0][0],NULL)) != DX_OK) return rc;
+
+  // the kernel does not count the run characters themselves: they are what is left over
+  if (probe.delchar >= 0)
+    { uint64_t s = 0;
+      for (int k = 0; k < 256; k++) if (k != probe.delchar) s += stats->hist[0][k];
+      stats->hist[0][probe.delchar] = tot - s;
+    }
+  if (probe.subchar >= 0)
+    { uint64_t s = 0;
+      for (int k = 0; k < 256; k++) if (k != probe.subchar) s += stats->hist[3][k];
+      stats->hist[3][probe.subchar] = tot - s;
+    }
+  stats->totchar  = tot;
+  stats->nentries = ctx->qv_ent.n;
+  stats->delchar  = probe.delchar;
+  stats->subchar  = probe.subchar;
+  memcpy(stats->sub_prefix,probe.sub_prefix,sizeof(stats->sub_prefix));
+  return DX_OK;
+}
+
+// ================================================================================================
+//  QV coder: encode
+// ================================================================================================
+
+static void pack_tables(const dx_qv_coding *c, QvEncTables *t)
+{ for (int k = 0; k < 6; k++)
+    { const dx_scheme &s = c->tab[k];
+      const bool isrun = (k == 1 || k == 5);
+      for (int x = 0; x < 256; x++)
+        { const bool esc = (isrun || s.type == 2) && s.lens[x] > 0 &&
+                           s.bits[x] == s.bits[255] && s.lens[x] == s.lens[255];   // QV.c:432,486
+          t->t[k][x] = (s.bits[x] & 0xffffu) | ((uint32_t) (s.lens[x] & 0x1f) << 16) |
+                       ((uint32_t) esc << 21);
+        }
+    }
+}
+
+extern "C" int dx_qv_encode_dev(dx_ctx *ctx, const uint8_t *d_text, size_t n,
+                                const dx_qv_coding *coding, int lossy, int32_t lwell_in,
+                                uint8_t *d_out, size_t cap, size_t *out_len, int32_t *last_well,
+                                int64_t *h_entry_off, int64_t max_entries)
+{ if (ctx == NULL || coding == NULL || out_len == NULL) return DX_E_ARG;
+  int rc;
+  *out_len = 0;
+  if ((rc = check_buf(ctx,d_text,"text")) != DX_OK) return rc;
+  cudaSetDevice(ctx->device);
+  dx_arena_reset(ctx);
+  if (ctx->qv_text != d_text || ctx->qv_n != n)
+    { uint64_t tot;
+      if ((rc = qv_frame(ctx,d_text,n,&tot)) != DX_OK) return rc;
+    }
+  QvEncTables tab;
+  pack_tables(coding,&tab);
+  return dxk_qv_encode(ctx,d_text,n,ctx->qv_ent,&tab,coding->delchar,coding->subchar,lossy,lwell_in,
+                       d_out,cap,out_len,last_well,h_entry_off,max_entries);
+}
+
+extern "C" int dx_dexqv_dev(dx_ctx *ctx, const uint8_t *d_text, size_t n, int lossy,
+                            uint8_t *d_out, size_t cap, size_t *out_len)
+{ if (ctx == NULL || out_len == NULL) return DX_E_ARG;
+  int rc;
+  *out_len = 0;
+  dx_qv_stats  *st = (dx_qv_stats *) malloc(sizeof(dx_qv_stats));
+  dx_qv_coding *cd = (dx_qv_coding *) malloc(sizeof(dx_qv_coding));
+  std::vector<uint8_t> head, fh(2 + 16384 + 100000);
+  size_t hlen = 0, body = 0;
+  if (st == NULL || cd == NULL) { rc = DX_E_NOMEM; goto done; }
+  if ((rc = dx_qv_scan_dev(ctx,d_text,n,NULL,st)) != DX_OK) goto done;
+  if (st->nentries == 0) { rc = dx_fail(ctx,DX_E_FORMAT,"no entries in .quiva input"); goto done; }
+  if ((rc = dx_qv_make_coding(st,lossy,cd)) != DX_OK)
+    { dx_fail(ctx,rc,"a QV stream has fewer than two distinct symbols: cannot build a code");
+      goto done;
+    }
+  // prefix := first header up to the first '/' after the '@' (dexqv.c:88-103)
+  if ((rc = peek(ctx,d_text,n,0,100000,head)) != DX_OK) goto done;
+  { const uint8_t *sl = (const uint8_t *) memchr(head.data()+1,'/',head.size()-1);
+    if (sl == NULL) { rc = dx_fail(ctx,DX_E_FORMAT,"Header line incorrectly formatted ?"); goto done; }
+    const uint16_t key = 0x55aa;                                         // dexqv.c:105-106
+    memcpy(fh.data(),&key,2);
+    if ((rc = dx_qv_write_coding(cd,(const char *) head.data(),(int) (sl - head.data()),
+                                 fh.data()+2,fh.size()-2,&hlen)) != DX_OK) goto done;
+    hlen += 2;
+  }
+  if (hlen > cap) { rc = dx_fail(ctx,DX_E_CAP,"output buffer too small"); goto done; }
+  if ((rc = upload(ctx,d_out,fh.data(),hlen)) != DX_OK) goto done;
+  if ((rc = dx_qv_encode_dev(ctx,d_text,n,cd,lossy,0,d_out+hlen,cap-hlen,&body,NULL,NULL,0)) != DX_OK)
+    goto done;
+  if ((rc = dx_sync(ctx)) != DX_OK) goto done;
+  *out_len = hlen + body;
+done:
+  free(st); free(cd);
+  return rc;
+}
+
+// ================================================================================================
+//  QV coder: decode
+// ================================================================================================
+
+static void build_dec_tables(const dx_qv_coding *c, QvDecTables *t)
+{ memset(t,0,sizeof(*t));
+  for (int k = 0; k < 6; k++)
+    { const dx_scheme &s = c->tab[k];
+      t->type[k] = s.type;
+      for (int i = 0; i < 256; i++)                       // ascending: 255 wins ties (QV.c:365-372)
+        { t->lens[k][i] = (uint8_t) s.lens[i];
+          if (s.lens[i] > 0 && s.lens[i] <= 16)
+            { const uint32_t base = (s.bits[i] << (16 - s.lens[i])) & 0xffffu;
+              const uint32_t span = 1u << (16 - s.lens[i]);
+              memset(&t->look[k][base],i,span);
+            }
+        }
+    }
+}
+
+struct QvPlan
+{ std::vector<QvDecEntry> ent;
+  int64_t     *d_soff;        // [count][6] device
+  QvDecTables *d_tab;
+  char        *d_prefix;
+  int          plen;
+  dx_qv_coding coding;
+  size_t       text_len;
+};
+
+struct QvWalkUser
+{ const uint8_t *d_in; size_t n; const QvDecTables *d_tab; const dx_qv_coding *coding;
+  std::vector<int64_t> side;           // 6 stream offsets per slow-path entry
+};
+
+static int qv_walk_one(dx_ctx *ctx, void *user, int64_t q, int64_t *end, int64_t *slot)
+{ QvWalkUser *u = (QvWalkUser *) user;
+  int rc;
+  std::vector<uint8_t> f;
+  if ((rc = peek(ctx,u->d_in,u->n,(size_t) q,12,f)) != DX_OK) return rc;
+  *slot = (int64_t) (u->side.size() / 6);
+  if (f.size() < 12) { *end = -1; return DX_OK; }
+  const int32_t rlen = le32(f.data()+4) - le32(f.data());
+  if (rlen < 0 || rlen >= (1 << 24)) { *end = -1; return DX_OK; }
+  int64_t *d_start = (int64_t *) dx_arena_get(ctx,8);
+  int32_t *d_rlen  = (int32_t *) dx_arena_get(ctx,4);
+  int64_t *d_soff  = (int64_t *) dx_arena_get(ctx,48);
+  int32_t *d_stat  = (int32_t *) dx_arena_get(ctx,4);
+  if (!d_start || !d_rlen || !d_soff || !d_stat) return DX_E_NOMEM;
+  const int64_t start = q + 12;
+  if ((rc = upload(ctx,d_start,&start,1)) != DX_OK) return rc;
+  if ((rc = upload(ctx,d_rlen,&rlen,1)) != DX_OK) return rc;
+  if ((rc = dxk_qv_walk(ctx,u->d_in,u->n,u->d_tab,u->coding->delchar,u->coding->subchar,
+                        u->coding->flip,d_start,d_rlen,1,d_soff,d_stat)) != DX_OK) return rc;
+  std::vector<int64_t> so; std::vector<int32_t> stt;
+  if ((rc = download(ctx,d_soff,6,so)) != DX_OK) return rc;
+  if ((rc = download(ctx,d_stat,1,stt)) != DX_OK) return rc;
+  *end = stt[0] ? -1 : so[5];
+  u->side.insert(u->side.end(),so.begin(),so.end());
+  return DX_OK;
+}
+
+static int plan_undexqv(dx_ctx *ctx, const uint8_t *d_in, size_t n, const int64_t *h_entry_off,
+                        int64_t nentries, QvPlan &plan)
+{ int rc;
+  std::vector<uint8_t> head;
+  if ((rc = peek(ctx,d_in,n,0,2 + 16384 + 100000,head)) != DX_OK) return rc;
+  if (head.size() < 2) return dx_fail(ctx,DX_E_TRUNC,"System error, read failed!");
+  uint16_t key; memcpy(&key,head.data(),2);
+  if (!(key == 0x55aa || key == 0xaa55))
+    return dx_fail(ctx,DX_E_KEY,"old-format .dexqv (16-bit entry fields, undexqv.c:107-110) is not supported");
+  std::vector<char> prefix(100001);
+  size_t used = 0;
+  if ((rc = dx_qv_read_coding(head.data()+2,head.size()-2,&plan.coding,prefix.data(),
+                              (int) prefix.size(),&used)) != DX_OK)
+    return dx_fail(ctx,rc,"Could not read the coding header (Read_QVcoding)");
+  if (plan.coding.flip)
+    return dx_fail(ctx,DX_E_KEY,"foreign-endian .dexqv is not supported");
+  const size_t first = 2 + used;
+  plan.plen = (int) strlen(prefix.data());
+
+  QvDecTables *h_tab = (QvDecTables *) malloc(sizeof(QvDecTables));
+  if (h_tab == NULL) return DX_E_NOMEM;
+  build_dec_tables(&plan.coding,h_tab);
+  plan.d_tab    = (QvDecTables *) dx_arena_get(ctx,sizeof(QvDecTables));
+  plan.d_prefix = (char *) dx_arena_get(ctx,(size_t) plan.plen + 1);
+  if (!plan.d_tab || !plan.d_prefix) { free(h_tab); return DX_E_NOMEM; }
+  rc = upload(ctx,plan.d_tab,h_tab,1);
+  free(h_tab);
+  if (rc != DX_OK) return rc;
+  if ((rc = upload(ctx,plan.d_prefix,prefix.data(),(size_t) plan.plen)) != DX_OK) return rc;
+
+  struct Hdr { int32_t well, beg, end, qv; };
+  std::vector<Hdr> hdrs;
+  const dx_qv_coding &cd = plan.coding;
+
+  if (h_entry_off != NULL)
+    { // entry starts are known (our encoder's index, or Dazzler .idx coff, DB.c:2598)
+      const size_t N = (size_t) nentries;
+      int64_t  *d_start = (int64_t *) dx_arena_get(ctx,N*8);
+      int64_t  *d_q     = (int64_t *) dx_arena_get(ctx,N*8);
+      int64_t  *d_fs    = (int64_t *) dx_arena_get(ctx,N*8);
+      int32_t  *d_rlen  = (int32_t *) dx_arena_get(ctx,N*4);
+      int32_t  *d_stat  = (int32_t *) dx_arena_get(ctx,N*4);
+      CandInfo *d_info  = (CandInfo *) dx_arena_get(ctx,N*sizeof(CandInfo));
+      plan.d_soff       = (int64_t *) dx_arena_get(ctx,N*48);
+      if (!d_start || !d_q || !d_fs || !d_rlen || !d_stat || !d_info || !plan.d_soff) return DX_E_NOMEM;
+      if ((rc = upload(ctx,d_start,h_entry_off,N)) != DX_OK) return rc;
+      if ((rc = dxk_skip_ff(ctx,d_in,n,d_start,(int64_t) N,d_q)) != DX_OK) return rc;
+      if ((rc = dxk_field_rlen(ctx,d_in,d_q,(int64_t) N,d_rlen)) != DX_OK) return rc;
+      if ((rc = dxk_cand_context(ctx,d_in,n,first,d_q,(int64_t) N,12,d_info)) != DX_OK) return rc;
+      std::vector<int64_t> q;
+      if ((rc = download(ctx,d_q,N,q)) != DX_OK) return rc;
+      for (size_t i = 0; i < N; i++) q[i] += 12;
+      if ((rc = upload(ctx,d_fs,q.data(),N)) != DX_OK) return rc;
+      if ((rc = dxk_qv_walk(ctx,d_in,n,plan.d_tab,cd.delchar,cd.subchar,cd.flip,d_fs,d_rlen,
+                            (int64_t) N,plan.d_soff,d_stat)) != DX_OK) return rc;
+      std::vector<CandInfo> info;
+      std::vector<int32_t> stat;
+      if ((rc = download(ctx,d_info,N,info)) != DX_OK) return rc;
+      if ((rc = download(ctx,d_stat,N,stat)) != DX_OK) return rc;
+      int32_t well = 0;
+      hdrs.resize(N);
+      for (size_t i = 0; i < N; i++)
+        { if (stat[i]) return dx_fail(ctx,DX_E_TRUNC,"Could not read more bits (Decode), entry %zu",i+1);
+          well += 255 * (int32_t) (q[i] - 13 - h_entry_off[i]) + info[i].last;
+          hdrs[i].well = well;
+          hdrs[i].beg = le32(info[i].field); hdrs[i].end = le32(info[i].field+4);
+          hdrs[i].qv  = le32(info[i].field+8);
+        }
+    }
+  else
+    { int64_t *d_q = NULL, nc = 0;
+      if ((rc = dxk_index_positions(ctx,DX_PRED_QVCAND,d_in,n,first + 1,&d_q,&nc)) != DX_OK) return rc;
+      const size_t N = (size_t) nc;
+      int64_t  *d_fs    = (int64_t *) dx_arena_get(ctx,N*8);
+      int32_t  *d_rlen  = (int32_t *) dx_arena_get(ctx,N*4);
+      int32_t  *d_stat  = (int32_t *) dx_arena_get(ctx,N*4);
+      int64_t  *d_soffc = (int64_t *) dx_arena_get(ctx,N*48);
+      CandInfo *d_info  = (CandInfo *) dx_arena_get(ctx,N*sizeof(CandInfo));
+      if (!d_fs || !d_rlen || !d_stat || !d_soffc || !d_info) return DX_E_NOMEM;
+      if ((rc = dxk_field_rlen(ctx,d_in,d_q,nc,d_rlen)) != DX_OK) return rc;
+      if ((rc = dxk_cand_context(ctx,d_in,n,first,d_q,nc,12,d_info)) != DX_OK) return rc;
+      std::vector<int64_t> q, fs;
+      if ((rc = download(ctx,d_q,N,q)) != DX_OK) return rc;
+      fs.resize(N);
+      for (size_t i = 0; i < N; i++) fs[i] = q[i] + 12;
+      if ((rc = upload(ctx,d_fs,fs.data(),N)) != DX_OK) return rc;
+      if ((rc = dxk_qv_walk(ctx,d_in,n,plan.d_tab,cd.delchar,cd.subchar,cd.flip,d_fs,d_rlen,nc,
+                            d_soffc,d_stat)) != DX_OK) return rc;
+      std::vector<int64_t> soff;
+      std::vector<int32_t> stat;
+      std::vector<CandInfo> info;
+      if ((rc = download(ctx,d_soffc,N*6,soff)) != DX_OK) return rc;
+      if ((rc = download(ctx,d_stat,N,stat)) != DX_OK) return rc;
+      if ((rc = download(ctx,d_info,N,info)) != DX_OK) return rc;
+      std::vector<int64_t> end(N);
+      for (size_t i = 0; i < N; i++) end[i] = stat[i] ? -1 : soff[6*i+5];
+      QvWalkUser user = { d_in, n, plan.d_tab, &plan.coding, {} };
+      std::vector<ChainEntry> chain;
+      if ((rc = resolve_chain(ctx,d_in,n,first,12,q,end,info,qv_walk_one,&user,chain)) != DX_OK)
+        return rc;
+      const size_t M = chain.size();
+      std::vector<int64_t> so(M*6);
+      hdrs.resize(M);
+      for (size_t i = 0; i < M; i++)
+        { const ChainEntry &c = chain[i];
+          const int64_t *src = (c.cand >= 0) ? &soff[6*(size_t) c.cand]
+                                             : &user.side[6*(size_t) (-2 - c.cand)];
+          memcpy(&so[6*i],src,48);
+          hdrs[i].well = c.well;
+          hdrs[i].beg = le32(c.field); hdrs[i].end = le32(c.field+4); hdrs[i].qv = le32(c.field+8);
+        }
+      plan.d_soff = (int64_t *) dx_arena_get(ctx,M*48);
+      if (!plan.d_soff) return DX_E_NOMEM;
+      if ((rc = upload(ctx,plan.d_soff,so.data(),M*6)) != DX_OK) return rc;
+    }
+
+  // output layout (undexqv.c:182, 206-207)
+  size_t at = 0;
+  plan.ent.resize(hdrs.size());
+  for (size_t i = 0; i < hdrs.size(); i++)
+    { QvDecEntry &d = plan.ent[i];
+      const Hdr &h = hdrs[i];
+      d.well = h.well; d.beg = h.beg; d.end = h.end; d.qv = h.qv;
+      d.out_off = (int64_t) at;
+      at += (size_t) plan.plen + 1 + ndigits(h.well) + 1 + ndigits(h.beg) + 1 + ndigits(h.end)
+          + 6 + ndigits(h.qv) + 1;
+      d.text_off = (int64_t) at;
+      const int64_t rlen = (int64_t) h.end - h.beg;
+      if (rlen < 0) return dx_fail(ctx,DX_E_FORMAT,"negative read length in entry header");
+      at += (size_t) (5*(rlen + 1));
+    }
+  plan.text_len = at;
+  return DX_OK;
+}
+
+extern "C" int dx_undexqv_dev(dx_ctx *ctx, const uint8_t *d_in, size_t n, int upper,
+                              uint8_t *d_out, size_t cap, size_t *out_len,
+                              const int64_t *h_entry_off, int64_t nentries)
+{ if (ctx == NULL || out_len == NULL) return DX_E_ARG;
+  int rc;
+  *out_len = 0;
+  if ((rc = check_buf(ctx,d_in,"image")) != DX_OK) return rc;
+  cudaSetDevice(ctx->device);
+  dx_arena_reset(ctx);
+  QvPlan plan;
+  if ((rc = plan_undexqv(ctx,d_in,n,h_entry_off,nentries,plan)) != DX_OK) return rc;
+  if (plan.text_len > cap)
+    return dx_fail(ctx,DX_E_CAP,"output needs %zu bytes, buffer has %zu",plan.text_len,cap);
+  const size_t N = plan.ent.size();
+  QvDecEntry *d_ent = (QvDecEntry *) dx_arena_get(ctx,N*sizeof(QvDecEntry));
+  int32_t *d_stat = (int32_t *) dx_arena_get(ctx,4);
+  if (!d_ent || !d_stat) return DX_E_NOMEM;
+  if ((rc = upload(ctx,d_ent,plan.ent.data(),N)) != DX_OK) return rc;
+  DX_CUDA(ctx,cudaMemsetAsync(d_stat,0,4,ctx->stream));
+  if ((rc = dxk_qv_decode(ctx,d_in,n,plan.d_tab,plan.coding.delchar,plan.coding.subchar,
+                          plan.coding.flip,upper,d_ent,plan.d_soff,(int64_t) N,plan.d_prefix,plan.plen,
+                          d_out,d_stat)) != DX_OK) return rc;
+  int32_t stat = 0;
+  DX_CUDA(ctx,cudaMemcpyAsync(&stat,d_stat,4,cudaMemcpyDeviceToHost,ctx->stream));
+  DX_CUDA(ctx,cudaStreamSynchronize(ctx->stream));
+  if (stat) return dx_fail(ctx,DX_E_TRUNC,"Could not read more bits (Decode)");
+  *out_len = plan.text_len;
+  return DX_OK;
+}
+
+extern "C" int dx_undexqv_size_dev(dx_ctx *ctx, const uint8_t *d_in, size_t n, size_t *out_len)
+{ if (ctx == NULL || out_len == NULL) return DX_E_ARG;
+  int rc;
+  *out_len = 0;
+  if ((rc = check_buf(ctx,d_in,"image")) != DX_OK) return rc;
+  cudaSetDevice(ctx->device);
+  dx_arena_reset(ctx);
+  QvPlan plan;
+  if ((rc = plan_undexqv(ctx,d_in,n,NULL,0,plan)) != DX_OK) return rc;
+  *out_len = plan.text_len;
+  return DX_OK;
+}
+
+// ================================================================================================
+//  *_host entry points: stage through device memory, copies included
+// ================================================================================================
+
+static int stage_in(dx_ctx *ctx, const uint8_t *h, size_t n)
+{ int rc;
+  cudaSetDevice(ctx->device);
+  if ((rc = ensure_io(ctx,&ctx->io_in,&ctx->io_in_cap,n)) != DX_OK) return rc;
+  if (n > 0)
+    DX_CUDA(ctx,cudaMemcpyAsync(ctx->io_in,h,n,cudaMemcpyHostToDevice,ctx->stream));
+  return DX_OK;
+}
+
+static int stage_out(dx_ctx *ctx, uint8_t *h, size_t n)
+{ if (n > 0)
+    DX_CUDA(ctx,cudaMemcpyAsync(h,ctx->io_out,n,cudaMemcpyDeviceToHost,ctx->stream));
+  DX_CUDA(ctx,cudaStreamSynchronize(ctx->stream));
+  return DX_OK;
+}
+
+extern "C" int dx_dexta_host(dx_ctx *ctx, int kind, const uint8_t *h_text, size_t n,
+                             uint8_t *h_out, size_t cap, size_t *out_len)
+{ if (ctx == NULL || h_text == NULL || h_out == NULL || out_len == NULL) return DX_E_ARG;
+  int rc;
+  if ((rc = stage_in(ctx,h_text,n)) != DX_OK) return rc;
+  if ((rc = ensure_io(ctx,&ctx->io_out,&ctx->io_out_cap,cap)) != DX_OK) return rc;
+  if ((rc = dx_dexta_dev(ctx,kind,ctx->io_in,n,ctx->io_out,cap,out_len)) != DX_OK) return rc;
+  return stage_out(ctx,h_out,*out_len);
+}
+
+extern "C" int dx_undexta_size_host(dx_ctx *ctx, int kind, const uint8_t *h_in, size_t n, int width,
+                                    size_t *out_len)
+{ if (ctx == NULL || h_in == NULL || out_len == NULL) return DX_E_ARG;
+  int rc;
+  if ((rc = stage_in(ctx,h_in,n)) != DX_OK) return rc;
+  dx_arena_reset(ctx);
+  PkPlan plan;
+  if ((rc = plan_undexta(ctx,kind,ctx->io_in,n,width,plan)) != DX_OK) return rc;
+  *out_len = plan.text_len;
+  return DX_OK;
+}
+
+extern "C" int dx_undexta_host(dx_ctx *ctx, int kind, const uint8_t *h_in, size_t n, int width,
+                               int upper, uint8_t *h_out, size_t cap, size_t *out_len)
+{ if (ctx == NULL || h_in == NULL || h_out == NULL || out_len == NULL) return DX_E_ARG;
+  int rc;
+  if ((rc = stage_in(ctx,h_in,n)) != DX_OK) return rc;
+  if ((rc = ensure_io(ctx,&ctx->io_out,&ctx->io_out_cap,cap)) != DX_OK) return rc;
+  if ((rc = dx_undexta_dev(ctx,kind,ctx->io_in,n,width,upper,ctx->io_out,cap,out_len)) != DX_OK) return rc;
+  return stage_out(ctx,h_out,*out_len);
+}
+
+extern "C" int dx_dexqv_host(dx_ctx *ctx, const uint8_t *h_text, size_t n, int lossy,
+                             uint8_t *h_out, size_t cap, size_t *out_len)
+{ if (ctx == NULL || h_text == NULL || h_out == NULL || out_len == NULL) return DX_E_ARG;
+  int rc;
+  if ((rc = stage_in(ctx,h_text,n)) != DX_OK) return rc;
+  if ((rc = ensure_io(ctx,&ctx->io_out,&ctx->io_out_cap,cap)) != DX_OK) return rc;
+  if ((rc = dx_dexqv_dev(ctx,ctx->io_in,n,lossy,ctx->io_out,cap,out_len)) != DX_OK) return rc;
+  return stage_out(ctx,h_out,*out_len);
+}
+
+extern "C" int dx_undexqv_host(dx_ctx *ctx, const uint8_t *h_in, size_t n, int upper,
+                               uint8_t *h_out, size_t cap, size_t *out_len)
+{ if (ctx == NULL || h_in == NULL || h_out == NULL || out_len == NULL) return DX_E_ARG;
+  int rc;
+  if ((rc = stage_in(ctx,h_in,n)) != DX_OK) return rc;
+  if ((rc = ensure_io(ctx,&ctx->io_out,&ctx->io_out_cap,cap)) != DX_OK) return rc;
+  if ((rc = dx_undexqv_dev(ctx,ctx->io_in,n,upper,ctx->io_out,cap,out_len,NULL,0)) != DX_OK) return rc;
+  return stage_out(ctx,h_out,*out_len);
+}

@@ -1,0 +1,359 @@
+// dx_frame.cu -- text framing on the device.
+//
+// Replaces the fgets()/strlen() line loops of the reference (Read_Lines, QV.c:751-798; the
+// sequence-line loop of dexta.c:161-183) by an ordered index of "interesting" byte positions:
+//   DX_PRED_NEWLINE    every '\n'
+//   DX_PRED_FASTA_HDR  every '>' that starts a line
+//   DX_PRED_QVCAND     every offset whose next 12 bytes look like the beg/end/qv fields of a
+//                      .dexqv entry header (dexqv.c:137-139) -- candidates only, verified later
+// Three launches: per-tile counts, an exclusive scan of the counts, an ordered write.
+
+#include "dx_internal.h"
+#include "dx_common.cuh"
+
+namespace {
+
+constexpr int kTileThreads = 256;
+constexpr int kTileChunks  = 4;                                  // 16-byte chunks per thread
+constexpr int kTileBytes   = kTileThreads * kTileChunks * 16;    // 16 KB
+
+// plausibility window for a .dexqv entry header (see dx_api.cpp: a true entry outside this
+// window is still found by the verified chain walk, only slower)
+constexpr uint32_t kCandMaxBeg  = 1u << 27;
+constexpr uint32_t kCandMaxLen  = 1u << 20;
+constexpr uint32_t kCandMaxQv   = 1u << 16;
+
+__device__ __forceinline__ uint32_t load_le32(const uint8_t *p)
+{ return (uint32_t) p[0] | ((uint32_t) p[1] << 8) | ((uint32_t) p[2] << 16) | ((uint32_t) p[3] << 24); }
+
+// 16-bit hit mask of the chunk starting at byte `at` (16-byte aligned, at < n)
+template <int PRED>
+__device__ __forceinline__ uint32_t chunk_hits(const uint8_t *buf, size_t n, size_t first, size_t at)
+{ uint4 v = dx_ldg16(buf + at);                    // the buffer is padded to a 16-byte multiple
+  uint32_t hits;
+  if (PRED == DX_PRED_NEWLINE)
+    hits = dx_eq_mask16(v,'\n');
+  else if (PRED == DX_PRED_FASTA_HDR)
+    { uint32_t gt = dx_eq_mask16(v,'>');
+      if (gt == 0) return 0;
+      uint32_t nl = dx_eq_mask16(v,'\n') << 1;
+      if (at == 0 || buf[at-1] == '\n') nl |= 1u;
+      hits = gt & nl;
+    }
+  else if (PRED == DX_PRED_ARCAND)
+    { // .dexar entry: int32 beg, int32 end, 4 x uint16 SNR (<= 9999 each)  (dexar.c:202-204)
+      uint4 w = (at + 16 < n) ? dx_ldg16(buf + at + 16) : make_uint4(~0u,~0u,~0u,~0u);
+      const uint32_t k = 0xf8f8f8f8u;
+      uint4 vm = make_uint4(v.x & k,v.y & k,v.z & k,v.w & k);
+      uint4 wm = make_uint4(w.x & k,w.y & k,w.z & k,w.w & k);
+      uint32_t z = dx_eq_mask16(vm,0) | (dx_eq_mask16(wm,0) << 16);    // bytes <= 7
+      uint32_t m = (z >> 3) & (z >> 7) & 0xffffu;
+      hits = 0;
+      while (m)
+        { int i = __ffs(m) - 1;
+          m &= m - 1;
+          size_t p = at + i;
+          if (p + 16 > n) break;
+          uint32_t beg = load_le32(buf+p), end = load_le32(buf+p+4);
+          uint32_t s01 = load_le32(buf+p+8), s23 = load_le32(buf+p+12);
+          if (beg < kCandMaxBeg && end >= beg && end - beg <= kCandMaxLen &&
+              (s01 & 0xffffu) <= 9999u && (s01 >> 16) <= 9999u &&
+              (s23 & 0xffffu) <= 9999u && (s23 >> 16) <= 9999u)
+            hits |= 1u << i;
+        }
+    }
+  else
+    { // cheap filter: bytes +10 and +11 (top half of qv) must be zero; then the full test
+      uint4 w = (at + 16 < n) ? dx_ldg16(buf + at + 16) : make_uint4(~0u,~0u,~0u,~0u);
+      uint32_t z = dx_eq_mask16(v,0) | (dx_eq_mask16(w,0) << 16);
+      uint32_t m = (z >> 10) & (z >> 11) & 0xffffu;
+      hits = 0;
+      while (m)
+        { int i = __ffs(m) - 1;
+          m &= m - 1;
+          size_t p = at + i;
+          if (p + 12 > n) break;
+          uint32_t beg = load_le32(buf+p), end = load_le32(buf+p+4), qv = load_le32(buf+p+8);
+          if (beg < kCandMaxBeg && end >= beg && end - beg <= kCandMaxLen && qv < kCandMaxQv)
+            hits |= 1u << i;
+        }
+    }
+  // clip to [first, n)
+  int lo = (first > at) ? (int) min((size_t) 16, first - at) : 0;
+  int hi = (n - at < 16) ? (int) (n - at) : 16;
+  return hits & dx_range16(lo,hi);
+}
+
+template <int PRED>
+__global__ void __launch_bounds__(kTileThreads)
+k_pred_count(const uint8_t *buf, size_t n, size_t first, uint32_t *tile_count)
+{ const size_t base = (size_t) blockIdx.x * kTileBytes;
+  uint32_t cnt = 0;
+#pragma unroll
+  for (int j = 0; j < kTileChunks; j++)
+    { size_t at = base + ((size_t) j * kTileThreads + threadIdx.x) * 16;
+      if (at < n)
+        cnt += __popc(chunk_hits<PRED>(buf,n,first,at));
+    }
+  __shared__ uint32_t part[kTileThreads/32];
+  cnt = dx_warp_sum(cnt);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = cnt;
+  __syncthreads();
+  if (threadIdx.x == 0)
+    { uint32_t s = 0;
+      for (int w = 0; w < kTileThreads/32; w++) s += part[w];
+      tile_count[blockIdx.x] = s;
+    }
+}
+
+// exclusive scan of ntiles 32-bit counts into 64-bit offsets; one CTA. total at prefix[ntiles].
+__global__ void __launch_bounds__(1024)
+k_tile_scan(const uint32_t *count, int64_t ntiles, int64_t *prefix)
+{ __shared__ uint64_t wsum[32];
+  __shared__ uint64_t carry;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int64_t b = 0; b < ntiles; b += 1024)
+    { int64_t i = b + threadIdx.x;
+      uint64_t v = (i < ntiles) ? count[i] : 0;
+      uint64_t inc = dx_warp_incl_sum64(v,lane);
+      if (lane == 31) wsum[warp] = inc;
+      __syncthreads();
+      if (warp == 0)
+        { uint64_t w = wsum[lane];
+          uint64_t wi = dx_warp_incl_sum64(w,lane);
+          wsum[lane] = wi - w;                     // exclusive over warps
+        }
+      __syncthreads();
+      uint64_t excl = carry + wsum[warp] + inc - v;
+      if (i < ntiles) prefix[i] = (int64_t) excl;
+      __syncthreads();
+      if (threadIdx.x == 1023) carry = excl + v;
+      __syncthreads();
+    }
+  if (threadIdx.x == 0) prefix[ntiles] = (int64_t) carry;
+}
+
+template <int PRED>
+__global__ void __launch_bounds__(kTileThreads)
+k_pred_write(const uint8_t *buf, size_t n, size_t first, const int64_t *tile_prefix, int64_t *pos)
+{ __shared__ uint32_t wsum[kTileThreads/32];
+  __shared__ uint32_t running;
+  const size_t base = (size_t) blockIdx.x * kTileBytes;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) running = 0;
+  __syncthreads();
+  int64_t *dst = pos + tile_prefix[blockIdx.x];
+  for (int j = 0; j < kTileChunks; j++)
+    { size_t at = base + ((size_t) j * kTileThreads + threadIdx.x) * 16;
+      uint32_t hits = (at < n) ? chunk_hits<PRED>(buf,n,first,at) : 0;
+      uint32_t c = __popc(hits);
+      uint32_t inc = dx_warp_incl_sum(c,lane);
+      if (lane == 31) wsum[warp] = inc;
+      __syncthreads();
+      uint32_t before = running;
+      for (int w = 0; w < warp; w++) before += wsum[w];
+      uint32_t r = before + inc - c;
+      while (hits)
+        { int i = __ffs(hits) - 1;
+          hits &= hits - 1;
+          dst[r++] = (int64_t) (at + i);
+        }
+      __syncthreads();
+      if (threadIdx.x == kTileThreads-1) running = before + inc;
+      __syncthreads();
+    }
+}
+
+// ---- .quiva entry table ------------------------------------------------------------------------
+
+__device__ __forceinline__ bool take_digits(const uint8_t *t, int64_t &p, int64_t end, int32_t &val)
+{ int64_t s = p;
+  uint32_t v = 0;
+  while (p < end && t[p] >= '0' && t[p] <= '9' && p - s < 9)
+    v = v*10 + (t[p++] - '0');
+  if (p == s || (p < end && t[p] >= '0' && t[p] <= '9')) return false;   // none, or > 9 digits
+  val = (int32_t) v;
+  return true;
+}
+
+// Canonical "<well>/<beg>_<end> RQ=0.<qv>" after the first '/' of the header (QV.c:958-968).
+// Anything else (signs, blanks, > 9 digits, missing RQ) is left to the host's sscanf.
+__device__ bool parse_quiva_header(const uint8_t *t, int64_t p, int64_t end,
+                                   int32_t &well, int32_t &beg, int32_t &en, int32_t &qv)
+{ p += 1;
+  while (p < end && t[p] != '/') p++;
+  if (p >= end) return false;
+  p++;
+  if (!take_digits(t,p,end,well) || p >= end || t[p] != '/') return false;
+  p++;
+  if (!take_digits(t,p,end,beg) || p >= end || t[p] != '_') return false;
+  p++;
+  if (!take_digits(t,p,end,en)) return false;
+  if (p + 6 > end || t[p] != ' ' || t[p+1] != 'R' || t[p+2] != 'Q' || t[p+3] != '=' ||
+      t[p+4] != '0' || t[p+5] != '.') return false;
+  p += 6;
+  return take_digits(t,p,end,qv);
+}
+
+__global__ void k_qv_entries(const uint8_t *text, const int64_t *nl, int64_t nent, QvEntries ent,
+                             unsigned long long *err /*[0] first error, [1] total positions*/)
+{ int64_t e = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+  { // total positions of the shard (totChar, QV.c:1005): one atomic per warp
+    uint32_t mylen = 0;
+    if (e < nent)
+      { int64_t l = nl[6*e+1] - nl[6*e] - 1;
+        mylen = (l > 0 && l < 0x7ffffff0) ? (uint32_t) l : 0;
+      }
+    unsigned long long s = dx_warp_incl_sum64(mylen,threadIdx.x & 31);
+    if ((threadIdx.x & 31) == 31 && s) atomicAdd(err+1,s);
+  }
+  if (e >= nent) return;
+  const int64_t h0 = (e == 0) ? 0 : nl[6*e-1] + 1;
+  const int64_t h1 = nl[6*e];
+  int64_t len = nl[6*e+1] - h1 - 1;
+  unsigned long long bad = 0;
+  if (h1 == h0 || text[h0] != '@')
+    bad = ((unsigned long long) (6*e+1) << 8) | 1;                // header missing
+  for (int k = 2; k <= 5 && !bad; k++)
+    if (nl[6*e+k] - nl[6*e+k-1] - 1 != len)
+      bad = ((unsigned long long) (6*e+k+1) << 8) | 5;            // lines differ in length
+  if (len >= (1 << 24)) bad = ((unsigned long long) (6*e+2) << 8) | 6;   // beyond 32-bit bit offsets
+  if (bad) { atomicMin(err,bad); return; }
+  ent.hdr[e]   = h0;
+  ent.line0[e] = h1 + 1;
+  ent.rlen[e]  = (int32_t) len;
+  int32_t well = 0, beg = 0, en = 0, qv = 0;
+  bool ok = parse_quiva_header(text,h0,h1,well,beg,en,qv);
+  ent.well[e] = well; ent.beg[e] = beg; ent.end[e] = en; ent.qv[e] = qv;
+  ent.flag[e] = ok ? 0 : 1;
+}
+
+template <int PRED>
+int index_positions(dx_ctx *ctx, const uint8_t *buf, size_t n, size_t first,
+                    int64_t **d_pos, int64_t *count)
+{ const int64_t ntiles = (int64_t) ((n + kTileBytes - 1) / kTileBytes);
+  *d_pos = NULL; *count = 0;
+  if (ntiles == 0) return DX_OK;
+  uint32_t *d_cnt = (uint32_t *) dx_arena_get(ctx,(size_t) ntiles*4);
+  int64_t  *d_pre = (int64_t *)  dx_arena_get(ctx,(size_t) (ntiles+1)*8);
+  if (d_cnt == NULL || d_pre == NULL) return DX_E_NOMEM;
+  k_pred_count<PRED><<<(unsigned) ntiles,kTileThreads,0,ctx->stream>>>(buf,n,first,d_cnt);
+  DX_LAUNCHED(ctx,"k_pred_count");
+  k_tile_scan<<<1,1024,0,ctx->stream>>>(d_cnt,ntiles,d_pre);
+  DX_LAUNCHED(ctx,"k_tile_scan");
+  int64_t total = 0;
+  DX_CUDA(ctx,cudaMemcpyAsync(&total,d_pre+ntiles,8,cudaMemcpyDeviceToHost,ctx->stream));
+  DX_CUDA(ctx,cudaStreamSynchronize(ctx->stream));
+  *count = total;
+  if (total == 0) return DX_OK;
+  int64_t *pos = (int64_t *) dx_arena_get(ctx,(size_t) total*8);
+  if (pos == NULL) return DX_E_NOMEM;
+  k_pred_write<PRED><<<(unsigned) ntiles,kTileThreads,0,ctx->stream>>>(buf,n,first,d_pre,pos);
+  DX_LAUNCHED(ctx,"k_pred_write");
+  *d_pos = pos;
+  return DX_OK;
+}
+
+// For every candidate field position q: how many 0xff bytes sit directly before byte q-1 (capped
+// at 2^20), what byte q-1 is, and the field bytes at q.  Lets the host verify "previous entry
+// ended at p, this entry's well-delta bytes are exactly [p, q)" and rebuild the header text
+// without seeing the image (dexqv.c:128-139).
+__global__ void k_cand_context(const uint8_t *buf, size_t n, size_t first, const int64_t *q,
+                               int64_t count, int fieldbytes, CandInfo *info)
+{ const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  CandInfo ci;
+  const int64_t p = q[i] - 1;                      // the delta terminator byte
+  for (int k = 0; k < 16; k++)
+    ci.field[k] = (k < fieldbytes && (size_t) (q[i] + k) < n) ? buf[q[i] + k] : 0;
+  ci.pad[0] = ci.pad[1] = ci.pad[2] = 0;
+  if (p < (int64_t) first)
+    { ci.ffrun = -1; ci.last = 0; }
+  else
+    { ci.last = buf[p];
+      int32_t r = 0;
+      int64_t k = p - 1;
+      while (k >= (int64_t) first && buf[k] == 0xff && r < (1 << 20)) { r++; k--; }
+      ci.ffrun = r;
+    }
+  info[i] = ci;
+}
+
+__global__ void k_skip_ff(const uint8_t *buf, int64_t n, const int64_t *start, int64_t count, int64_t *q)
+{ const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  int64_t p = start[i];
+  while (p < n && buf[p] == 0xff) p++;
+  q[i] = p + 1;
+}
+
+__global__ void k_field_rlen(const uint8_t *buf, const int64_t *q, int64_t count, int32_t *rlen)
+{ const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const uint8_t *p = buf + q[i];
+  rlen[i] = (int32_t) (load_le32(p+4) - load_le32(p));
+}
+
+}  // namespace
+
+int dxk_cand_context(dx_ctx *ctx, const uint8_t *d_in, size_t n, size_t first, const int64_t *d_q,
+                     int64_t count, int fieldbytes, CandInfo *d_info)
+{ if (count == 0) return DX_OK;
+  k_cand_context<<<(unsigned) ((count+255)/256),256,0,ctx->stream>>>(d_in,n,first,d_q,count,fieldbytes,d_info);
+  DX_LAUNCHED(ctx,"k_cand_context");
+  return DX_OK;
+}
+
+int dxk_skip_ff(dx_ctx *ctx, const uint8_t *d_in, size_t n, const int64_t *d_start, int64_t count,
+                int64_t *d_q)
+{ if (count == 0) return DX_OK;
+  k_skip_ff<<<(unsigned) ((count+255)/256),256,0,ctx->stream>>>(d_in,(int64_t) n,d_start,count,d_q);
+  DX_LAUNCHED(ctx,"k_skip_ff");
+  return DX_OK;
+}
+
+int dxk_field_rlen(dx_ctx *ctx, const uint8_t *d_in, const int64_t *d_q, int64_t count, int32_t *d_rlen)
+{ if (count == 0) return DX_OK;
+  k_field_rlen<<<(unsigned) ((count+255)/256),256,0,ctx->stream>>>(d_in,d_q,count,d_rlen);
+  DX_LAUNCHED(ctx,"k_field_rlen");
+  return DX_OK;
+}
+
+// NOTE: `buf` must be readable up to the next 16-byte multiple of n (all library-owned and
+// torch-allocated device buffers are; dx_api pads the ones it stages itself).
+int dxk_index_positions(dx_ctx *ctx, int pred, const uint8_t *d_buf, size_t n, size_t first,
+                        int64_t **d_pos, int64_t *count)
+{ switch (pred)
+    { case DX_PRED_NEWLINE:   return index_positions<DX_PRED_NEWLINE>(ctx,d_buf,n,first,d_pos,count);
+      case DX_PRED_FASTA_HDR: return index_positions<DX_PRED_FASTA_HDR>(ctx,d_buf,n,first,d_pos,count);
+      case DX_PRED_QVCAND:    return index_positions<DX_PRED_QVCAND>(ctx,d_buf,n,first,d_pos,count);
+      case DX_PRED_ARCAND:    return index_positions<DX_PRED_ARCAND>(ctx,d_buf,n,first,d_pos,count);
+    }
+  return dx_fail(ctx,DX_E_ARG,"unknown position predicate %d",pred);
+}
+
+int dxk_qv_entries(dx_ctx *ctx, const uint8_t *d_text, size_t n, const int64_t *d_nl,
+                   int64_t nlines, QvEntries ent, int32_t *h_err, uint64_t *h_totchar)
+{ (void) n;
+  const int64_t nent = nlines / 6;
+  h_err[0] = 0; h_err[1] = 0; *h_totchar = 0;
+  if (nent == 0) return DX_OK;
+  unsigned long long *d_err = (unsigned long long *) dx_arena_get(ctx,16);
+  if (d_err == NULL) return DX_E_NOMEM;
+  DX_CUDA(ctx,cudaMemsetAsync(d_err,0xff,8,ctx->stream));
+  DX_CUDA(ctx,cudaMemsetAsync(d_err+1,0,8,ctx->stream));
+  k_qv_entries<<<(unsigned) ((nent+255)/256),256,0,ctx->stream>>>(d_text,d_nl,nent,ent,d_err);
+  DX_LAUNCHED(ctx,"k_qv_entries");
+  unsigned long long res[2] = { 0, 0 };
+  DX_CUDA(ctx,cudaMemcpyAsync(res,d_err,16,cudaMemcpyDeviceToHost,ctx->stream));
+  DX_CUDA(ctx,cudaStreamSynchronize(ctx->stream));
+  const unsigned long long e = res[0];
+  *h_totchar = res[1];
+  if (e != ~0ull)
+    { h_err[0] = (int32_t) (e & 0xff);
+      h_err[1] = (int32_t) (e >> 8);        // 1-based line number
+    }
+  return DX_OK;
+}

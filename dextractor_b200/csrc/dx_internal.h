@@ -1,0 +1,180 @@
+// dx_internal.h -- declarations shared by the host C++ and the CUDA translation units of
+// libdexb200.so.  Nothing here is part of the public ABI (that is include/dexb200.h).
+#ifndef DX_INTERNAL_H
+#define DX_INTERNAL_H
+
+#include <stdint.h>
+#include <stddef.h>
+#include <cuda_runtime.h>
+#include "dexb200.h"
+
+// ---- device-side entry tables (structure of arrays, all in HBM) -----------------------------
+
+// One .quiva entry = header line + 5 equal-length lines (reference QV.c:751-798).
+struct QvEntries
+{ int64_t  n;            // entries
+  int64_t *hdr;          // byte offset of '@'
+  int64_t *line0;        // byte offset of the first QV line (delQV); line k at line0 + k*(rlen+1)
+  int32_t *rlen;
+  int32_t *well, *beg, *end, *qv;
+  int32_t *flag;         // 0 ok, 1 header needs the host sscanf path
+};
+
+// Per-entry encode bookkeeping
+struct QvSizes
+{ uint32_t *bytes;       // [n][6]: header bytes, del, tags, ins, mrg, sub
+  int64_t  *off;         // [n+1] entry byte offsets in the output
+};
+
+// Packed code-table entry handed to the encode kernels:
+//   bits 0..15 code, 16..20 length, bit 21 "followed by a literal" (escape)
+#define DX_ENC_CODE(e)  ((e) & 0xffffu)
+#define DX_ENC_LEN(e)   (((e) >> 16) & 0x1fu)
+#define DX_ENC_ESC(e)   (((e) >> 21) & 1u)
+
+struct QvEncTables { uint32_t t[6][256]; };          // 6 KB, passed via HBM pointer
+
+// Decode LUTs: 16-bit window -> symbol (reference QV.c:365-372), one 64 KB table per scheme,
+// plus the code lengths.  lens[k][255] is the escape length for truncated tables.
+struct QvDecTables
+{ uint8_t look[6][65536];
+  uint8_t lens[6][256];
+  int32_t type[6];
+};
+
+// ---- context --------------------------------------------------------------------------------
+
+struct DxBlock { uint8_t *p; size_t cap, top; };
+
+struct dx_ctx
+{ int          device;
+  cudaStream_t stream;
+  int          sm_count;
+  char         err[512];
+  int64_t      err_line;
+  uint64_t     launches;
+
+  // scratch arena in HBM: a bump allocator over a few cudaMalloc'ed blocks, reset per call and
+  // consolidated into one block when a call needed more than one
+  DxBlock      blk[32];
+  int          nblk;
+
+  // device staging for the *_host entry points (grown on demand, kept)
+  uint8_t     *io_in;   size_t io_in_cap;
+  uint8_t     *io_out;  size_t io_out_cap;
+
+  // framing of the last scanned .quiva buffer (reused by the encode pass)
+  const uint8_t *qv_text;
+  size_t         qv_n;
+  QvEntries      qv_ent;
+  uint8_t       *qv_store;     // cudaMalloc'ed backing of qv_ent
+  size_t         qv_store_cap;
+};
+
+int   dx_fail(dx_ctx *ctx, int code, const char *fmt, ...);
+int   dx_cuda_fail(dx_ctx *ctx, cudaError_t e, const char *what);
+void  dx_arena_reset(dx_ctx *ctx);
+void *dx_arena_get(dx_ctx *ctx, size_t bytes);        // 256-byte aligned; NULL + error on failure
+int   dx_arena_reserve(dx_ctx *ctx, size_t bytes);    // make sure this much is available
+
+#define DX_CUDA(ctx, call) do { cudaError_t e__ = (call); \
+    if (e__ != cudaSuccess) return dx_cuda_fail(ctx, e__, #call); } while (0)
+#define DX_LAUNCHED(ctx, what) do { (ctx)->launches++; cudaError_t e__ = cudaGetLastError(); \
+    if (e__ != cudaSuccess) return dx_cuda_fail(ctx, e__, what); } while (0)
+
+// ---- kernels' host launchers (defined in the .cu files) ---------------------------------------
+
+// dx_frame.cu : positions of bytes satisfying a predicate, in order
+enum { DX_PRED_NEWLINE = 0, DX_PRED_FASTA_HDR = 1, DX_PRED_QVCAND = 2, DX_PRED_ARCAND = 3 };
+int dxk_index_positions(dx_ctx *ctx, int pred, const uint8_t *d_buf, size_t n, size_t first,
+                        int64_t **d_pos, int64_t *count);
+int dxk_qv_entries(dx_ctx *ctx, const uint8_t *d_text, size_t n, const int64_t *d_nl,
+                   int64_t nlines, QvEntries ent, int32_t *h_err /*[2]: code, line*/,
+                   uint64_t *h_totchar);
+
+// dx_qv_stats.cu
+struct QvProbe                  // device-resident result of the order-dependent prefix rules
+{ int32_t  delchar, subchar;
+  int64_t  e_del, e_sub;        // first entry whose runs are counted (n if never)
+  uint64_t sub_prefix[256];
+  uint64_t totchar;
+};
+int dxk_qv_probe(dx_ctx *ctx, const uint8_t *d_text, QvEntries ent, const dx_qv_carry *carry,
+                 QvProbe *h_probe);
+int dxk_qv_hist(dx_ctx *ctx, const uint8_t *d_text, QvEntries ent, const QvProbe *h_probe,
+                uint64_t *h_hist /*[6][256]*/, int32_t *h_newline_inside);
+
+// dx_qv_encode.cu
+int dxk_qv_encode(dx_ctx *ctx, const uint8_t *d_text, size_t text_n, QvEntries ent,
+                  const QvEncTables *h_tab,
+                  int delchar, int subchar, int lossy, int32_t lwell_in,
+                  uint8_t *d_out, size_t cap, size_t *out_len, int32_t *last_well,
+                  int64_t *h_entry_off, int64_t max_entries);
+
+// dx_qv_decode.cu
+struct QvDecEntry               // host-built table for the decode kernel
+{ int64_t out_off;              // where the entry's header text starts in the output
+  int64_t text_off;             // where its first QV line starts in the output
+  int32_t well, beg, end, qv;
+};
+// soff: [count][6] = byte offsets of the 5 streams (del, tags, ins, mrg, sub) + entry end
+int dxk_qv_walk(dx_ctx *ctx, const uint8_t *d_in, size_t n, const QvDecTables *d_tab,
+                int delchar, int subchar, int flip, const int64_t *d_start, const int32_t *d_rlen,
+                int64_t count, int64_t *d_soff, int32_t *d_status /*[count]*/);
+int dxk_qv_decode(dx_ctx *ctx, const uint8_t *d_in, size_t n, const QvDecTables *d_tab,
+                  int delchar, int subchar, int flip, int upper, const QvDecEntry *d_ent,
+                  const int64_t *d_soff, int64_t count, const char *d_prefix, int plen,
+                  uint8_t *d_out, int32_t *d_status /*[1]*/);
+
+// dx_pack.cu : .fasta/.arrow <-> 2-bit images
+struct FaEntries                // one fasta/arrow entry (structure of arrays in HBM)
+{ int64_t  n;
+  int64_t *hdr;                 // offset of '>'
+  int64_t *seq;                 // offset of the first sequence character
+  int64_t *region;              // bytes from seq to the next header / end of text
+  int32_t *rlen;                // sequence symbols (newlines excluded)
+  int32_t *width;               // length of the first sequence line
+  int32_t *well, *beg, *end;
+  int32_t *aux;                 // [n][2]: fasta qv,0 ; arrow cnr[0..3] as 4 x uint16
+  int32_t *flag;                // bit0 header needs host sscanf, bit1 ragged lines, bit2 line too long
+  uint32_t *bytes;              // encoded bytes of the entry (header fields + payload)
+  int64_t *off;                 // [n+1] encoded offsets
+};
+int dxk_fa_measure(dx_ctx *ctx, int kind, const uint8_t *d_text, size_t n, const int64_t *d_hdr,
+                   FaEntries ent);
+int dxk_fa_offsets(dx_ctx *ctx, int kind, FaEntries ent, int32_t lwell_in, int64_t *h_total);
+int dxk_fa_pack(dx_ctx *ctx, int kind, const uint8_t *d_text, size_t n, FaEntries ent,
+                int32_t lwell_in, uint8_t *d_out);
+
+struct PkDecEntry               // host-built table for the unpack kernel
+{ int64_t bin_off;              // first payload byte in the image
+  int64_t out_off;              // header text start in the output
+  int64_t text_off;             // first sequence character in the output
+  int32_t well, beg, end;
+  int32_t aux[2];               // fasta: qv ; arrow: 4 x uint16 cnr
+};
+int dxk_pk_walk(dx_ctx *ctx, int fieldbytes, const uint8_t *d_in, size_t n, const int64_t *d_q,
+                int64_t count, int64_t *d_end);
+int dxk_unpack(dx_ctx *ctx, int kind, int upper, int width, const uint8_t *d_in,
+               const PkDecEntry *d_ent, int64_t count, const char *d_prefix, int plen,
+               uint8_t *d_out);
+// candidate bookkeeping shared by the .dexta/.dexar/.dexqv chain resolvers: for each candidate
+// field position q, the number of 0xff bytes directly before q-1 (capped) and the byte at q-1
+struct CandInfo { int32_t ffrun; uint8_t last; uint8_t pad[3]; uint8_t field[16]; };
+int dxk_cand_context(dx_ctx *ctx, const uint8_t *d_in, size_t n, size_t first, const int64_t *d_q,
+                     int64_t count, int fieldbytes, CandInfo *d_info);
+// starts (first well-delta byte of each entry) -> field positions q
+int dxk_skip_ff(dx_ctx *ctx, const uint8_t *d_in, size_t n, const int64_t *d_start, int64_t count,
+                int64_t *d_q);
+// rlen[i] = end - beg read from the 32-bit fields at q[i]
+int dxk_field_rlen(dx_ctx *ctx, const uint8_t *d_in, const int64_t *d_q, int64_t count,
+                   int32_t *d_rlen);
+
+// batched in-memory reads (DB.c loaders / dex2DB writer)
+int dxk_compress_reads(dx_ctx *ctx, int kind, const uint8_t *d_src, const int64_t *d_src_off,
+                       const int32_t *d_len, int64_t nreads, uint8_t *d_dst, const int64_t *d_dst_off);
+int dxk_uncompress_reads(dx_ctx *ctx, int kind, int upper, const uint8_t *d_src,
+                         const int64_t *d_src_off, const int32_t *d_len, int64_t nreads,
+                         uint8_t *d_dst, const int64_t *d_dst_off);
+
+#endif
