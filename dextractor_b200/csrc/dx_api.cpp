@@ -83,6 +83,61 @@ int dx_arena_reserve(dx_ctx *ctx, size_t bytes)
   return DX_OK;
 }
 
+// ---- per-kernel event timing -------------------------------------------------------------------
+
+struct DxProfRec { const char *name; cudaEvent_t a, b; };
+typedef std::vector<DxProfRec> DxProf;
+
+void dx_prof_begin(dx_ctx *ctx)
+{ DxProf *pv = (DxProf *) ctx->prof;
+  DxProfRec r; r.name = NULL;
+  cudaEventCreate(&r.a); cudaEventCreate(&r.b);
+  cudaEventRecord(r.a,ctx->stream);
+  pv->push_back(r);
+}
+
+void dx_prof_end(dx_ctx *ctx, const char *what)
+{ DxProf *pv = (DxProf *) ctx->prof;
+  if (pv->empty() || pv->back().name != NULL) return;
+  pv->back().name = what;
+  cudaEventRecord(pv->back().b,ctx->stream);
+}
+
+extern "C" int dx_profile(dx_ctx *ctx, int enable)
+{ if (ctx == NULL) return DX_E_ARG;
+  if (ctx->prof == NULL) ctx->prof = new DxProf();
+  ctx->prof_on = enable ? 1 : 0;
+  return DX_OK;
+}
+
+extern "C" int dx_profile_report(dx_ctx *ctx, char *buf, size_t cap)
+{ if (ctx == NULL || buf == NULL || cap == 0) return DX_E_ARG;
+  buf[0] = '\0';
+  if (ctx->prof == NULL) return DX_OK;
+  DX_CUDA(ctx,cudaStreamSynchronize(ctx->stream));
+  DxProf *pv = (DxProf *) ctx->prof;
+  struct Acc { const char *name; int calls; double ms; };
+  std::vector<Acc> acc;
+  for (DxProfRec &r : *pv)
+    { float ms = 0;
+      if (r.name != NULL && cudaEventElapsedTime(&ms,r.a,r.b) == cudaSuccess)
+        { size_t k = 0;
+          while (k < acc.size() && strcmp(acc[k].name,r.name) != 0) k++;
+          if (k == acc.size()) acc.push_back(Acc{r.name,0,0.0});
+          acc[k].calls += 1; acc[k].ms += ms;
+        }
+      cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+    }
+  pv->clear();
+  size_t at = 0;
+  for (const Acc &a : acc)
+    { int w = snprintf(buf+at,cap-at,"%s %d %.6f\n",a.name,a.calls,a.ms);
+      if (w < 0 || (size_t) w >= cap-at) return DX_E_CAP;
+      at += (size_t) w;
+    }
+  return DX_OK;
+}
+
 extern "C" int dx_open(int device, dx_ctx **out)
 { if (out == NULL) return DX_E_ARG;
   *out = NULL;
@@ -115,6 +170,10 @@ extern "C" void dx_close(dx_ctx *ctx)
   if (ctx->io_in)    cudaFree(ctx->io_in);
   if (ctx->io_out)   cudaFree(ctx->io_out);
   if (ctx->qv_store) cudaFree(ctx->qv_store);
+  if (ctx->prof)
+    { char tmp[16]; ctx->prof_on = 0; dx_profile_report(ctx,tmp,sizeof(tmp));
+      delete (DxProf *) ctx->prof;
+    }
   cudaStreamDestroy(ctx->stream);
   free(ctx);
 }

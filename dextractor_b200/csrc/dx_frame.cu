@@ -239,9 +239,9 @@ int index_positions(dx_ctx *ctx, const uint8_t *buf, size_t n, size_t first,
   uint32_t *d_cnt = (uint32_t *) dx_arena_get(ctx,(size_t) ntiles*4);
   int64_t  *d_pre = (int64_t *)  dx_arena_get(ctx,(size_t) (ntiles+1)*8);
   if (d_cnt == NULL || d_pre == NULL) return DX_E_NOMEM;
-  k_pred_count<PRED><<<(unsigned) ntiles,kTileThreads,0,ctx->stream>>>(buf,n,first,d_cnt);
+  DX_PROF_BEGIN(ctx); k_pred_count<PRED><<<(unsigned) ntiles,kTileThreads,0,ctx->stream>>>(buf,n,first,d_cnt);
   DX_LAUNCHED(ctx,"k_pred_count");
-  k_tile_scan<<<1,1024,0,ctx->stream>>>(d_cnt,ntiles,d_pre);
+  DX_PROF_BEGIN(ctx); k_tile_scan<<<1,1024,0,ctx->stream>>>(d_cnt,ntiles,d_pre);
   DX_LAUNCHED(ctx,"k_tile_scan");
   int64_t total = 0;
   DX_CUDA(ctx,cudaMemcpyAsync(&total,d_pre+ntiles,8,cudaMemcpyDeviceToHost,ctx->stream));
@@ -250,7 +250,7 @@ int index_positions(dx_ctx *ctx, const uint8_t *buf, size_t n, size_t first,
   if (total == 0) return DX_OK;
   int64_t *pos = (int64_t *) dx_arena_get(ctx,(size_t) total*8);
   if (pos == NULL) return DX_E_NOMEM;
-  k_pred_write<PRED><<<(unsigned) ntiles,kTileThreads,0,ctx->stream>>>(buf,n,first,d_pre,pos);
+  DX_PROF_BEGIN(ctx); k_pred_write<PRED><<<(unsigned) ntiles,kTileThreads,0,ctx->stream>>>(buf,n,first,d_pre,pos);
   DX_LAUNCHED(ctx,"k_pred_write");
   *d_pos = pos;
   return DX_OK;
@@ -301,7 +301,7 @@ __global__ void k_field_rlen(const uint8_t *buf, const int64_t *q, int64_t count
 int dxk_cand_context(dx_ctx *ctx, const uint8_t *d_in, size_t n, size_t first, const int64_t *d_q,
                      int64_t count, int fieldbytes, CandInfo *d_info)
 { if (count == 0) return DX_OK;
-  k_cand_context<<<(unsigned) ((count+255)/256),256,0,ctx->stream>>>(d_in,n,first,d_q,count,fieldbytes,d_info);
+  DX_PROF_BEGIN(ctx); k_cand_context<<<(unsigned) ((count+255)/256),256,0,ctx->stream>>>(d_in,n,first,d_q,count,fieldbytes,d_info);
   DX_LAUNCHED(ctx,"k_cand_context");
   return DX_OK;
 }
@@ -309,14 +309,14 @@ int dxk_cand_context(dx_ctx *ctx, const uint8_t *d_in, size_t n, size_t first, c
 int dxk_skip_ff(dx_ctx *ctx, const uint8_t *d_in, size_t n, const int64_t *d_start, int64_t count,
                 int64_t *d_q)
 { if (count == 0) return DX_OK;
-  k_skip_ff<<<(unsigned) ((count+255)/256),256,0,ctx->stream>>>(d_in,(int64_t) n,d_start,count,d_q);
+  DX_PROF_BEGIN(ctx); k_skip_ff<<<(unsigned) ((count+255)/256),256,0,ctx->stream>>>(d_in,(int64_t) n,d_start,count,d_q);
   DX_LAUNCHED(ctx,"k_skip_ff");
   return DX_OK;
 }
 
 int dxk_field_rlen(dx_ctx *ctx, const uint8_t *d_in, const int64_t *d_q, int64_t count, int32_t *d_rlen)
 { if (count == 0) return DX_OK;
-  k_field_rlen<<<(unsigned) ((count+255)/256),256,0,ctx->stream>>>(d_in,d_q,count,d_rlen);
+  DX_PROF_BEGIN(ctx); k_field_rlen<<<(unsigned) ((count+255)/256),256,0,ctx->stream>>>(d_in,d_q,count,d_rlen);
   DX_LAUNCHED(ctx,"k_field_rlen");
   return DX_OK;
 }
@@ -344,7 +344,7 @@ int dxk_qv_entries(dx_ctx *ctx, const uint8_t *d_text, size_t n, const int64_t *
   if (d_err == NULL) return DX_E_NOMEM;
   DX_CUDA(ctx,cudaMemsetAsync(d_err,0xff,8,ctx->stream));
   DX_CUDA(ctx,cudaMemsetAsync(d_err+1,0,8,ctx->stream));
-  k_qv_entries<<<(unsigned) ((nent+255)/256),256,0,ctx->stream>>>(d_text,d_nl,nent,ent,d_err);
+  DX_PROF_BEGIN(ctx); k_qv_entries<<<(unsigned) ((nent+255)/256),256,0,ctx->stream>>>(d_text,d_nl,nent,ent,d_err);
   DX_LAUNCHED(ctx,"k_qv_entries");
   unsigned long long res[2] = { 0, 0 };
   DX_CUDA(ctx,cudaMemcpyAsync(res,d_err,16,cudaMemcpyDeviceToHost,ctx->stream));

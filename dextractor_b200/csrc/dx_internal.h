@@ -63,6 +63,10 @@ struct dx_ctx
   uint8_t     *io_in;   size_t io_in_cap;
   uint8_t     *io_out;  size_t io_out_cap;
 
+  // per-kernel CUDA-event timing (dx_profile): (name, start, stop) per launch
+  int          prof_on;
+  void        *prof;           // std::vector<DxProfRec>*
+
   // framing of the last scanned .quiva buffer (reused by the encode pass)
   const uint8_t *qv_text;
   size_t         qv_n;
@@ -79,7 +83,11 @@ int   dx_arena_reserve(dx_ctx *ctx, size_t bytes);    // make sure this much is 
 
 #define DX_CUDA(ctx, call) do { cudaError_t e__ = (call); \
     if (e__ != cudaSuccess) return dx_cuda_fail(ctx, e__, #call); } while (0)
+void dx_prof_begin(dx_ctx *ctx);
+void dx_prof_end(dx_ctx *ctx, const char *what);
+#define DX_PROF_BEGIN(ctx) do { if ((ctx)->prof_on) dx_prof_begin(ctx); } while (0)
 #define DX_LAUNCHED(ctx, what) do { (ctx)->launches++; cudaError_t e__ = cudaGetLastError(); \
+    if ((ctx)->prof_on) dx_prof_end(ctx, what); \
     if (e__ != cudaSuccess) return dx_cuda_fail(ctx, e__, what); } while (0)
 
 // ---- kernels' host launchers (defined in the .cu files) ---------------------------------------

@@ -455,7 +455,7 @@ k_uncompress_reads(int kind, int upper, const uint8_t *src, const int64_t *src_o
 int dxk_compress_reads(dx_ctx *ctx, int kind, const uint8_t *d_src, const int64_t *d_src_off,
                        const int32_t *d_len, int64_t nreads, uint8_t *d_dst, const int64_t *d_dst_off)
 { if (nreads == 0) return DX_OK;
-  k_compress_reads<<<ctx->sm_count*8,kPkThreads,0,ctx->stream>>>(kind,d_src,d_src_off,d_len,nreads,d_dst,d_dst_off);
+  DX_PROF_BEGIN(ctx); k_compress_reads<<<ctx->sm_count*8,kPkThreads,0,ctx->stream>>>(kind,d_src,d_src_off,d_len,nreads,d_dst,d_dst_off);
   DX_LAUNCHED(ctx,"k_compress_reads");
   return DX_OK;
 }
@@ -464,7 +464,7 @@ int dxk_uncompress_reads(dx_ctx *ctx, int kind, int upper, const uint8_t *d_src,
                          const int64_t *d_src_off, const int32_t *d_len, int64_t nreads,
                          uint8_t *d_dst, const int64_t *d_dst_off)
 { if (nreads == 0) return DX_OK;
-  k_uncompress_reads<<<ctx->sm_count*8,kPkThreads,0,ctx->stream>>>(kind,upper,d_src,d_src_off,d_len,nreads,d_dst,d_dst_off);
+  DX_PROF_BEGIN(ctx); k_uncompress_reads<<<ctx->sm_count*8,kPkThreads,0,ctx->stream>>>(kind,upper,d_src,d_src_off,d_len,nreads,d_dst,d_dst_off);
   DX_LAUNCHED(ctx,"k_uncompress_reads");
   return DX_OK;
 }
@@ -473,7 +473,7 @@ int dxk_fa_measure(dx_ctx *ctx, int kind, const uint8_t *d_text, size_t n, const
                    FaEntries ent)
 { if (ent.n == 0) return DX_OK;
   const int grid = ctx->sm_count * 8;
-  k_fa_measure<<<grid,kPkThreads,0,ctx->stream>>>(kind,d_text,(int64_t) n,d_hdr,ent);
+  DX_PROF_BEGIN(ctx); k_fa_measure<<<grid,kPkThreads,0,ctx->stream>>>(kind,d_text,(int64_t) n,d_hdr,ent);
   DX_LAUNCHED(ctx,"k_fa_measure");
   return DX_OK;
 }
@@ -481,7 +481,7 @@ int dxk_fa_measure(dx_ctx *ctx, int kind, const uint8_t *d_text, size_t n, const
 int dxk_fa_offsets(dx_ctx *ctx, int kind, FaEntries ent, int32_t lwell_in, int64_t *h_total)
 { *h_total = 0;
   if (ent.n == 0) return DX_OK;
-  k_fa_offsets<<<1,1024,0,ctx->stream>>>(kind,ent,lwell_in);
+  DX_PROF_BEGIN(ctx); k_fa_offsets<<<1,1024,0,ctx->stream>>>(kind,ent,lwell_in);
   DX_LAUNCHED(ctx,"k_fa_offsets");
   DX_CUDA(ctx,cudaMemcpyAsync(h_total,ent.off+ent.n,8,cudaMemcpyDeviceToHost,ctx->stream));
   DX_CUDA(ctx,cudaStreamSynchronize(ctx->stream));
@@ -493,7 +493,7 @@ int dxk_fa_pack(dx_ctx *ctx, int kind, const uint8_t *d_text, size_t n, FaEntrie
 { (void) n;
   if (ent.n == 0) return DX_OK;
   const int grid = ctx->sm_count * 8;
-  k_fa_pack<<<grid,kPkThreads,0,ctx->stream>>>(kind,d_text,ent,lwell_in,d_out);
+  DX_PROF_BEGIN(ctx); k_fa_pack<<<grid,kPkThreads,0,ctx->stream>>>(kind,d_text,ent,lwell_in,d_out);
   DX_LAUNCHED(ctx,"k_fa_pack");
   return DX_OK;
 }
@@ -501,7 +501,7 @@ int dxk_fa_pack(dx_ctx *ctx, int kind, const uint8_t *d_text, size_t n, FaEntrie
 int dxk_pk_walk(dx_ctx *ctx, int fieldbytes, const uint8_t *d_in, size_t n, const int64_t *d_q,
                 int64_t count, int64_t *d_end)
 { if (count == 0) return DX_OK;
-  k_pk_walk<<<(unsigned) ((count+255)/256),256,0,ctx->stream>>>(fieldbytes,d_in,(int64_t) n,d_q,count,d_end);
+  DX_PROF_BEGIN(ctx); k_pk_walk<<<(unsigned) ((count+255)/256),256,0,ctx->stream>>>(fieldbytes,d_in,(int64_t) n,d_q,count,d_end);
   DX_LAUNCHED(ctx,"k_pk_walk");
   return DX_OK;
 }
@@ -511,7 +511,7 @@ int dxk_unpack(dx_ctx *ctx, int kind, int upper, int width, const uint8_t *d_in,
                uint8_t *d_out)
 { if (count == 0) return DX_OK;
   const int grid = ctx->sm_count * 8;
-  k_unpack<<<grid,kPkThreads,0,ctx->stream>>>(kind,upper,width,d_in,d_ent,count,d_prefix,plen,d_out);
+  DX_PROF_BEGIN(ctx); k_unpack<<<grid,kPkThreads,0,ctx->stream>>>(kind,upper,width,d_in,d_ent,count,d_prefix,plen,d_out);
   DX_LAUNCHED(ctx,"k_unpack");
   return DX_OK;
 }

@@ -292,7 +292,7 @@ int dxk_qv_walk(dx_ctx *ctx, const uint8_t *d_in, size_t n, const QvDecTables *d
                 int64_t count, int64_t *d_soff, int32_t *d_status)
 { if (count == 0) return DX_OK;
   DecArgs a = { d_in, (int64_t) n, d_tab, delchar, subchar, flip, 0 };
-  k_qv_walk<<<(unsigned) ((count+63)/64),64,0,ctx->stream>>>(a,d_start,d_rlen,count,d_soff,d_status);
+  DX_PROF_BEGIN(ctx); k_qv_walk<<<(unsigned) ((count+63)/64),64,0,ctx->stream>>>(a,d_start,d_rlen,count,d_soff,d_status);
   DX_LAUNCHED(ctx,"k_qv_walk");
   return DX_OK;
 }
@@ -304,7 +304,7 @@ int dxk_qv_decode(dx_ctx *ctx, const uint8_t *d_in, size_t n, const QvDecTables 
 { if (count == 0) return DX_OK;
   DecArgs a = { d_in, (int64_t) n, d_tab, delchar, subchar, flip, upper };
   const int64_t threads = count*5;
-  k_qv_decode<<<(unsigned) ((threads+63)/64),64,0,ctx->stream>>>(a,d_ent,d_soff,count,d_prefix,plen,
+  DX_PROF_BEGIN(ctx); k_qv_decode<<<(unsigned) ((threads+63)/64),64,0,ctx->stream>>>(a,d_ent,d_soff,count,d_prefix,plen,
                                                                  d_out,d_status);
   DX_LAUNCHED(ctx,"k_qv_decode");
   return DX_OK;

@@ -483,9 +483,9 @@ int dxk_qv_encode(dx_ctx *ctx, const uint8_t *d_text, size_t text_n, QvEntries e
   const size_t smem1 = 6*256*4 + (size_t) kEncWarps*kStageWords*4;
   DX_CUDA(ctx,cudaFuncSetAttribute(k_qv_code<1>,cudaFuncAttributeMaxDynamicSharedMemorySize,(int) smem1));
 
-  k_qv_code<0><<<grid,kEncThreads,smem0,ctx->stream>>>(a);
+  DX_PROF_BEGIN(ctx); k_qv_code<0><<<grid,kEncThreads,smem0,ctx->stream>>>(a);
   DX_LAUNCHED(ctx,"k_qv_size");
-  k_qv_offsets<<<1,1024,0,ctx->stream>>>(d_bytes,n,d_off);
+  DX_PROF_BEGIN(ctx); k_qv_offsets<<<1,1024,0,ctx->stream>>>(d_bytes,n,d_off);
   DX_LAUNCHED(ctx,"k_qv_offsets");
 
   int64_t total = 0;
@@ -497,7 +497,7 @@ int dxk_qv_encode(dx_ctx *ctx, const uint8_t *d_text, size_t text_n, QvEntries e
     return dx_fail(ctx,DX_E_CAP,"output needs %lld bytes, buffer has %zu",(long long) total,cap);
 
   a.ticket = d_ticket + 1;
-  k_qv_code<1><<<grid,kEncThreads,smem1,ctx->stream>>>(a);
+  DX_PROF_BEGIN(ctx); k_qv_code<1><<<grid,kEncThreads,smem1,ctx->stream>>>(a);
   DX_LAUNCHED(ctx,"k_qv_emit");
   if (h_entry_off != NULL)
     { if (max_entries < n)
@@ -506,6 +506,7 @@ int dxk_qv_encode(dx_ctx *ctx, const uint8_t *d_text, size_t text_n, QvEntries e
       DX_CUDA(ctx,cudaMemcpyAsync(h_entry_off,d_off,(size_t) (n+1)*8,cudaMemcpyDeviceToHost,ctx->stream));
       DX_CUDA(ctx,cudaStreamSynchronize(ctx->stream));
     }
+  DX_CUDA(ctx,cudaStreamSynchronize(ctx->stream));      // _dev calls return with the work done
   *out_len = (size_t) total;
   if (last_well) *last_well = lastw;
   return DX_OK;

@@ -230,9 +230,9 @@ int dxk_qv_probe(dx_ctx *ctx, const uint8_t *d_text, QvEntries ent, const dx_qv_
   const bool need_del = (carry->delchar < 0), need_sub = (carry->subchar < 0);
   if (need_del && ent.n > 0)
     { int blocks = ctx->sm_count * 4;
-      k_find_delchar<<<blocks,256,0,ctx->stream>>>(d_text,ent,d_found);
+      DX_PROF_BEGIN(ctx); k_find_delchar<<<blocks,256,0,ctx->stream>>>(d_text,ent,d_found);
       DX_LAUNCHED(ctx,"k_find_delchar");
-      k_pick_delchar<<<1,1,0,ctx->stream>>>(d_text,ent,d_found,d_probe);
+      DX_PROF_BEGIN(ctx); k_pick_delchar<<<1,1,0,ctx->stream>>>(d_text,ent,d_found,d_probe);
       DX_LAUNCHED(ctx,"k_pick_delchar");
     }
   if (need_sub)
@@ -269,7 +269,7 @@ int dxk_qv_hist(dx_ctx *ctx, const uint8_t *d_text, QvEntries ent, const QvProbe
     { DX_CUDA(ctx,cudaFuncSetAttribute(k_qv_hist,cudaFuncAttributeMaxDynamicSharedMemorySize,(int) smem));
       attr_done = true;
     }
-  k_qv_hist<<<ctx->sm_count,kHistThreads,smem,ctx->stream>>>(a);
+  DX_PROF_BEGIN(ctx); k_qv_hist<<<ctx->sm_count,kHistThreads,smem,ctx->stream>>>(a);
   DX_LAUNCHED(ctx,"k_qv_hist");
   DX_CUDA(ctx,cudaMemcpyAsync(h_hist,d_hist,6*256*8,cudaMemcpyDeviceToHost,ctx->stream));
   DX_CUDA(ctx,cudaStreamSynchronize(ctx->stream));

@@ -18,7 +18,7 @@ ERRNAMES = {-1: "FORMAT", -2: "CAP", -3: "TRUNC", -4: "KEY", -5: "LINELEN", -6: 
 SYMBOLS = [
     "dx_open", "dx_close", "dx_strerror", "dx_error_line", "dx_sync", "dx_stream",
     "dx_device_alloc", "dx_device_free", "dx_pinned_alloc", "dx_pinned_free", "dx_h2d", "dx_d2h",
-    "dx_launch_count",
+    "dx_launch_count", "dx_profile", "dx_profile_report",
     "dx_dexta_dev", "dx_dexta_host", "dx_undexta_dev", "dx_undexta_host", "dx_undexta_size_host",
     "dx_compress_reads_dev", "dx_uncompress_reads_dev",
     "dx_qv_scan_dev", "dx_qv_make_coding", "dx_qv_write_coding", "dx_qv_read_coding",
@@ -91,6 +91,8 @@ def load_library():
         "dx_h2d": (C.c_int, [vp, vp, vp, sz]),
         "dx_d2h": (C.c_int, [vp, vp, vp, sz]),
         "dx_launch_count": (C.c_uint64, [vp, C.c_int]),
+        "dx_profile": (C.c_int, [vp, C.c_int]),
+        "dx_profile_report": (C.c_int, [vp, C.c_char_p, sz]),
         "dx_dexta_dev": (C.c_int, [vp, C.c_int, vp, sz, vp, sz, szp]),
         "dx_dexta_host": (C.c_int, [vp, C.c_int, vp, sz, vp, sz, szp]),
         "dx_undexta_dev": (C.c_int, [vp, C.c_int, vp, sz, C.c_int, C.c_int, vp, sz, szp]),
@@ -187,6 +189,25 @@ class Context:
 
     def launch_count(self, reset: bool = False) -> int:
         return int(self.L.dx_launch_count(self.h, int(reset)))
+
+    def h2d(self, d_dst: int, data: bytes):
+        """small synchronous host->device copy on the context's stream"""
+        src = np.frombuffer(data, dtype=np.uint8)
+        self._check(self.L.dx_h2d(self.h, d_dst, src.ctypes.data, len(data)))
+        self.sync()
+
+    def profile(self, enable: bool):
+        self._check(self.L.dx_profile(self.h, int(enable)))
+
+    def profile_report(self) -> dict:
+        """{kernel name: (calls, total ms)} since the last report; clears the records"""
+        buf = C.create_string_buffer(1 << 16)
+        self._check(self.L.dx_profile_report(self.h, buf, len(buf)))
+        out = {}
+        for line in buf.value.decode().splitlines():
+            name, calls, ms = line.split()
+            out[name] = (int(calls), float(ms))
+        return out
 
     # ---- host-buffer API (copies included) ----------------------------------------------------
     def dexta(self, text: bytes, kind: int = FASTA) -> bytes:

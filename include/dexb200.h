@@ -63,6 +63,12 @@ int   dx_d2h(dx_ctx *ctx, void *h_dst, const void *d_src, size_t bytes);   /* as
 /* launches issued by this context since the last reset (for the bench's gpu_launches claim) */
 uint64_t dx_launch_count(dx_ctx *ctx, int reset);
 
+/* Per-kernel device timing.  While enabled every kernel launch of this context is bracketed by
+ * CUDA events on the context's stream; dx_profile_report waits for the stream, writes one line
+ * per kernel name -- "name calls total_ms" -- into buf and clears the records. */
+int dx_profile(dx_ctx *ctx, int enable);
+int dx_profile_report(dx_ctx *ctx, char *buf, size_t cap);
+
 /* ----------------------------------------------------------------------------------------------
  *  2-bit codec: .fasta <-> .dexta and .arrow <-> .dexar
  * -------------------------------------------------------------------------------------------- */

@@ -98,7 +98,7 @@ def dexta(text: bytes, arrow: bool = False) -> bytes:
 
 
 def undexta(data: bytes, arrow: bool = False, width: int = 80, upper: bool = False) -> bytes:
-    cap = len(data) * 6 + 65536
+    cap = len(data) * 9 + 65536
     return _run(lib().orc_undexta, data, cap, int(arrow), width, int(upper))
 
 
