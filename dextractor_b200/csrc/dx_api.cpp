@@ -649,6 +649,20 @@ extern "C" int dx_undexta_dev(dx_ctx *ctx, int kind, const uint8_t *d_in, size_t
   return DX_OK;
 }
 
+extern "C" int dx_undexta_size_dev(dx_ctx *ctx, int kind, const uint8_t *d_in, size_t n, int width,
+                                   size_t *out_len)
+{ if (ctx == NULL || out_len == NULL || (kind != DX_FASTA && kind != DX_ARROW)) return DX_E_ARG;
+  *out_len = 0;
+  int rc;
+  if ((rc = check_buf(ctx,d_in,"image")) != DX_OK) return rc;
+  cudaSetDevice(ctx->device);
+  dx_arena_reset(ctx);
+  PkPlan plan;
+  if ((rc = plan_undexta(ctx,kind,d_in,n,width,plan)) != DX_OK) return rc;
+  *out_len = plan.text_len;
+  return DX_OK;
+}
+
 extern "C" int dx_compress_reads_dev(dx_ctx *ctx, int kind, const uint8_t *d_src,
                                      const int64_t *d_src_off, const int32_t *d_len, int64_t nreads,
                                      uint8_t *d_dst, const int64_t *d_dst_off)

@@ -20,6 +20,7 @@ SYMBOLS = [
     "dx_device_alloc", "dx_device_free", "dx_pinned_alloc", "dx_pinned_free", "dx_h2d", "dx_d2h",
     "dx_launch_count", "dx_profile", "dx_profile_report",
     "dx_dexta_dev", "dx_dexta_host", "dx_undexta_dev", "dx_undexta_host", "dx_undexta_size_host",
+    "dx_undexta_size_dev",
     "dx_compress_reads_dev", "dx_uncompress_reads_dev",
     "dx_qv_scan_dev", "dx_qv_make_coding", "dx_qv_write_coding", "dx_qv_read_coding",
     "dx_qv_encode_dev", "dx_dexqv_dev", "dx_dexqv_host", "dx_undexqv_dev", "dx_undexqv_host",
@@ -98,6 +99,7 @@ def load_library():
         "dx_undexta_dev": (C.c_int, [vp, C.c_int, vp, sz, C.c_int, C.c_int, vp, sz, szp]),
         "dx_undexta_host": (C.c_int, [vp, C.c_int, vp, sz, C.c_int, C.c_int, vp, sz, szp]),
         "dx_undexta_size_host": (C.c_int, [vp, C.c_int, vp, sz, C.c_int, szp]),
+        "dx_undexta_size_dev": (C.c_int, [vp, C.c_int, vp, sz, C.c_int, szp]),
         "dx_compress_reads_dev": (C.c_int, [vp, C.c_int, vp, vp, vp, i64, vp, vp]),
         "dx_uncompress_reads_dev": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, vp, i64, vp, vp]),
         "dx_qv_scan_dev": (C.c_int, [vp, vp, sz, C.POINTER(Carry), C.POINTER(Stats)]),

@@ -95,6 +95,8 @@ int dx_undexta_host(dx_ctx *ctx, int kind, const uint8_t *h_in, size_t n, int wi
 /* size of the text dx_undexta_* would produce (header walk only; no payload decode) */
 int dx_undexta_size_host(dx_ctx *ctx, int kind, const uint8_t *h_in, size_t n, int width,
                          size_t *out_len);
+int dx_undexta_size_dev (dx_ctx *ctx, int kind, const uint8_t *d_in, size_t n, int width,
+                         size_t *out_len);
 
 /* Batched in-memory form of the same codec for callers that already hold reads in memory
  * (the Dazzler DB loaders, DB.c:1279-1286, 1414-1432, 1533-1540, 1592-1600 and the dex2DB

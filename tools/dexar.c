@@ -1,0 +1,21 @@
+/* dexar -- .arrow -> .dexar (2 bits per pulse width).
+ * Same command line, flags and file format as the reference's dexar (dexar.c:19-66); the work is
+ * done by libdexb200.so on the GPU (see dxcli.h). */
+#include "dxcli.h"
+
+static int run(dx_ctx *ctx, const dx_opts *o, const uint8_t *d_in, size_t n,
+               uint8_t **d_out, size_t *out_len)
+{ size_t cap = n/3 + 200000;
+  (void) o;
+  *d_out = (uint8_t *) dx_device_alloc(ctx,cap);
+  if (*d_out == NULL) return DX_E_NOMEM;
+  return dx_dexta_dev(ctx,DX_ARROW,d_in,n,*d_out,cap,out_len);
+}
+
+int main(int argc, char *argv[])
+{ static const dx_tool tool =
+    { "dexar", "[-vk] ( -i | <path:arrow> ... )", "vki", 0, ".arrow", ".dexar",
+      { "      -i: source is on standard input.",
+        "      -k: do *not* remove the .arrow file on completion.", NULL, NULL, NULL }, run };
+  return dx_cli_main(&tool,argc,argv);
+}
