@@ -901,10 +901,47 @@ static void build_dec_tables(const dx_qv_coding *c, QvDecTables *t)
     }
 }
 
+// Two-level tables for the parallel decoder.  false if a table needs more sub-tables than fit
+// (then the sequential kernels of dx_qv_decode.cu take over).
+static bool build_dec_tables2(const dx_qv_coding *c, QvDecTables2 *t)
+{ memset(t,0,sizeof(*t));
+  for (int k = 0; k < 6; k++)
+    { const dx_scheme &s = c->tab[k];
+      int nsub = 0;
+      t->type[k] = s.type;
+      for (int i = 0; i < 256; i++)                       // ascending: 255 wins ties (QV.c:365-372)
+        { const int len = s.lens[i];
+          if (len <= 0 || len > 16) continue;
+          const uint16_t val = (uint16_t) (i | (len << 8));
+          if (len <= 11)
+            { const uint32_t base = (s.bits[i] << (11 - len)) & 0x7ffu;
+              for (uint32_t j = 0; j < (1u << (11 - len)); j++) t->prim[k][base + j] = val;
+            }
+          else
+            { const uint32_t pre = (s.bits[i] >> (len - 11)) & 0x7ffu;
+              uint16_t &pe = t->prim[k][pre];
+              if (!(pe & 0x8000u))
+                { if (nsub >= DX_DEC2_MAXSUB) return false;
+                  pe = (uint16_t) (0x8000u | nsub);
+                  nsub++;
+                }
+              const uint32_t idx = pe & 0x7fffu;
+              const uint32_t base = (s.bits[i] << (16 - len)) & 31u;
+              for (uint32_t j = 0; j < (1u << (16 - len)); j++) t->sub[k][idx*32 + base + j] = val;
+            }
+        }
+    }
+  return true;
+}
+
 struct QvPlan
 { std::vector<QvDecEntry> ent;
-  int64_t     *d_soff;        // [count][6] device
-  QvDecTables *d_tab;
+  bool         v2;            // parallel decoder usable
+  int64_t     *d_soff;        // v1 only: [count][6] device
+  int64_t     *d_start;       // v2: first stream byte of every entry
+  int32_t     *d_rlen;        // v2
+  QvDecTables  *d_tab;
+  QvDecTables2 *d_tab2;
   char        *d_prefix;
   int          plen;
   dx_qv_coding coding;
@@ -912,9 +949,21 @@ struct QvPlan
 };
 
 struct QvWalkUser
-{ const uint8_t *d_in; size_t n; const QvDecTables *d_tab; const dx_qv_coding *coding;
+{ const uint8_t *d_in; size_t n; const QvPlan *plan;
   std::vector<int64_t> side;           // 6 stream offsets per slow-path entry
 };
+
+// walk `count` entries whose first stream byte / length are on the device
+static int qv_walk(dx_ctx *ctx, const uint8_t *d_in, size_t n, const QvPlan &plan,
+                   const int64_t *d_start, const int32_t *d_rlen, int64_t count,
+                   int64_t *d_soff, int32_t *d_stat)
+{ const dx_qv_coding &cd = plan.coding;
+  if (plan.v2)
+    return dxk_qv_decode2(ctx,d_in,n,plan.d_tab2,cd.delchar,cd.subchar,0,0,count,d_start,d_rlen,
+                          NULL,NULL,0,NULL,d_soff,d_stat);
+  return dxk_qv_walk(ctx,d_in,n,plan.d_tab,cd.delchar,cd.subchar,cd.flip,d_start,d_rlen,count,
+                     d_soff,d_stat);
+}
 
 static int qv_walk_one(dx_ctx *ctx, void *user, int64_t q, int64_t *end, int64_t *slot)
 { QvWalkUser *u = (QvWalkUser *) user;
@@ -933,8 +982,7 @@ static int qv_walk_one(dx_ctx *ctx, void *user, int64_t q, int64_t *end, int64_t
   const int64_t start = q + 12;
   if ((rc = upload(ctx,d_start,&start,1)) != DX_OK) return rc;
   if ((rc = upload(ctx,d_rlen,&rlen,1)) != DX_OK) return rc;
-  if ((rc = dxk_qv_walk(ctx,u->d_in,u->n,u->d_tab,u->coding->delchar,u->coding->subchar,
-                        u->coding->flip,d_start,d_rlen,1,d_soff,d_stat)) != DX_OK) return rc;
+  if ((rc = qv_walk(ctx,u->d_in,u->n,*u->plan,d_start,d_rlen,1,d_soff,d_stat)) != DX_OK) return rc;
   std::vector<int64_t> so; std::vector<int32_t> stt;
   if ((rc = download(ctx,d_soff,6,so)) != DX_OK) return rc;
   if ((rc = download(ctx,d_stat,1,stt)) != DX_OK) return rc;
@@ -944,7 +992,7 @@ static int qv_walk_one(dx_ctx *ctx, void *user, int64_t q, int64_t *end, int64_t
 }
 
 static int plan_undexqv(dx_ctx *ctx, const uint8_t *d_in, size_t n, const int64_t *h_entry_off,
-                        int64_t nentries, QvPlan &plan)
+                        int64_t nentries, bool need_streams, QvPlan &plan)
 { int rc;
   std::vector<uint8_t> head;
   if ((rc = peek(ctx,d_in,n,0,2 + 16384 + 100000,head)) != DX_OK) return rc;
@@ -961,52 +1009,73 @@ static int plan_undexqv(dx_ctx *ctx, const uint8_t *d_in, size_t n, const int64_
     return dx_fail(ctx,DX_E_KEY,"foreign-endian .dexqv is not supported");
   const size_t first = 2 + used;
   plan.plen = (int) strlen(prefix.data());
+  plan.d_soff = NULL; plan.d_start = NULL; plan.d_rlen = NULL; plan.d_tab = NULL; plan.d_tab2 = NULL;
 
-  QvDecTables *h_tab = (QvDecTables *) malloc(sizeof(QvDecTables));
-  if (h_tab == NULL) return DX_E_NOMEM;
-  build_dec_tables(&plan.coding,h_tab);
-  plan.d_tab    = (QvDecTables *) dx_arena_get(ctx,sizeof(QvDecTables));
+  { QvDecTables2 *h2 = (QvDecTables2 *) malloc(sizeof(QvDecTables2));
+    if (h2 == NULL) return DX_E_NOMEM;
+    plan.v2 = build_dec_tables2(&plan.coding,h2);
+    { const char *force = getenv("DEXB200_DECODER");        // "v1": sequential kernels (testing)
+      if (force != NULL && strcmp(force,"v1") == 0) plan.v2 = false;
+    }
+    if (plan.v2)
+      { plan.d_tab2 = (QvDecTables2 *) dx_arena_get(ctx,sizeof(QvDecTables2));
+        rc = plan.d_tab2 ? upload(ctx,plan.d_tab2,h2,1) : DX_E_NOMEM;
+      }
+    free(h2);
+    if (rc != DX_OK) return rc;
+  }
+  if (!plan.v2)
+    { QvDecTables *h_tab = (QvDecTables *) malloc(sizeof(QvDecTables));
+      if (h_tab == NULL) return DX_E_NOMEM;
+      build_dec_tables(&plan.coding,h_tab);
+      plan.d_tab = (QvDecTables *) dx_arena_get(ctx,sizeof(QvDecTables));
+      rc = plan.d_tab ? upload(ctx,plan.d_tab,h_tab,1) : DX_E_NOMEM;
+      free(h_tab);
+      if (rc != DX_OK) return rc;
+    }
   plan.d_prefix = (char *) dx_arena_get(ctx,(size_t) plan.plen + 1);
-  if (!plan.d_tab || !plan.d_prefix) { free(h_tab); return DX_E_NOMEM; }
-  rc = upload(ctx,plan.d_tab,h_tab,1);
-  free(h_tab);
-  if (rc != DX_OK) return rc;
+  if (!plan.d_prefix) return DX_E_NOMEM;
   if ((rc = upload(ctx,plan.d_prefix,prefix.data(),(size_t) plan.plen)) != DX_OK) return rc;
 
   struct Hdr { int32_t well, beg, end, qv; };
   std::vector<Hdr> hdrs;
-  const dx_qv_coding &cd = plan.coding;
+  const bool want_soff = need_streams && !plan.v2;      // v1 decode kernel needs stream offsets
 
   if (h_entry_off != NULL)
     { // entry starts are known (our encoder's index, or Dazzler .idx coff, DB.c:2598)
       const size_t N = (size_t) nentries;
-      int64_t  *d_start = (int64_t *) dx_arena_get(ctx,N*8);
-      int64_t  *d_q     = (int64_t *) dx_arena_get(ctx,N*8);
-      int64_t  *d_fs    = (int64_t *) dx_arena_get(ctx,N*8);
-      int32_t  *d_rlen  = (int32_t *) dx_arena_get(ctx,N*4);
-      int32_t  *d_stat  = (int32_t *) dx_arena_get(ctx,N*4);
-      CandInfo *d_info  = (CandInfo *) dx_arena_get(ctx,N*sizeof(CandInfo));
-      plan.d_soff       = (int64_t *) dx_arena_get(ctx,N*48);
-      if (!d_start || !d_q || !d_fs || !d_rlen || !d_stat || !d_info || !plan.d_soff) return DX_E_NOMEM;
-      if ((rc = upload(ctx,d_start,h_entry_off,N)) != DX_OK) return rc;
-      if ((rc = dxk_skip_ff(ctx,d_in,n,d_start,(int64_t) N,d_q)) != DX_OK) return rc;
-      if ((rc = dxk_field_rlen(ctx,d_in,d_q,(int64_t) N,d_rlen)) != DX_OK) return rc;
+      int64_t  *d_estart = (int64_t *) dx_arena_get(ctx,N*8);
+      int64_t  *d_q      = (int64_t *) dx_arena_get(ctx,N*8);
+      CandInfo *d_info   = (CandInfo *) dx_arena_get(ctx,N*sizeof(CandInfo));
+      plan.d_start       = (int64_t *) dx_arena_get(ctx,N*8);
+      plan.d_rlen        = (int32_t *) dx_arena_get(ctx,N*4);
+      if (!d_estart || !d_q || !d_info || !plan.d_start || !plan.d_rlen) return DX_E_NOMEM;
+      if ((rc = upload(ctx,d_estart,h_entry_off,N)) != DX_OK) return rc;
+      if ((rc = dxk_skip_ff(ctx,d_in,n,d_estart,(int64_t) N,d_q)) != DX_OK) return rc;
+      if ((rc = dxk_field_rlen(ctx,d_in,d_q,(int64_t) N,plan.d_rlen)) != DX_OK) return rc;
       if ((rc = dxk_cand_context(ctx,d_in,n,first,d_q,(int64_t) N,12,d_info)) != DX_OK) return rc;
       std::vector<int64_t> q;
       if ((rc = download(ctx,d_q,N,q)) != DX_OK) return rc;
-      for (size_t i = 0; i < N; i++) q[i] += 12;
-      if ((rc = upload(ctx,d_fs,q.data(),N)) != DX_OK) return rc;
-      if ((rc = dxk_qv_walk(ctx,d_in,n,plan.d_tab,cd.delchar,cd.subchar,cd.flip,d_fs,d_rlen,
-                            (int64_t) N,plan.d_soff,d_stat)) != DX_OK) return rc;
+      std::vector<int64_t> fs(N);
+      for (size_t i = 0; i < N; i++) fs[i] = q[i] + 12;
+      if ((rc = upload(ctx,plan.d_start,fs.data(),N)) != DX_OK) return rc;
       std::vector<CandInfo> info;
-      std::vector<int32_t> stat;
       if ((rc = download(ctx,d_info,N,info)) != DX_OK) return rc;
-      if ((rc = download(ctx,d_stat,N,stat)) != DX_OK) return rc;
+      if (want_soff)
+        { int32_t *d_stat = (int32_t *) dx_arena_get(ctx,N*4);
+          plan.d_soff = (int64_t *) dx_arena_get(ctx,N*48);
+          if (!d_stat || !plan.d_soff) return DX_E_NOMEM;
+          if ((rc = qv_walk(ctx,d_in,n,plan,plan.d_start,plan.d_rlen,(int64_t) N,plan.d_soff,d_stat)) != DX_OK)
+            return rc;
+          std::vector<int32_t> stat;
+          if ((rc = download(ctx,d_stat,N,stat)) != DX_OK) return rc;
+          for (size_t i = 0; i < N; i++)
+            if (stat[i]) return dx_fail(ctx,DX_E_TRUNC,"Could not read more bits (Decode), entry %zu",i+1);
+        }
       int32_t well = 0;
       hdrs.resize(N);
       for (size_t i = 0; i < N; i++)
-        { if (stat[i]) return dx_fail(ctx,DX_E_TRUNC,"Could not read more bits (Decode), entry %zu",i+1);
-          well += 255 * (int32_t) (q[i] - 13 - h_entry_off[i]) + info[i].last;
+        { well += 255 * (int32_t) (q[i] - 1 - h_entry_off[i]) + info[i].last;
           hdrs[i].well = well;
           hdrs[i].beg = le32(info[i].field); hdrs[i].end = le32(info[i].field+4);
           hdrs[i].qv  = le32(info[i].field+8);
@@ -1029,8 +1098,7 @@ static int plan_undexqv(dx_ctx *ctx, const uint8_t *d_in, size_t n, const int64_
       fs.resize(N);
       for (size_t i = 0; i < N; i++) fs[i] = q[i] + 12;
       if ((rc = upload(ctx,d_fs,fs.data(),N)) != DX_OK) return rc;
-      if ((rc = dxk_qv_walk(ctx,d_in,n,plan.d_tab,cd.delchar,cd.subchar,cd.flip,d_fs,d_rlen,nc,
-                            d_soffc,d_stat)) != DX_OK) return rc;
+      if ((rc = qv_walk(ctx,d_in,n,plan,d_fs,d_rlen,nc,d_soffc,d_stat)) != DX_OK) return rc;
       std::vector<int64_t> soff;
       std::vector<int32_t> stat;
       std::vector<CandInfo> info;
@@ -1039,12 +1107,13 @@ static int plan_undexqv(dx_ctx *ctx, const uint8_t *d_in, size_t n, const int64_
       if ((rc = download(ctx,d_info,N,info)) != DX_OK) return rc;
       std::vector<int64_t> end(N);
       for (size_t i = 0; i < N; i++) end[i] = stat[i] ? -1 : soff[6*i+5];
-      QvWalkUser user = { d_in, n, plan.d_tab, &plan.coding, {} };
+      QvWalkUser user = { d_in, n, &plan, {} };
       std::vector<ChainEntry> chain;
       if ((rc = resolve_chain(ctx,d_in,n,first,12,q,end,info,qv_walk_one,&user,chain)) != DX_OK)
         return rc;
       const size_t M = chain.size();
-      std::vector<int64_t> so(M*6);
+      std::vector<int64_t> so(M*6), st(M);
+      std::vector<int32_t> rl(M);
       hdrs.resize(M);
       for (size_t i = 0; i < M; i++)
         { const ChainEntry &c = chain[i];
@@ -1053,10 +1122,21 @@ static int plan_undexqv(dx_ctx *ctx, const uint8_t *d_in, size_t n, const int64_
           memcpy(&so[6*i],src,48);
           hdrs[i].well = c.well;
           hdrs[i].beg = le32(c.field); hdrs[i].end = le32(c.field+4); hdrs[i].qv = le32(c.field+8);
+          st[i] = c.q + 12;
+          rl[i] = hdrs[i].end - hdrs[i].beg;
         }
-      plan.d_soff = (int64_t *) dx_arena_get(ctx,M*48);
-      if (!plan.d_soff) return DX_E_NOMEM;
-      if ((rc = upload(ctx,plan.d_soff,so.data(),M*6)) != DX_OK) return rc;
+      if (need_streams)
+        { plan.d_start = (int64_t *) dx_arena_get(ctx,M*8);
+          plan.d_rlen  = (int32_t *) dx_arena_get(ctx,M*4);
+          if (!plan.d_start || !plan.d_rlen) return DX_E_NOMEM;
+          if ((rc = upload(ctx,plan.d_start,st.data(),M)) != DX_OK) return rc;
+          if ((rc = upload(ctx,plan.d_rlen,rl.data(),M)) != DX_OK) return rc;
+          if (want_soff)
+            { plan.d_soff = (int64_t *) dx_arena_get(ctx,M*48);
+              if (!plan.d_soff) return DX_E_NOMEM;
+              if ((rc = upload(ctx,plan.d_soff,so.data(),M*6)) != DX_OK) return rc;
+            }
+        }
     }
 
   // output layout (undexqv.c:182, 206-207)
@@ -1071,7 +1151,8 @@ static int plan_undexqv(dx_ctx *ctx, const uint8_t *d_in, size_t n, const int64_
           + 6 + ndigits(h.qv) + 1;
       d.text_off = (int64_t) at;
       const int64_t rlen = (int64_t) h.end - h.beg;
-      if (rlen < 0) return dx_fail(ctx,DX_E_FORMAT,"negative read length in entry header");
+      if (rlen < 0 || rlen >= (1 << 24))
+        return dx_fail(ctx,DX_E_FORMAT,"unusable read length %lld in entry header",(long long) rlen);
       at += (size_t) (5*(rlen + 1));
     }
   plan.text_len = at;
@@ -1088,7 +1169,7 @@ extern "C" int dx_undexqv_dev(dx_ctx *ctx, const uint8_t *d_in, size_t n, int up
   cudaSetDevice(ctx->device);
   dx_arena_reset(ctx);
   QvPlan plan;
-  if ((rc = plan_undexqv(ctx,d_in,n,h_entry_off,nentries,plan)) != DX_OK) return rc;
+  if ((rc = plan_undexqv(ctx,d_in,n,h_entry_off,nentries,true,plan)) != DX_OK) return rc;
   if (plan.text_len > cap)
     return dx_fail(ctx,DX_E_CAP,"output needs %zu bytes, buffer has %zu",plan.text_len,cap);
   const size_t N = plan.ent.size();
@@ -1097,9 +1178,14 @@ extern "C" int dx_undexqv_dev(dx_ctx *ctx, const uint8_t *d_in, size_t n, int up
   if (!d_ent || !d_stat) return DX_E_NOMEM;
   if ((rc = upload(ctx,d_ent,plan.ent.data(),N)) != DX_OK) return rc;
   DX_CUDA(ctx,cudaMemsetAsync(d_stat,0,4,ctx->stream));
-  if ((rc = dxk_qv_decode(ctx,d_in,n,plan.d_tab,plan.coding.delchar,plan.coding.subchar,
-                          plan.coding.flip,upper,d_ent,plan.d_soff,(int64_t) N,plan.d_prefix,plan.plen,
-                          d_out,d_stat)) != DX_OK) return rc;
+  const dx_qv_coding &cd = plan.coding;
+  if (plan.v2)
+    rc = dxk_qv_decode2(ctx,d_in,n,plan.d_tab2,cd.delchar,cd.subchar,upper,1,(int64_t) N,
+                        plan.d_start,plan.d_rlen,d_ent,plan.d_prefix,plan.plen,d_out,NULL,d_stat);
+  else
+    rc = dxk_qv_decode(ctx,d_in,n,plan.d_tab,cd.delchar,cd.subchar,cd.flip,upper,d_ent,plan.d_soff,
+                       (int64_t) N,plan.d_prefix,plan.plen,d_out,d_stat);
+  if (rc != DX_OK) return rc;
   int32_t stat = 0;
   DX_CUDA(ctx,cudaMemcpyAsync(&stat,d_stat,4,cudaMemcpyDeviceToHost,ctx->stream));
   DX_CUDA(ctx,cudaStreamSynchronize(ctx->stream));
@@ -1116,7 +1202,7 @@ extern "C" int dx_undexqv_size_dev(dx_ctx *ctx, const uint8_t *d_in, size_t n, s
   cudaSetDevice(ctx->device);
   dx_arena_reset(ctx);
   QvPlan plan;
-  if ((rc = plan_undexqv(ctx,d_in,n,NULL,0,plan)) != DX_OK) return rc;
+  if ((rc = plan_undexqv(ctx,d_in,n,NULL,0,false,plan)) != DX_OK) return rc;
   *out_len = plan.text_len;
   return DX_OK;
 }

@@ -42,6 +42,16 @@ struct QvDecTables
   int32_t type[6];
 };
 
+// Compact two-level decode tables for the parallel decoder (dx_qv_decode2.cu): the top 11 bits of
+// the 16-bit window index prim; codes longer than 11 bits go through a 32-entry sub-table.
+// entry = symbol | length << 8 ; bit 15 of a prim entry = "low 15 bits are a sub-table index".
+#define DX_DEC2_MAXSUB 64
+struct QvDecTables2
+{ uint16_t prim[6][2048];
+  uint16_t sub[6][DX_DEC2_MAXSUB*32];
+  int32_t  type[6];
+};
+
 // ---- context --------------------------------------------------------------------------------
 
 struct DxBlock { uint8_t *p; size_t cap, top; };
@@ -133,6 +143,13 @@ int dxk_qv_decode(dx_ctx *ctx, const uint8_t *d_in, size_t n, const QvDecTables 
                   int delchar, int subchar, int flip, int upper, const QvDecEntry *d_ent,
                   const int64_t *d_soff, int64_t count, const char *d_prefix, int plen,
                   uint8_t *d_out, int32_t *d_status /*[1]*/);
+
+// dx_qv_decode2.cu : one CTA per entry, speculative parallel decoding inside every stream.
+// write = 0: only walk (d_soff[count][6], d_status[count]); write = 1: produce the text.
+int dxk_qv_decode2(dx_ctx *ctx, const uint8_t *d_in, size_t n, const QvDecTables2 *d_tab,
+                   int delchar, int subchar, int upper, int write, int64_t count,
+                   const int64_t *d_start, const int32_t *d_rlen, const QvDecEntry *d_ent,
+                   const char *d_prefix, int plen, uint8_t *d_out, int64_t *d_soff, int32_t *d_status);
 
 // dx_pack.cu : .fasta/.arrow <-> 2-bit images
 struct FaEntries                // one fasta/arrow entry (structure of arrays in HBM)
