@@ -252,18 +252,18 @@ def main():
         body, lastw_out, offs = ctx.qv_encode_dev(text.data_ptr(), U, cd, False, lwell_in,
                                                   enc.data_ptr() + hl, enc.numel() - hl,
                                                   want_offsets=nent)
-        state.update(hdr=hdr, img_len=hl + body, offs=offs + hl)
+        state.update(hdr=hdr, img_len=hl + body, offs=offs + hl, lwell_in=lwell_in)
         return hl + body
 
     def decode_known():
         m = ctx.undexqv_dev(enc.data_ptr(), state["img_len"], False, back.data_ptr(), back.numel(),
-                            entry_off=state["offs"])
+                            entry_off=state["offs"], well_in=state["lwell_in"])
         state["out_len"] = m
         return m
 
     def decode_discover():
         return ctx.undexqv_dev(enc.data_ptr(), state["img_len"], False, back.data_ptr(),
-                               back.numel())
+                               back.numel(), well_in=state["lwell_in"])
 
     def full_step():
         step_device()

@@ -992,7 +992,7 @@ static int qv_walk_one(dx_ctx *ctx, void *user, int64_t q, int64_t *end, int64_t
 }
 
 static int plan_undexqv(dx_ctx *ctx, const uint8_t *d_in, size_t n, const int64_t *h_entry_off,
-                        int64_t nentries, bool need_streams, QvPlan &plan)
+                        int64_t nentries, int32_t well_in, bool need_streams, QvPlan &plan)
 { int rc;
   std::vector<uint8_t> head;
   if ((rc = peek(ctx,d_in,n,0,2 + 16384 + 100000,head)) != DX_OK) return rc;
@@ -1072,7 +1072,7 @@ static int plan_undexqv(dx_ctx *ctx, const uint8_t *d_in, size_t n, const int64_
           for (size_t i = 0; i < N; i++)
             if (stat[i]) return dx_fail(ctx,DX_E_TRUNC,"Could not read more bits (Decode), entry %zu",i+1);
         }
-      int32_t well = 0;
+      int32_t well = well_in;
       hdrs.resize(N);
       for (size_t i = 0; i < N; i++)
         { well += 255 * (int32_t) (q[i] - 1 - h_entry_off[i]) + info[i].last;
@@ -1120,7 +1120,7 @@ static int plan_undexqv(dx_ctx *ctx, const uint8_t *d_in, size_t n, const int64_
           const int64_t *src = (c.cand >= 0) ? &soff[6*(size_t) c.cand]
                                              : &user.side[6*(size_t) (-2 - c.cand)];
           memcpy(&so[6*i],src,48);
-          hdrs[i].well = c.well;
+          hdrs[i].well = c.well + well_in;
           hdrs[i].beg = le32(c.field); hdrs[i].end = le32(c.field+4); hdrs[i].qv = le32(c.field+8);
           st[i] = c.q + 12;
           rl[i] = hdrs[i].end - hdrs[i].beg;
@@ -1161,7 +1161,7 @@ static int plan_undexqv(dx_ctx *ctx, const uint8_t *d_in, size_t n, const int64_
 
 extern "C" int dx_undexqv_dev(dx_ctx *ctx, const uint8_t *d_in, size_t n, int upper,
                               uint8_t *d_out, size_t cap, size_t *out_len,
-                              const int64_t *h_entry_off, int64_t nentries)
+                              const int64_t *h_entry_off, int64_t nentries, int32_t well_in)
 { if (ctx == NULL || out_len == NULL) return DX_E_ARG;
   int rc;
   *out_len = 0;
@@ -1169,7 +1169,7 @@ extern "C" int dx_undexqv_dev(dx_ctx *ctx, const uint8_t *d_in, size_t n, int up
   cudaSetDevice(ctx->device);
   dx_arena_reset(ctx);
   QvPlan plan;
-  if ((rc = plan_undexqv(ctx,d_in,n,h_entry_off,nentries,true,plan)) != DX_OK) return rc;
+  if ((rc = plan_undexqv(ctx,d_in,n,h_entry_off,nentries,well_in,true,plan)) != DX_OK) return rc;
   if (plan.text_len > cap)
     return dx_fail(ctx,DX_E_CAP,"output needs %zu bytes, buffer has %zu",plan.text_len,cap);
   const size_t N = plan.ent.size();
@@ -1202,7 +1202,7 @@ extern "C" int dx_undexqv_size_dev(dx_ctx *ctx, const uint8_t *d_in, size_t n, s
   cudaSetDevice(ctx->device);
   dx_arena_reset(ctx);
   QvPlan plan;
-  if ((rc = plan_undexqv(ctx,d_in,n,NULL,0,false,plan)) != DX_OK) return rc;
+  if ((rc = plan_undexqv(ctx,d_in,n,NULL,0,0,false,plan)) != DX_OK) return rc;
   *out_len = plan.text_len;
   return DX_OK;
 }
@@ -1275,6 +1275,6 @@ extern "C" int dx_undexqv_host(dx_ctx *ctx, const uint8_t *h_in, size_t n, int u
   int rc;
   if ((rc = stage_in(ctx,h_in,n)) != DX_OK) return rc;
   if ((rc = ensure_io(ctx,&ctx->io_out,&ctx->io_out_cap,cap)) != DX_OK) return rc;
-  if ((rc = dx_undexqv_dev(ctx,ctx->io_in,n,upper,ctx->io_out,cap,out_len,NULL,0)) != DX_OK) return rc;
+  if ((rc = dx_undexqv_dev(ctx,ctx->io_in,n,upper,ctx->io_out,cap,out_len,NULL,0,0)) != DX_OK) return rc;
   return stage_out(ctx,h_out,*out_len);
 }

@@ -19,6 +19,8 @@
 //   4. every thread decodes its subsequence once more, now writing text.
 // Speculation only costs time: nothing is written before the fix point is reached.
 
+#include <stdio.h>
+#include <stdlib.h>
 #include "dx_internal.h"
 #include "dx_common.cuh"
 
@@ -43,6 +45,7 @@ struct Dec2Args
   int64_t       *soff;         // [count][6] or NULL
   int32_t       *status;       // [count] (walk) or [1] (decode)
   unsigned long long *ticket;
+  unsigned long long *dbg;     // optional counters: [kind][0 rounds, 1 windows, 2 streams]
 };
 
 // ---- bit reader over 32-bit words at an arbitrary byte address --------------------------------
@@ -268,8 +271,10 @@ __device__ uint32_t decode_stream(const Dec2Args &a, Shared &sm, int64_t so, int
               sm.exit_pos[t] = s.exit_pos; sm.exit_par[t] = s.exit_par;
               changed = 1;
             }
+          if (a.dbg != NULL && t == 0) atomicAdd(&a.dbg[symtab*4],1ull);
           if (!__syncthreads_or(changed)) break;
         }
+      if (a.dbg != NULL && t == 0) atomicAdd(&a.dbg[symtab*4+1],1ull);
 
       // place the subsequences: exclusive scan of symbol counts
       uint32_t total;
@@ -327,6 +332,7 @@ __device__ uint32_t decode_stream(const Dec2Args &a, Shared &sm, int64_t so, int
           break;
         }
     }
+  if (a.dbg != NULL && t == 0) atomicAdd(&a.dbg[symtab*4+2],1ull);
   if (dst != NULL && t == 0) dst[rlen] = '\n';
   *kept = kept_total;
   return words*4u;
@@ -461,9 +467,24 @@ int dxk_qv_decode2(dx_ctx *ctx, const uint8_t *d_in, size_t n, const QvDecTables
   a.count = count; a.start = d_start; a.rlen = d_rlen; a.ent = d_ent;
   a.prefix = d_prefix; a.plen = plen; a.out = d_out; a.soff = d_soff; a.status = d_status;
   a.ticket = d_ticket;
+  a.dbg = NULL;
+  if (getenv("DEXB200_DEBUG") != NULL)
+    { a.dbg = (unsigned long long *) dx_arena_get(ctx,32*8);
+      if (a.dbg == NULL) return DX_E_NOMEM;
+      DX_CUDA(ctx,cudaMemsetAsync(a.dbg,0,32*8,ctx->stream));
+    }
   int64_t grid = (int64_t) ctx->sm_count * 6;
   if (grid > count) grid = count;
   DX_PROF_BEGIN(ctx); k_qv_decode2<<<(unsigned) grid,kThreads,0,ctx->stream>>>(a);
   DX_LAUNCHED(ctx,write ? "k_qv_decode2" : "k_qv_walk2");
+  if (a.dbg != NULL)
+    { unsigned long long h[32];
+      DX_CUDA(ctx,cudaMemcpyAsync(h,a.dbg,sizeof(h),cudaMemcpyDeviceToHost,ctx->stream));
+      DX_CUDA(ctx,cudaStreamSynchronize(ctx->stream));
+      for (int k = 0; k < 5; k++)
+        if (h[k*4+2])
+          fprintf(stderr,"[dexb200 debug] table %d: streams %llu windows/stream %.2f sync rounds/window %.2f\n",
+                  k,h[k*4+2],(double) h[k*4+1]/h[k*4+2],(double) h[k*4]/(h[k*4+1] ? h[k*4+1] : 1));
+    }
   return DX_OK;
 }

@@ -110,7 +110,7 @@ def load_library():
                                        C.POINTER(i32), vp, i64]),
         "dx_dexqv_dev": (C.c_int, [vp, vp, sz, C.c_int, vp, sz, szp]),
         "dx_dexqv_host": (C.c_int, [vp, vp, sz, C.c_int, vp, sz, szp]),
-        "dx_undexqv_dev": (C.c_int, [vp, vp, sz, C.c_int, vp, sz, szp, vp, i64]),
+        "dx_undexqv_dev": (C.c_int, [vp, vp, sz, C.c_int, vp, sz, szp, vp, i64, i32]),
         "dx_undexqv_host": (C.c_int, [vp, vp, sz, C.c_int, vp, sz, szp]),
         "dx_undexqv_size_dev": (C.c_int, [vp, vp, sz, szp]),
     }
@@ -290,15 +290,16 @@ class Context:
         self._check(self.L.dx_dexqv_dev(self.h, d_text, n, int(lossy), d_out, cap, C.byref(m)))
         return m.value
 
-    def undexqv_dev(self, d_in, n, upper, d_out, cap, entry_off: np.ndarray | None = None) -> int:
+    def undexqv_dev(self, d_in, n, upper, d_out, cap, entry_off: np.ndarray | None = None,
+                    well_in: int = 0) -> int:
         m = C.c_size_t(0)
         if entry_off is not None:
             entry_off = np.ascontiguousarray(entry_off, dtype=np.int64)
             self._check(self.L.dx_undexqv_dev(self.h, d_in, n, int(upper), d_out, cap, C.byref(m),
-                                              entry_off.ctypes.data, len(entry_off) - 1))
+                                              entry_off.ctypes.data, len(entry_off) - 1, well_in))
         else:
             self._check(self.L.dx_undexqv_dev(self.h, d_in, n, int(upper), d_out, cap, C.byref(m),
-                                              None, 0))
+                                              None, 0, well_in))
         return m.value
 
     def undexqv_size_dev(self, d_in, n) -> int:

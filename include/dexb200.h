@@ -185,10 +185,13 @@ int dx_dexqv_host(dx_ctx *ctx, const uint8_t *h_text, size_t n, int lossy,
 /* Replaces undexqv.c:99-208 with Uncompress_Next_QVentry (QV.c:1428-1481) over the whole file.
  * The file stores no entry lengths, so entry starts are first recovered on the device
  * (candidate headers + verified chain walk); pass h_entry_off/nentries (from dx_qv_encode_dev or
- * a Dazzler .idx, DB.c:2598) to skip that pass.  Offsets are relative to d_in. */
+ * a Dazzler .idx, DB.c:2598) to skip that pass.  Offsets are relative to d_in.
+ * well_in is the well number of the entry preceding this image (0 for a whole file; for a shard
+ * [header][entries of shard r] it is the last well of shard r-1, the decode-side twin of
+ * lwell_in above). */
 int dx_undexqv_dev (dx_ctx *ctx, const uint8_t *d_in, size_t n, int upper,
                     uint8_t *d_out, size_t cap, size_t *out_len,
-                    const int64_t *h_entry_off, int64_t nentries);
+                    const int64_t *h_entry_off, int64_t nentries, int32_t well_in);
 int dx_undexqv_host(dx_ctx *ctx, const uint8_t *h_in, size_t n, int upper,
                     uint8_t *h_out, size_t cap, size_t *out_len);
 /* size of the .quiva text dx_undexqv_* would produce for this file */

@@ -45,6 +45,8 @@ def test_product_never_imports_oracle():
                 if re.search(r"oracle|dx_oracle|libdxoracle|_ref/", txt):
                     bad.append(f)
     for f in os.listdir(os.path.join(ROOT, "tools")):
+        if not os.path.isfile(os.path.join(ROOT, "tools", f)):
+            continue
         txt = open(os.path.join(ROOT, "tools", f), errors="replace").read()
         if re.search(r"oracle|dx_oracle|libdxoracle", txt):
             bad.append(f)

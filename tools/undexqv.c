@@ -10,7 +10,7 @@ static int run(dx_ctx *ctx, const dx_opts *o, const uint8_t *d_in, size_t n,
   if (rc != DX_OK) return rc;
   *d_out = (uint8_t *) dx_device_alloc(ctx,cap + 64);
   if (*d_out == NULL) return DX_E_NOMEM;
-  return dx_undexqv_dev(ctx,d_in,n,o->upper,*d_out,cap + 64,out_len,NULL,0);
+  return dx_undexqv_dev(ctx,d_in,n,o->upper,*d_out,cap + 64,out_len,NULL,0,0);
 }
 
 int main(int argc, char *argv[])
