@@ -937,6 +937,7 @@ static bool build_dec_tables2(const dx_qv_coding *c, QvDecTables2 *t)
 struct QvPlan
 { std::vector<QvDecEntry> ent;
   bool         v2;            // parallel decoder usable
+  bool         v3;            // ... and the third-generation kernel is selected (default)
   int64_t     *d_soff;        // v1 only: [count][6] device
   int64_t     *d_start;       // v2: first stream byte of every entry
   int32_t     *d_rlen;        // v2
@@ -959,8 +960,8 @@ static int qv_walk(dx_ctx *ctx, const uint8_t *d_in, size_t n, const QvPlan &pla
                    int64_t *d_soff, int32_t *d_stat)
 { const dx_qv_coding &cd = plan.coding;
   if (plan.v2)
-    return dxk_qv_decode2(ctx,d_in,n,plan.d_tab2,cd.delchar,cd.subchar,0,0,count,d_start,d_rlen,
-                          NULL,NULL,0,NULL,d_soff,d_stat);
+    return (plan.v3 ? dxk_qv_decode3 : dxk_qv_decode2)(ctx,d_in,n,plan.d_tab2,cd.delchar,cd.subchar,
+                          0,0,count,d_start,d_rlen,NULL,NULL,0,NULL,d_soff,d_stat);
   return dxk_qv_walk(ctx,d_in,n,plan.d_tab,cd.delchar,cd.subchar,cd.flip,d_start,d_rlen,count,
                      d_soff,d_stat);
 }
@@ -1016,6 +1017,7 @@ static int plan_undexqv(dx_ctx *ctx, const uint8_t *d_in, size_t n, const int64_
     plan.v2 = build_dec_tables2(&plan.coding,h2);
     { const char *force = getenv("DEXB200_DECODER");        // "v1": sequential kernels (testing)
       if (force != NULL && strcmp(force,"v1") == 0) plan.v2 = false;
+      plan.v3 = !(force != NULL && strcmp(force,"v2") == 0);
     }
     if (plan.v2)
       { plan.d_tab2 = (QvDecTables2 *) dx_arena_get(ctx,sizeof(QvDecTables2));
@@ -1180,8 +1182,9 @@ extern "C" int dx_undexqv_dev(dx_ctx *ctx, const uint8_t *d_in, size_t n, int up
   DX_CUDA(ctx,cudaMemsetAsync(d_stat,0,4,ctx->stream));
   const dx_qv_coding &cd = plan.coding;
   if (plan.v2)
-    rc = dxk_qv_decode2(ctx,d_in,n,plan.d_tab2,cd.delchar,cd.subchar,upper,1,(int64_t) N,
-                        plan.d_start,plan.d_rlen,d_ent,plan.d_prefix,plan.plen,d_out,NULL,d_stat);
+    rc = (plan.v3 ? dxk_qv_decode3 : dxk_qv_decode2)(ctx,d_in,n,plan.d_tab2,cd.delchar,cd.subchar,
+                        upper,1,(int64_t) N,plan.d_start,plan.d_rlen,d_ent,plan.d_prefix,plan.plen,
+                        d_out,NULL,d_stat);
   else
     rc = dxk_qv_decode(ctx,d_in,n,plan.d_tab,cd.delchar,cd.subchar,cd.flip,upper,d_ent,plan.d_soff,
                        (int64_t) N,plan.d_prefix,plan.plen,d_out,d_stat);
