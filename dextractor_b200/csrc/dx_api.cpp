@@ -934,10 +934,68 @@ static bool build_dec_tables2(const dx_qv_coding *c, QvDecTables2 *t)
   return true;
 }
 
+// 12-bit shared-memory tables for dx_qv_decode4.cu, derived from the reference's 16-bit LUT
+// (build_dec_tables) so that ties resolve exactly as in QV.c:365-372.
+static bool build_dec_tables4(const dx_qv_coding *c, QvDecTables4 *t)
+{ memset(t,0,sizeof(*t));
+  if (!build_dec_tables2(c,&t->t2)) return false;
+  QvDecTables *full = (QvDecTables *) malloc(sizeof(QvDecTables));
+  if (full == NULL) return false;
+  build_dec_tables(c,full);
+  double ab[6], erun[6];
+  for (int k = 0; k < 6; k++)
+    { const dx_scheme &s = c->tab[k];
+      const bool isrun = (k == 1 || k == 5);
+      auto first = [&](uint32_t w16, int &sym, int &len) -> bool
+        { sym = full->look[k][w16]; len = s.lens[sym];
+          if (len <= 0 || len > 16) return false;
+          return (w16 >> (16 - len)) == (s.bits[sym] & ((1u << len) - 1u));
+        };
+      for (uint32_t p = 0; p < 4096; p++)
+        { int s0, l0;
+          if (!first(p << 4,s0,l0) || l0 > 12) continue;
+          t->single[k][p] = (uint16_t) (s0 | (l0 << 8));
+          if (isrun) continue;
+          if (s.type == 2 && s0 == 255)
+            { t->multi[k][p] = (uint32_t) (l0 + 8) | (1u << 5) | 0x80u | ((uint32_t) l0 << 8) | (255u << 16);
+              continue;
+            }
+          int s1 = 0, l1 = 0;
+          const bool two = (l0 < 12) && first(((p << l0) & 0xfffu) << 4,s1,l1) && l1 <= 12 - l0 &&
+                           !(s.type == 2 && s1 == 255);
+          if (two)
+            t->multi[k][p] = (uint32_t) (l0 + l1) | (2u << 5) | ((uint32_t) l0 << 8) |
+                             ((uint32_t) s0 << 16) | ((uint32_t) s1 << 24);
+          else
+            t->multi[k][p] = (uint32_t) l0 | (1u << 5) | ((uint32_t) l0 << 8) | ((uint32_t) s0 << 16);
+        }
+      // expected bits per item (and expected run length) under the code's own distribution
+      ab[k] = 0; erun[k] = 0;
+      for (int i = 0; i < 256; i++)
+        { const int len = s.lens[i];
+          if (len <= 0 || len > 16) continue;
+          const bool folded = (i < 255 && s.lens[255] == len && s.bits[255] == s.bits[i] &&
+                               (isrun || s.type == 2));
+          if (folded) continue;
+          const bool escape = (i == 255) && (isrun || s.type == 2);
+          const double q = 1.0 / (double) (1u << len);
+          ab[k]   += q * (len + (escape ? (isrun ? 16 : 8) : 0));
+          erun[k] += q * (escape ? 400.0 : (double) i);
+        }
+    }
+  free(full);
+  t->abits[0] = (float) (c->delchar >= 0 ? (ab[0] + ab[1]) / (erun[1] + 1.0) : ab[0]);
+  t->abits[2] = (float) ab[2];
+  t->abits[3] = (float) ab[3];
+  t->abits[4] = (float) (c->subchar >= 0 ? (ab[4] + ab[5]) / (erun[5] + 1.0) : ab[4]);
+  return true;
+}
+
 struct QvPlan
 { std::vector<QvDecEntry> ent;
   bool         v2;            // parallel decoder usable
-  bool         v3;            // ... and the third-generation kernel is selected (default)
+  int          ver;           // which parallel kernel: 2, 3 or 4 (default)
+  QvDecTables4 *d_tab4;
   int64_t     *d_soff;        // v1 only: [count][6] device
   int64_t     *d_start;       // v2: first stream byte of every entry
   int32_t     *d_rlen;        // v2
@@ -959,8 +1017,11 @@ static int qv_walk(dx_ctx *ctx, const uint8_t *d_in, size_t n, const QvPlan &pla
                    const int64_t *d_start, const int32_t *d_rlen, int64_t count,
                    int64_t *d_soff, int32_t *d_stat)
 { const dx_qv_coding &cd = plan.coding;
+  if (plan.v2 && plan.ver == 4)
+    return dxk_qv_decode4(ctx,d_in,n,plan.d_tab4,cd.delchar,cd.subchar,0,0,count,d_start,d_rlen,
+                          NULL,NULL,0,NULL,d_soff,d_stat);
   if (plan.v2)
-    return (plan.v3 ? dxk_qv_decode3 : dxk_qv_decode2)(ctx,d_in,n,plan.d_tab2,cd.delchar,cd.subchar,
+    return (plan.ver == 3 ? dxk_qv_decode3 : dxk_qv_decode2)(ctx,d_in,n,plan.d_tab2,cd.delchar,cd.subchar,
                           0,0,count,d_start,d_rlen,NULL,NULL,0,NULL,d_soff,d_stat);
   return dxk_qv_walk(ctx,d_in,n,plan.d_tab,cd.delchar,cd.subchar,cd.flip,d_start,d_rlen,count,
                      d_soff,d_stat);
@@ -1017,9 +1078,24 @@ static int plan_undexqv(dx_ctx *ctx, const uint8_t *d_in, size_t n, const int64_
     plan.v2 = build_dec_tables2(&plan.coding,h2);
     { const char *force = getenv("DEXB200_DECODER");        // "v1": sequential kernels (testing)
       if (force != NULL && strcmp(force,"v1") == 0) plan.v2 = false;
-      plan.v3 = !(force != NULL && strcmp(force,"v2") == 0);
+      plan.ver = 4;
+      if (force != NULL && strcmp(force,"v2") == 0) plan.ver = 2;
+      if (force != NULL && strcmp(force,"v3") == 0) plan.ver = 3;
     }
-    if (plan.v2)
+    plan.d_tab4 = NULL;
+    if (plan.v2 && plan.ver == 4)
+      { QvDecTables4 *h4 = (QvDecTables4 *) malloc(sizeof(QvDecTables4));
+        if (h4 == NULL) { free(h2); return DX_E_NOMEM; }
+        if (build_dec_tables4(&plan.coding,h4))
+          { plan.d_tab4 = (QvDecTables4 *) dx_arena_get(ctx,sizeof(QvDecTables4));
+            rc = plan.d_tab4 ? upload(ctx,plan.d_tab4,h4,1) : DX_E_NOMEM;
+          }
+        else
+          plan.ver = 3;
+        free(h4);
+        if (rc != DX_OK) { free(h2); return rc; }
+      }
+    if (plan.v2 && plan.ver != 4)
       { plan.d_tab2 = (QvDecTables2 *) dx_arena_get(ctx,sizeof(QvDecTables2));
         rc = plan.d_tab2 ? upload(ctx,plan.d_tab2,h2,1) : DX_E_NOMEM;
       }
@@ -1181,8 +1257,11 @@ extern "C" int dx_undexqv_dev(dx_ctx *ctx, const uint8_t *d_in, size_t n, int up
   if ((rc = upload(ctx,d_ent,plan.ent.data(),N)) != DX_OK) return rc;
   DX_CUDA(ctx,cudaMemsetAsync(d_stat,0,4,ctx->stream));
   const dx_qv_coding &cd = plan.coding;
-  if (plan.v2)
-    rc = (plan.v3 ? dxk_qv_decode3 : dxk_qv_decode2)(ctx,d_in,n,plan.d_tab2,cd.delchar,cd.subchar,
+  if (plan.v2 && plan.ver == 4)
+    rc = dxk_qv_decode4(ctx,d_in,n,plan.d_tab4,cd.delchar,cd.subchar,upper,1,(int64_t) N,
+                        plan.d_start,plan.d_rlen,d_ent,plan.d_prefix,plan.plen,d_out,NULL,d_stat);
+  else if (plan.v2)
+    rc = (plan.ver == 3 ? dxk_qv_decode3 : dxk_qv_decode2)(ctx,d_in,n,plan.d_tab2,cd.delchar,cd.subchar,
                         upper,1,(int64_t) N,plan.d_start,plan.d_rlen,d_ent,plan.d_prefix,plan.plen,
                         d_out,NULL,d_stat);
   else

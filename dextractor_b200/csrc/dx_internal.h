@@ -52,6 +52,18 @@ struct QvDecTables2
   int32_t  type[6];
 };
 
+// Tables of the fourth-generation decoder (dx_qv_decode4.cu): 12-bit primary tables that are copied
+// to shared memory per stream.  multi: plain streams, up to two symbols per entry (bits 0-4 total
+// length incl. the 8 literal bits of an escape, 5-6 symbol count, bit 7 escape, 8-12 length of the
+// first code, 16-23 / 24-31 the symbols); single: sym | len << 8.  0 = code longer than 12 bits
+// (or no code): look in t2.  abits: predicted stream bits per output position.
+struct QvDecTables4
+{ uint32_t multi[6][4096];
+  uint16_t single[6][4096];
+  float    abits[6];
+  QvDecTables2 t2;
+};
+
 // ---- context --------------------------------------------------------------------------------
 
 struct DxBlock { uint8_t *p; size_t cap, top; };
@@ -153,6 +165,11 @@ int dxk_qv_decode2(dx_ctx *ctx, const uint8_t *d_in, size_t n, const QvDecTables
 
 // dx_qv_decode3.cu : same contract as dxk_qv_decode2; checkpointed speculation, staged bit window
 int dxk_qv_decode3(dx_ctx *ctx, const uint8_t *d_in, size_t n, const QvDecTables2 *d_tab,
+                   int delchar, int subchar, int upper, int write, int64_t count,
+                   const int64_t *d_start, const int32_t *d_rlen, const QvDecEntry *d_ent,
+                   const char *d_prefix, int plen, uint8_t *d_out, int64_t *d_soff, int32_t *d_status);
+
+int dxk_qv_decode4(dx_ctx *ctx, const uint8_t *d_in, size_t n, const QvDecTables4 *d_tab,
                    int delchar, int subchar, int upper, int write, int64_t count,
                    const int64_t *d_start, const int32_t *d_rlen, const QvDecEntry *d_ent,
                    const char *d_prefix, int plen, uint8_t *d_out, int64_t *d_soff, int32_t *d_status);
