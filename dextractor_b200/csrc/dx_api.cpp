@@ -994,7 +994,7 @@ static bool build_dec_tables4(const dx_qv_coding *c, QvDecTables4 *t)
 struct QvPlan
 { std::vector<QvDecEntry> ent;
   bool         v2;            // parallel decoder usable
-  int          ver;           // which parallel kernel: 2, 3 or 4 (default)
+  int          ver;           // which parallel kernel: 2, 3, 4 or 5 (default)
   QvDecTables4 *d_tab4;
   int64_t     *d_soff;        // v1 only: [count][6] device
   int64_t     *d_start;       // v2: first stream byte of every entry
@@ -1017,8 +1017,8 @@ static int qv_walk(dx_ctx *ctx, const uint8_t *d_in, size_t n, const QvPlan &pla
                    const int64_t *d_start, const int32_t *d_rlen, int64_t count,
                    int64_t *d_soff, int32_t *d_stat)
 { const dx_qv_coding &cd = plan.coding;
-  if (plan.v2 && plan.ver == 4)
-    return dxk_qv_decode4(ctx,d_in,n,plan.d_tab4,cd.delchar,cd.subchar,0,0,count,d_start,d_rlen,
+  if (plan.v2 && plan.ver >= 4)
+    return (plan.ver == 5 ? dxk_qv_decode5 : dxk_qv_decode4)(ctx,d_in,n,plan.d_tab4,cd.delchar,cd.subchar,0,0,count,d_start,d_rlen,
                           NULL,NULL,0,NULL,d_soff,d_stat);
   if (plan.v2)
     return (plan.ver == 3 ? dxk_qv_decode3 : dxk_qv_decode2)(ctx,d_in,n,plan.d_tab2,cd.delchar,cd.subchar,
@@ -1078,12 +1078,13 @@ static int plan_undexqv(dx_ctx *ctx, const uint8_t *d_in, size_t n, const int64_
     plan.v2 = build_dec_tables2(&plan.coding,h2);
     { const char *force = getenv("DEXB200_DECODER");        // "v1": sequential kernels (testing)
       if (force != NULL && strcmp(force,"v1") == 0) plan.v2 = false;
-      plan.ver = 4;
+      plan.ver = 5;
+      if (force != NULL && strcmp(force,"v4") == 0) plan.ver = 4;
       if (force != NULL && strcmp(force,"v2") == 0) plan.ver = 2;
       if (force != NULL && strcmp(force,"v3") == 0) plan.ver = 3;
     }
     plan.d_tab4 = NULL;
-    if (plan.v2 && plan.ver == 4)
+    if (plan.v2 && plan.ver >= 4)
       { QvDecTables4 *h4 = (QvDecTables4 *) malloc(sizeof(QvDecTables4));
         if (h4 == NULL) { free(h2); return DX_E_NOMEM; }
         if (build_dec_tables4(&plan.coding,h4))
@@ -1095,7 +1096,7 @@ static int plan_undexqv(dx_ctx *ctx, const uint8_t *d_in, size_t n, const int64_
         free(h4);
         if (rc != DX_OK) { free(h2); return rc; }
       }
-    if (plan.v2 && plan.ver != 4)
+    if (plan.v2 && plan.ver < 4)
       { plan.d_tab2 = (QvDecTables2 *) dx_arena_get(ctx,sizeof(QvDecTables2));
         rc = plan.d_tab2 ? upload(ctx,plan.d_tab2,h2,1) : DX_E_NOMEM;
       }
@@ -1257,8 +1258,8 @@ extern "C" int dx_undexqv_dev(dx_ctx *ctx, const uint8_t *d_in, size_t n, int up
   if ((rc = upload(ctx,d_ent,plan.ent.data(),N)) != DX_OK) return rc;
   DX_CUDA(ctx,cudaMemsetAsync(d_stat,0,4,ctx->stream));
   const dx_qv_coding &cd = plan.coding;
-  if (plan.v2 && plan.ver == 4)
-    rc = dxk_qv_decode4(ctx,d_in,n,plan.d_tab4,cd.delchar,cd.subchar,upper,1,(int64_t) N,
+  if (plan.v2 && plan.ver >= 4)
+    rc = (plan.ver == 5 ? dxk_qv_decode5 : dxk_qv_decode4)(ctx,d_in,n,plan.d_tab4,cd.delchar,cd.subchar,upper,1,(int64_t) N,
                         plan.d_start,plan.d_rlen,d_ent,plan.d_prefix,plan.plen,d_out,NULL,d_stat);
   else if (plan.v2)
     rc = (plan.ver == 3 ? dxk_qv_decode3 : dxk_qv_decode2)(ctx,d_in,n,plan.d_tab2,cd.delchar,cd.subchar,

@@ -20,6 +20,29 @@ __device__ __forceinline__ void dx_stg16(void *p, uint4 v)          // p must be
                :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
+// 16 bytes at any address (two aligned loads + funnel shifts); never reads past text_end16
+__device__ __forceinline__ uint4 dx_ld16_any(const uint8_t *p, const uint8_t *end16)
+{ const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+  const uint8_t *al = reinterpret_cast<const uint8_t *>(a & ~(uintptr_t) 15);
+  const int sk = (int) (a & 15);
+  uint4 lo = dx_ldg16(al);
+  if (sk == 0) return lo;
+  uint4 hi = (al + 16 < end16) ? dx_ldg16(al + 16) : make_uint4(0,0,0,0);
+  const uint32_t sb = (sk & 3) * 8;
+  uint4 r;
+  switch (sk >> 2)
+    { case 0:  r.x = __funnelshift_r(lo.x,lo.y,sb); r.y = __funnelshift_r(lo.y,lo.z,sb);
+               r.z = __funnelshift_r(lo.z,lo.w,sb); r.w = __funnelshift_r(lo.w,hi.x,sb); break;
+      case 1:  r.x = __funnelshift_r(lo.y,lo.z,sb); r.y = __funnelshift_r(lo.z,lo.w,sb);
+               r.z = __funnelshift_r(lo.w,hi.x,sb); r.w = __funnelshift_r(hi.x,hi.y,sb); break;
+      case 2:  r.x = __funnelshift_r(lo.z,lo.w,sb); r.y = __funnelshift_r(lo.w,hi.x,sb);
+               r.z = __funnelshift_r(hi.x,hi.y,sb); r.w = __funnelshift_r(hi.y,hi.z,sb); break;
+      default: r.x = __funnelshift_r(lo.w,hi.x,sb); r.y = __funnelshift_r(hi.x,hi.y,sb);
+               r.z = __funnelshift_r(hi.y,hi.z,sb); r.w = __funnelshift_r(hi.z,hi.w,sb); break;
+    }
+  return r;
+}
+
 // ---- SWAR byte predicates on a 32-bit word (4 text bytes) --------------------------------------
 // 0x80 in every byte lane of x that equals c (exact, no cross-lane borrow).
 __device__ __forceinline__ uint32_t dx_eq_mask(uint32_t x, uint32_t c)

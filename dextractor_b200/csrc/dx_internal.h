@@ -174,6 +174,12 @@ int dxk_qv_decode4(dx_ctx *ctx, const uint8_t *d_in, size_t n, const QvDecTables
                    const int64_t *d_start, const int32_t *d_rlen, const QvDecEntry *d_ent,
                    const char *d_prefix, int plen, uint8_t *d_out, int64_t *d_soff, int32_t *d_status);
 
+// dx_qv_decode5.cu : one warp per entry, tables resident in shared memory (same contract)
+int dxk_qv_decode5(dx_ctx *ctx, const uint8_t *d_in, size_t n, const QvDecTables4 *d_tab,
+                   int delchar, int subchar, int upper, int write, int64_t count,
+                   const int64_t *d_start, const int32_t *d_rlen, const QvDecEntry *d_ent,
+                   const char *d_prefix, int plen, uint8_t *d_out, int64_t *d_soff, int32_t *d_status);
+
 // dx_pack.cu : .fasta/.arrow <-> 2-bit images
 struct FaEntries                // one fasta/arrow entry (structure of arrays in HBM)
 { int64_t  n;

@@ -36,29 +36,6 @@ struct EncArgs
   unsigned long long *ticket;
 };
 
-// 16 bytes at any address (two aligned loads + funnel shifts); never reads past text_end16
-__device__ __forceinline__ uint4 ld16_any(const uint8_t *p, const uint8_t *end16)
-{ const uintptr_t a = reinterpret_cast<uintptr_t>(p);
-  const uint8_t *al = reinterpret_cast<const uint8_t *>(a & ~(uintptr_t) 15);
-  const int sk = (int) (a & 15);
-  uint4 lo = dx_ldg16(al);
-  if (sk == 0) return lo;
-  uint4 hi = (al + 16 < end16) ? dx_ldg16(al + 16) : make_uint4(0,0,0,0);
-  const uint32_t sb = (sk & 3) * 8;
-  uint4 r;
-  switch (sk >> 2)
-    { case 0:  r.x = __funnelshift_r(lo.x,lo.y,sb); r.y = __funnelshift_r(lo.y,lo.z,sb);
-               r.z = __funnelshift_r(lo.z,lo.w,sb); r.w = __funnelshift_r(lo.w,hi.x,sb); break;
-      case 1:  r.x = __funnelshift_r(lo.y,lo.z,sb); r.y = __funnelshift_r(lo.z,lo.w,sb);
-               r.z = __funnelshift_r(lo.w,hi.x,sb); r.w = __funnelshift_r(hi.x,hi.y,sb); break;
-      case 2:  r.x = __funnelshift_r(lo.z,lo.w,sb); r.y = __funnelshift_r(lo.w,hi.x,sb);
-               r.z = __funnelshift_r(hi.x,hi.y,sb); r.w = __funnelshift_r(hi.y,hi.z,sb); break;
-      default: r.x = __funnelshift_r(lo.w,hi.x,sb); r.y = __funnelshift_r(hi.x,hi.y,sb);
-               r.z = __funnelshift_r(hi.y,hi.z,sb); r.w = __funnelshift_r(hi.z,hi.w,sb); break;
-    }
-  return r;
-}
-
 __device__ __forceinline__ uint32_t item_len(uint32_t e, uint32_t lit)
 { return DX_ENC_LEN(e) + (DX_ENC_ESC(e) ? lit : 0u); }
 
@@ -300,7 +277,7 @@ __device__ uint32_t code_tags(const EncArgs &a, const uint8_t *del, const uint8_
       if (c < lw.nchunk)
         { tv = dx_ldg16(lw.base + (int64_t) c*16);
           if (a.delchar >= 0)
-            { uint4 dv = ld16_any(del + p0,a.text_end16);    // del bytes at the same positions
+            { uint4 dv = dx_ld16_any(del + p0,a.text_end16);    // del bytes at the same positions
               m &= ~dx_eq_mask16(dv,(uint32_t) a.delchar);
             }
         }
