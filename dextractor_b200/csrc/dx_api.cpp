@@ -811,6 +811,9 @@ extern "C" int dx_qv_scan_dev(dx_ctx *ctx, const uint8_t *d_text, size_t n, cons
 //  QV coder: encode
 // ================================================================================================
 
+// Encoder tables (dx_qv_encode.cu): bits 0-4 length of the whole item, bit 5 escape, bits 8-31 the
+// item's bits.  An escaped SYMBOL carries its 8-bit literal inside the item (QV.c:432-434); an
+// escaped RUN LENGTH is followed by a separate 16-bit literal (QV.c:486-487).
 static void pack_tables(const dx_qv_coding *c, QvEncTables *t)
 { for (int k = 0; k < 6; k++)
     { const dx_scheme &s = c->tab[k];
@@ -818,8 +821,11 @@ static void pack_tables(const dx_qv_coding *c, QvEncTables *t)
       for (int x = 0; x < 256; x++)
         { const bool esc = (isrun || s.type == 2) && s.lens[x] > 0 &&
                            s.bits[x] == s.bits[255] && s.lens[x] == s.lens[255];   // QV.c:432,486
-          t->t[k][x] = (s.bits[x] & 0xffffu) | ((uint32_t) (s.lens[x] & 0x1f) << 16) |
-                       ((uint32_t) esc << 21);
+          uint32_t len  = (uint32_t) (s.lens[x] & 0x1f);
+          uint32_t bits = s.bits[x] & 0xffffu;
+          if (len > 16) { len = 0; bits = 0; }          // no usable code: the symbol does not occur
+          if (esc && !isrun) { bits = (bits << 8) | (uint32_t) x; len += 8; }
+          t->t[k][x] = len | ((uint32_t) esc << 5) | (bits << 8);
         }
     }
 }

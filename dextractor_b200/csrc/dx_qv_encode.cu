@@ -6,13 +6,20 @@
 //
 //   k_qv_size     one warp per (entry, stream): bits of every item, position of the last item
 //                 -> 32-bit words the reference would write (the (p_last+47)>>5 rule,
-//                 QV.c:436-442), kept-tag count -> tag bytes
+//                 QV.c:436-442), kept-tag count -> tag bytes.  No bit positions are needed here,
+//                 so lanes only sum code lengths.
 //   k_qv_offsets  exclusive scan of the per-entry byte totals (the implicit file position of
 //                 the reference's fwrite calls)
-//   k_qv_emit     one warp per (entry, stream): every lane codes 16 consecutive symbols, a warp
-//                 scan gives each lane its bit offset, lanes OR their codes MSB-first into a
-//                 shared-memory staging area, which is flushed with aligned 32-bit stores at
-//                 whatever byte alignment the stream has in the file
+//   k_qv_emit     one warp per (entry, stream).  Plain streams: every lane looks up the codes of
+//                 16 consecutive symbols, a warp scan of the bit counts gives each lane its bit
+//                 offset, the lane shifts its codes (two per step) through a 64-bit register and
+//                 stores the words it COMPLETES into the warp's staging area; the partial words
+//                 between neighbouring lanes are merged by a segmented OR-scan over shuffles, so
+//                 no shared-memory atomics are involved.  Run-length streams first compact the
+//                 (position, symbol) pairs that are not the run character into a per-warp queue,
+//                 then code 32 items at a time, one item (run code [+ literal] + symbol code) per
+//                 lane.  The stage is flushed with aligned 32-bit stores at whatever byte alignment
+//                 the stream has in the file.
 
 #include "dx_internal.h"
 #include "dx_common.cuh"
@@ -21,14 +28,15 @@ namespace {
 
 constexpr int kEncWarps   = 16;
 constexpr int kEncThreads = kEncWarps * 32;
-constexpr int kStageWords = 1024;                 // per warp; a 512-symbol row needs <= 897
-constexpr int kFetch      = 4;
+constexpr int kStageWords = 512;                  // per warp; a 512-symbol row needs <= 384
+constexpr int kQueue      = 1024;                 // per warp ring of (position << 8 | symbol)
+constexpr int kWarpWords  = kStageWords + 4 + kQueue;
 
 struct EncArgs
 { const uint8_t  *text;
   const uint8_t  *text_end16;     // first address past the readable 16-byte-padded text
   QvEntries       ent;
-  const uint32_t *tab;            // [6][256] packed entries (DX_ENC_*)
+  const uint32_t *tab;            // [6][256] packed entries (DX_ENC2_*)
   int32_t         delchar, subchar, lossy, lwell_in;
   uint32_t       *bytes;          // [n][6]
   int64_t        *off;            // [n+1]
@@ -36,28 +44,12 @@ struct EncArgs
   unsigned long long *ticket;
 };
 
-__device__ __forceinline__ uint32_t item_len(uint32_t e, uint32_t lit)
-{ return DX_ENC_LEN(e) + (DX_ENC_ESC(e) ? lit : 0u); }
-
-// local bit accumulator: whole words go to the staging area with one atomicOr each
-struct BitSink
-{ uint32_t *stage; uint32_t w, cur, fill;
-  __device__ __forceinline__ void start(uint32_t *st, uint32_t pos)
-  { stage = st; w = pos >> 5; fill = pos & 31u; cur = 0; }
-  __device__ __forceinline__ void put(uint32_t code, uint32_t len)
-  { if (fill + len < 32u)
-      { cur |= code << (32u - fill - len); fill += len; }
-    else
-      { const uint32_t spill = fill + len - 32u;
-        cur |= code >> spill;
-        atomicOr(&stage[w],cur);
-        w += 1;
-        cur  = spill ? (code << (32u - spill)) : 0u;
-        fill = spill;
-      }
-  }
-  __device__ __forceinline__ void done() { if (cur) atomicOr(&stage[w],cur); }
-};
+// table entry: bits 0-4 length of the whole item, bit 5 escape, bits 8-31 the item's bits.
+// Symbol tables fold the 8-bit literal of an escaped symbol into the item (length <= 24); run
+// tables keep only the code, the 16-bit literal run length follows as a second piece.
+#define E_LEN(e)   ((e) & 31u)
+#define E_ESC(e)   ((e) & 32u)
+#define E_BITS(e)  ((e) >> 8)
 
 __device__ __forceinline__ uint32_t base2(uint32_t c)        // Number_Read, DB.c:394-411
 { c |= 0x20u;
@@ -79,25 +71,189 @@ struct LineWalk
   }
 };
 
-// MODE 0: size only.  MODE 1: size + emit.
-// Returns (through refs) the stream's total bits and the bit position of its last item.
-// In MODE 1 the staging area holds the not yet flushed tail; `gptr` advances over flushed bytes.
-template <int MODE>
-__device__ void code_stream(const EncArgs &a, const uint32_t *stab, const uint8_t *line,
-                            int32_t rlen, int kind /*0 del 2 ins 3 mrg 4 sub*/, int lane,
-                            uint32_t *stage, uint8_t *&gptr,
-                            uint32_t &total_bits, uint32_t &plast_out)
-{ const int32_t rc = (kind == 0) ? a.delchar : (kind == 4) ? a.subchar : -1;
-  const uint32_t *sym = stab + kind*256;
-  const uint32_t *run = stab + (kind == 0 ? 1 : 5)*256;
-  const uint32_t lossmask = !a.lossy ? 0xffffffffu : (kind == 2) ? 0xfefefefeu
-                                                    : (kind == 3) ? 0xfcfcfcfcu : 0xffffffffu;
-  LineWalk lw; lw.set(line,rlen);
+// staged words -> global at any byte alignment; SWAP: the stage holds MSB-first words that are
+// to appear in the file as a byte string (the 2-bit packed tags), so every word is byte-swapped
+template <bool SWAP>
+__device__ __forceinline__ void copy_out(uint8_t *gdst, const uint32_t *ssrc, uint32_t n, int lane)
+{ const uint8_t *sb = reinterpret_cast<const uint8_t *>(ssrc);
+  uint32_t head = (4u - (uint32_t) (reinterpret_cast<uintptr_t>(gdst) & 3u)) & 3u;
+  if (head > n) head = n;
+  if ((uint32_t) lane < head)
+    gdst[lane] = sb[SWAP ? (lane ^ 3) : lane];
+  const uint32_t body = (n - head) >> 2;
+  uint32_t *gw = reinterpret_cast<uint32_t *>(gdst + head);
+  const uint32_t sh = head * 8u;                   // source is `head` bytes ahead of a word
+  for (uint32_t i = lane; i < body; i += 32)
+    { uint32_t lo = ssrc[i], hi = ssrc[i+1];
+      if (SWAP) { lo = __byte_perm(lo,0,0x0123); hi = __byte_perm(hi,0,0x0123); }
+      gw[i] = __funnelshift_r(lo,hi,sh);          // sh == 0 -> lo
+    }
+  const uint32_t done = head + 4u*body;
+  if ((uint32_t) lane < n - done)
+    gdst[done + lane] = sb[SWAP ? ((done + lane) ^ 3u) : (done + lane)];
+}
 
-  uint32_t flushed_bits = 0;      // bits already written to global (multiple of 32)
-  uint32_t stage_bits   = 0;      // bits currently staged (from word 0 of stage)
-  int32_t  prev  = -1;            // last non-run position so far
-  int32_t  plast = -1;            // lane-local candidate for the last item's bit position
+// ---- the warp's output: completed words in shared memory, the trailing partial word in a register
+struct WarpBits
+{ uint32_t *stage;          // [kStageWords + 4]
+  uint32_t  nst;            // completed words staged                        (warp-uniform)
+  uint32_t  carry, cbits;   // trailing partial word, top aligned; its bits  (warp-uniform)
+  uint32_t  flushed;        // words already written to global               (warp-uniform)
+  uint8_t  *gptr;           // global address of word 0 of the stream
+
+  __device__ __forceinline__ void init(uint32_t *st, uint8_t *g)
+  { stage = st; nst = 0; carry = 0; cbits = 0; flushed = 0; gptr = g; }
+  __device__ __forceinline__ uint32_t bitpos() const { return nst*32u + cbits; }       // in the stage
+  __device__ __forceinline__ uint32_t total() const { return (flushed + nst)*32u + cbits; }
+
+  // make room for `bits` more bits
+  template <bool SWAP>
+  __device__ __forceinline__ void reserve(uint32_t bits, int lane)
+  { if (nst + ((cbits + bits + 31u) >> 5) + 1u > (uint32_t) kStageWords)
+      { __syncwarp();
+        copy_out<SWAP>(gptr + (size_t) flushed*4u,stage,nst*4u,lane);
+        __syncwarp();
+        flushed += nst; nst = 0;
+      }
+  }
+};
+
+// one lane's bit string inside a row: pieces are shifted through a 64-bit register; every word the
+// lane completes is stored, what is left over joins its neighbours in finish()
+struct LaneSink
+{ uint64_t acc; uint32_t nacc, widx, fw;
+  __device__ __forceinline__ void start(uint32_t pos)
+  { widx = fw = pos >> 5; nacc = pos & 31u; acc = 0; }
+  __device__ __forceinline__ void put(uint32_t *stage, uint32_t bits, uint32_t len)    // len <= 32
+  { acc = (acc << len) | bits;
+    nacc += len;
+    if (nacc >= 32u)
+      { nacc -= 32u;
+        stage[widx++] = (uint32_t) (acc >> nacc);
+      }
+  }
+  // warp-collective: merge the partial words, update the warp state
+  __device__ __forceinline__ void finish(WarpBits &wb, int lane)
+  { uint32_t t = nacc ? (uint32_t) (acc << (32u - nacc)) : 0u;          // my trailing partial word
+    if (lane == 0 && widx == fw) t |= wb.carry;                          // still in the carry's word
+    // segmented inclusive OR-scan keyed by the word the partial belongs to (keys ascend by lane)
+    const uint32_t kprev = __shfl_up_sync(DX_FULL,widx,1);
+    const uint32_t heads = __ballot_sync(DX_FULL,lane == 0 || kprev != widx);
+    const int seg = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));   // first lane of my segment
+    uint32_t sc = t;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1)
+      { const uint32_t o = __shfl_up_sync(DX_FULL,sc,d);
+        if (lane - d >= seg) sc |= o;
+      }
+    uint32_t before = __shfl_up_sync(DX_FULL,sc,1);                      // what is already in my first word
+    if (lane == 0) before = wb.carry;
+    if (widx != fw && before) wb.stage[fw] |= before;                    // I completed that word
+    wb.carry = __shfl_sync(DX_FULL,sc,31);
+    const uint32_t endw = __shfl_sync(DX_FULL,widx,31), endb = __shfl_sync(DX_FULL,nacc,31);
+    wb.nst = endw; wb.cbits = endb;
+    if (endb == 0) wb.carry = 0;
+  }
+};
+
+// ---- plain stream: one Huffman item per symbol (Encode, QV.c:386-443) --------------------------------
+template <int MODE>
+__device__ void code_plain(const EncArgs &a, const uint32_t *sym, const uint8_t *line, int32_t rlen,
+                           uint32_t lossmask, int lane, WarpBits &wb, uint32_t &total_bits,
+                           uint32_t &plast_out)
+{ LineWalk lw; lw.set(line,rlen);
+  uint32_t mybits = 0;                                   // MODE 0: lane-local sum over the line
+  for (int32_t c0 = 0; c0 < lw.nchunk; c0 += 128)
+    { uint4 v[4];
+#pragma unroll
+      for (int j = 0; j < 4; j++)
+        { const int32_t c = c0 + j*32 + lane;
+          v[j] = (c < lw.nchunk) ? dx_ldg16(lw.base + (int64_t) c*16) : make_uint4(0,0,0,0);
+        }
+#pragma unroll
+      for (int j = 0; j < 4; j++)
+        { const int32_t c = c0 + j*32 + lane;
+          if (c0 + j*32 >= lw.nchunk) break;                        // warp-uniform
+          const uint32_t valid = lw.valid(c);
+          const uint32_t w[4] = { v[j].x & lossmask, v[j].y & lossmask, v[j].z & lossmask, v[j].w & lossmask };
+          uint32_t e[16];
+          uint32_t bits = 0, esc = 0;
+#pragma unroll
+          for (int i = 0; i < 16; i++)
+            { const uint32_t x = (w[i >> 2] >> ((i & 3)*8)) & 0xffu;
+              uint32_t t = sym[x];
+              if (valid != 0xffffu && !((valid >> i) & 1u)) t = 0;
+              e[i] = t;
+              bits += E_LEN(t);
+              esc  |= t;
+            }
+          if (MODE == 0) { mybits += bits; continue; }
+          const uint32_t inc = dx_warp_incl_sum(bits,lane);
+          const uint32_t row = __shfl_sync(DX_FULL,inc,31);
+          wb.reserve<false>(row,lane);
+          LaneSink sk;
+          sk.start(wb.bitpos() + inc - bits);
+          if (!E_ESC(esc))
+            {
+#pragma unroll
+              for (int i = 0; i < 16; i += 2)              // codes <= 16 bits: two per step
+                { const uint32_t l1 = E_LEN(e[i+1]);
+                  sk.put(wb.stage,(E_BITS(e[i]) << l1) | E_BITS(e[i+1]),E_LEN(e[i]) + l1);
+                }
+            }
+          else
+            {
+#pragma unroll
+              for (int i = 0; i < 16; i++)
+                sk.put(wb.stage,E_BITS(e[i]),E_LEN(e[i]));
+            }
+          sk.finish(wb,lane);
+        }
+    }
+  if (MODE == 0) total_bits = dx_warp_sum(mybits);
+  else           total_bits = wb.total();
+  // the last item: the last symbol's code, or its literal when it is escaped
+  const uint32_t el = sym[line[rlen-1] & lossmask & 0xffu];
+  plast_out = total_bits - E_LEN(el) + (E_ESC(el) ? E_LEN(el) - 8u : 0u);
+}
+
+// ---- run-length stream (Encode_Run, QV.c:448-506) -----------------------------------------------------
+// items = (run of the run character, next other symbol); a trailing run has no symbol
+template <int MODE>
+__device__ void code_run(const EncArgs &a, const uint32_t *sym, const uint32_t *run, uint32_t rc,
+                         const uint8_t *line, int32_t rlen, int lane, uint32_t *queue, WarpBits &wb,
+                         uint32_t &total_bits, uint32_t &plast_out)
+{ LineWalk lw; lw.set(line,rlen);
+  uint32_t qhead = 0, qtail = 0;                         // ring positions (warp-uniform)
+  int32_t  prevpos = -1;                                 // last position that was not the run character
+  uint32_t mybits = 0;
+
+  // code n (<= 32) queued items, lane i takes item qhead + i
+  auto batch = [&](uint32_t n)
+    { uint32_t R = 0, E = 0, r = 0, bits = 0;
+      int32_t p = 0;
+      if ((uint32_t) lane < n)
+        { const uint32_t it = queue[(qhead + lane) & (kQueue-1)];
+          p = (int32_t) (it >> 8);
+          const int32_t pp = (lane == 0) ? prevpos : (int32_t) (queue[(qhead + lane - 1) & (kQueue-1)] >> 8);
+          r = (uint32_t) (p - pp - 1);
+          R = run[min(r,255u)];
+          E = sym[it & 0xffu];
+          bits = E_LEN(R) + (E_ESC(R) ? 16u : 0u) + E_LEN(E);
+        }
+      prevpos = __shfl_sync(DX_FULL,p,n-1);
+      qhead += n;
+      if (MODE == 0) { mybits += bits; return; }
+      const uint32_t inc = dx_warp_incl_sum(bits,lane);
+      const uint32_t row = __shfl_sync(DX_FULL,inc,31);
+      wb.reserve<false>(row,lane);
+      LaneSink sk;
+      sk.start(wb.bitpos() + inc - bits);
+      sk.put(wb.stage,E_BITS(R) & 0xffffu,E_LEN(R));
+      if (E_ESC(R)) sk.put(wb.stage,r & 0xffffu,16);
+      sk.put(wb.stage,E_BITS(E),E_LEN(E));
+      sk.finish(wb,lane);
+    };
 
   for (int32_t c0 = 0; c0 < lw.nchunk; c0 += 128)
     { uint4 v[4];
@@ -105,152 +261,84 @@ __device__ void code_stream(const EncArgs &a, const uint32_t *stab, const uint8_
       for (int j = 0; j < 4; j++)
         { const int32_t c = c0 + j*32 + lane;
           v[j] = (c < lw.nchunk) ? dx_ldg16(lw.base + (int64_t) c*16) : make_uint4(0,0,0,0);
-          v[j].x &= lossmask; v[j].y &= lossmask; v[j].z &= lossmask; v[j].w &= lossmask;
         }
 #pragma unroll
       for (int j = 0; j < 4; j++)
-        { const int32_t c  = c0 + j*32 + lane;
+        { const int32_t c = c0 + j*32 + lane;
           if (c0 + j*32 >= lw.nchunk) break;                        // warp-uniform
           const int32_t p0 = c*16 - lw.skew;
-          const uint32_t valid = lw.valid(c);
-          uint32_t lane_bits = 0;
-          uint32_t m = valid;
-          int32_t  pv = -1;
-
-          if (rc < 0)
-            { uint32_t mm = m;
-              while (mm)
-                { const int i = __ffs(mm) - 1; mm &= mm - 1;
-                  lane_bits += item_len(sym[dx_byte_of(v[j],i)],8);
-                }
+          uint32_t m = lw.valid(c) & ~dx_eq_mask16(v[j],rc);
+          const uint32_t cnt = __popc(m);
+          const uint32_t inc = dx_warp_incl_sum(cnt,lane);
+          const uint32_t row = __shfl_sync(DX_FULL,inc,31);
+          uint32_t at = qtail + inc - cnt;
+          while (m)
+            { const int i = __ffs(m) - 1; m &= m - 1;
+              queue[at & (kQueue-1)] = ((uint32_t) (p0 + i) << 8) | dx_byte_of(v[j],i);
+              at++;
             }
-          else
-            { m &= ~dx_eq_mask16(v[j],(uint32_t) rc);
-              const int32_t mylast = m ? p0 + (31 - __clz(m)) : -1;
-              const int32_t inc = dx_warp_incl_max(mylast,lane);
-              int32_t before = __shfl_up_sync(DX_FULL,inc,1);
-              if (lane == 0) before = -1;
-              pv = max(prev,before);
-              prev = max(prev,__shfl_sync(DX_FULL,inc,31));
-              uint32_t mm = m;
-              int32_t  q = pv;
-              while (mm)
-                { const int i = __ffs(mm) - 1; mm &= mm - 1;
-                  const int32_t p = p0 + i, r = p - q - 1;
-                  lane_bits += item_len(run[min(r,255)],16) + item_len(sym[dx_byte_of(v[j],i)],8);
-                  q = p;
-                }
-            }
-
-          const uint32_t inc_bits = dx_warp_incl_sum(lane_bits,lane);
-          const uint32_t row_bits = __shfl_sync(DX_FULL,inc_bits,31);
-          if (MODE == 1 && stage_bits + row_bits > (uint32_t) (kStageWords-4)*32u)
-            { // make room: flush the whole words staged so far
-              const uint32_t nfull = stage_bits >> 5;
-              __syncwarp();
-              dx_warp_copy_out(gptr,stage,nfull*4u,lane);
-              gptr += nfull*4u;
-              __syncwarp();
-              const uint32_t partial = stage[nfull];
-              __syncwarp();
-              for (uint32_t i = lane; i <= nfull; i += 32) stage[i] = (i == 0) ? partial : 0u;
-              __syncwarp();
-              flushed_bits += nfull*32u;
-              stage_bits   &= 31u;
-            }
-          uint32_t pos = stage_bits + inc_bits - lane_bits;         // lane's first bit in stage
-
-          // second walk over the lane's symbols: positions (+ emission in MODE 1)
-          BitSink sink;
-          if (MODE == 1) sink.start(stage,pos);
-          if (rc < 0)
-            { uint32_t mm = m;
-              while (mm)
-                { const int i = __ffs(mm) - 1; mm &= mm - 1;
-                  const uint32_t x = dx_byte_of(v[j],i), e = sym[x];
-                  const uint32_t len = DX_ENC_LEN(e);
-                  if (MODE == 1) sink.put(DX_ENC_CODE(e),len);
-                  int32_t here = (int32_t) (flushed_bits + pos);
-                  pos += len;
-                  if (DX_ENC_ESC(e))
-                    { if (MODE == 1) sink.put(x,8);
-                      here = (int32_t) (flushed_bits + pos);
-                      pos += 8;
-                    }
-                  if (p0 + i == rlen-1) plast = here;
-                }
-            }
-          else
-            { uint32_t mm = m;
-              int32_t  q = pv;
-              while (mm)
-                { const int i = __ffs(mm) - 1; mm &= mm - 1;
-                  const int32_t p = p0 + i, r = p - q - 1;
-                  q = p;
-                  uint32_t e = run[min(r,255)], len = DX_ENC_LEN(e);
-                  if (MODE == 1) sink.put(DX_ENC_CODE(e),len);
-                  pos += len;
-                  if (DX_ENC_ESC(e))
-                    { if (MODE == 1) sink.put((uint32_t) r & 0xffffu,16);
-                      pos += 16;
-                    }
-                  const uint32_t x = dx_byte_of(v[j],i);
-                  e = sym[x]; len = DX_ENC_LEN(e);
-                  if (MODE == 1) sink.put(DX_ENC_CODE(e),len);
-                  int32_t here = (int32_t) (flushed_bits + pos);
-                  pos += len;
-                  if (DX_ENC_ESC(e))
-                    { if (MODE == 1) sink.put(x,8);
-                      here = (int32_t) (flushed_bits + pos);
-                      pos += 8;
-                    }
-                  if (p == rlen-1) plast = here;
-                }
-            }
-          if (MODE == 1) sink.done();
-          stage_bits += row_bits;
+          qtail += row;
+          __syncwarp();
+          while (qtail - qhead >= 32u) batch(32u);
         }
     }
+  if (qtail != qhead) batch(qtail - qhead);
 
   // trailing run of the run character (QV.c:475-487 when k reaches rlen inside a run)
-  if (rc >= 0 && prev < rlen-1)
-    { const int32_t r = rlen-1-prev;
-      const uint32_t e = run[min(r,255)], len = DX_ENC_LEN(e);
-      if (MODE == 1)
-        { __syncwarp();
+  uint32_t Rt = 0, rt = 0;
+  const bool trailing = (prevpos < rlen-1);
+  if (trailing)
+    { rt = (uint32_t) (rlen-1-prevpos);
+      Rt = run[min(rt,255u)];
+      const uint32_t bits = (lane == 0) ? E_LEN(Rt) + (E_ESC(Rt) ? 16u : 0u) : 0u;
+      if (MODE == 0) mybits += bits;
+      else
+        { wb.reserve<false>(32u,lane);
+          LaneSink sk;
+          sk.start(wb.bitpos() + (lane == 0 ? 0u : E_LEN(Rt) + (E_ESC(Rt) ? 16u : 0u)));
           if (lane == 0)
-            { dx_or_bits(stage,stage_bits,DX_ENC_CODE(e),len);
-              if (DX_ENC_ESC(e)) dx_or_bits(stage,stage_bits+len,(uint32_t) r & 0xffffu,16);
+            { sk.put(wb.stage,E_BITS(Rt) & 0xffffu,E_LEN(Rt));
+              if (E_ESC(Rt)) sk.put(wb.stage,rt & 0xffffu,16);
             }
+          sk.finish(wb,lane);
         }
-      plast = (int32_t) (flushed_bits + stage_bits + (DX_ENC_ESC(e) ? len : 0u));
-      stage_bits += item_len(e,16);
     }
+  if (MODE == 0) total_bits = dx_warp_sum(mybits);
+  else           total_bits = wb.total();
+  if (trailing)
+    plast_out = total_bits - (E_ESC(Rt) ? 16u : E_LEN(Rt));
+  else
+    { const uint32_t el = sym[line[rlen-1]];
+      plast_out = total_bits - E_LEN(el) + (E_ESC(el) ? E_LEN(el) - 8u : 0u);
+    }
+}
 
-  // last item position: exactly one lane (or all, for the trailing run) holds it
-#pragma unroll
-  for (int d = 16; d > 0; d >>= 1)
-    plast = max(plast,__shfl_xor_sync(DX_FULL,plast,d));
-
-  total_bits = flushed_bits + stage_bits;
-  plast_out  = (uint32_t) plast;
-
+template <int MODE>
+__device__ void code_stream(const EncArgs &a, const uint32_t *stab, const uint8_t *line,
+                            int32_t rlen, int kind /*0 del 2 ins 3 mrg 4 sub*/, int lane,
+                            uint32_t *stage, uint32_t *queue, uint8_t *gptr,
+                            uint32_t &total_bits, uint32_t &plast_out)
+{ total_bits = 0; plast_out = 0;
+  if (rlen <= 0) return;
+  const int32_t rc = (kind == 0) ? a.delchar : (kind == 4) ? a.subchar : -1;
+  const uint32_t lossmask = !a.lossy ? 0xffffffffu : (kind == 2) ? 0xfefefefeu
+                                                    : (kind == 3) ? 0xfcfcfcfcu : 0xffffffffu;
+  WarpBits wb; wb.init(stage,gptr);
+  if (rc < 0) code_plain<MODE>(a,stab + kind*256,line,rlen,lossmask,lane,wb,total_bits,plast_out);
+  else        code_run<MODE>(a,stab + kind*256,stab + (kind == 0 ? 1 : 5)*256,(uint32_t) rc,line,rlen,lane,
+                             queue,wb,total_bits,plast_out);
   if (MODE == 1)
     { // final flush incl. the look-ahead padding word (QV.c:436-442)
       __syncwarp();
-      uint32_t nst = (stage_bits + 31u) >> 5;
       const uint32_t full_total = (total_bits + 31u) >> 5;
-      const uint32_t want_total = (rlen > 0) ? (((uint32_t) plast + 47u) >> 5) : 0u;
-      if (want_total > full_total)
-        { if (lane == 0)
-            stage[nst] = (total_bits & 31u) ? stage[nst-1] : 0u;
-          nst += 1;
-          __syncwarp();
+      const uint32_t want_total = (plast_out + 47u) >> 5;
+      if (lane == 0)
+        { if (wb.cbits) stage[wb.nst] = wb.carry;
+          if (want_total > full_total) stage[wb.nst + (wb.cbits ? 1u : 0u)] = wb.cbits ? wb.carry : 0u;
         }
-      dx_warp_copy_out(gptr,stage,nst*4u,lane);
-      gptr += nst*4u;
+      uint32_t nst = wb.nst + (wb.cbits ? 1u : 0u) + (want_total > full_total ? 1u : 0u);
       __syncwarp();
-      for (uint32_t i = lane; i <= nst; i += 32) stage[i] = 0u;
+      copy_out<false>(gptr + (size_t) wb.flushed*4u,stage,nst*4u,lane);
       __syncwarp();
     }
 }
@@ -267,67 +355,45 @@ __device__ uint32_t code_tags(const EncArgs &a, const uint8_t *del, const uint8_
                               int32_t rlen, int lane, uint32_t *stage, uint8_t *gptr)
 { if (MODE == 0 && a.delchar < 0) return (uint32_t) rlen;      // every tag is kept
   LineWalk lw; lw.set(tag,rlen);
-  uint32_t kept_total = 0;       // symbols kept so far (all rows)
-  uint32_t stage_syms = 0;       // symbols staged (2 bits each, from word 0)
+  WarpBits wb; wb.init(stage,gptr);
+  uint32_t mykept = 0;
   for (int32_t c0 = 0; c0 < lw.nchunk; c0 += 32)
     { const int32_t c = c0 + lane;
       const int32_t p0 = c*16 - lw.skew;
       uint32_t m = lw.valid(c);
       uint4 tv = make_uint4(0,0,0,0);
       if (c < lw.nchunk)
-        { tv = dx_ldg16(lw.base + (int64_t) c*16);
+        { if (MODE == 1) tv = dx_ldg16(lw.base + (int64_t) c*16);
           if (a.delchar >= 0)
             { uint4 dv = dx_ld16_any(del + p0,a.text_end16);    // del bytes at the same positions
               m &= ~dx_eq_mask16(dv,(uint32_t) a.delchar);
             }
         }
       const uint32_t cnt = __popc(m);
+      if (MODE == 0) { mykept += cnt; continue; }
       const uint32_t inc = dx_warp_incl_sum(cnt,lane);
       const uint32_t row = __shfl_sync(DX_FULL,inc,31);
-      if (MODE == 1)
-        { if ((stage_syms + row)*2u > (uint32_t) (kStageWords-4)*32u)
-            { const uint32_t nfull = (stage_syms*2u) >> 5;
-              __syncwarp();
-              dx_warp_copy_out(gptr,stage,nfull*4u,lane);
-              gptr += nfull*4u;
-              __syncwarp();
-              const uint32_t partial = stage[nfull];
-              __syncwarp();
-              for (uint32_t i = lane; i <= nfull; i += 32) stage[i] = (i == 0) ? partial : 0u;
-              __syncwarp();
-              stage_syms &= 15u;
-            }
-          if (cnt)
-            { uint32_t val = 0;
-              uint32_t mm = m;
-              while (mm)
-                { const int i = __ffs(mm) - 1; mm &= mm - 1;
-                  val = (val << 2) | base2(dx_byte_of(tv,i));
-                }
-              // MSB-first inside BYTES: compose big-endian words, store them byte-swapped
-              const uint32_t pos = (stage_syms + inc - cnt)*2u, len = cnt*2u;
-              const uint32_t w = pos >> 5, off = pos & 31u;
-              if (off + len <= 32u)
-                atomicOr(&stage[w],__byte_perm(val << (32u - off - len),0,0x0123));
-              else
-                { const uint32_t spill = off + len - 32u;
-                  atomicOr(&stage[w],__byte_perm(val >> spill,0,0x0123));
-                  atomicOr(&stage[w+1],__byte_perm(val << (32u - spill),0,0x0123));
-                }
-            }
-          stage_syms += row;
+      wb.reserve<true>(row*2u,lane);
+      uint32_t val = 0;
+      while (m)
+        { const int i = __ffs(m) - 1; m &= m - 1;
+          val = (val << 2) | base2(dx_byte_of(tv,i));
         }
-      kept_total += row;
+      LaneSink sk;
+      sk.start(wb.bitpos() + (inc - cnt)*2u);
+      sk.put(wb.stage,val,cnt*2u);
+      sk.finish(wb,lane);
     }
-  if (MODE == 1)
-    { __syncwarp();
-      const uint32_t nbytes = (stage_syms + 3u) >> 2;      // partial word: only the bytes in use
-      dx_warp_copy_out(gptr,stage,nbytes,lane);
-      __syncwarp();
-      for (uint32_t i = lane; i <= (nbytes >> 2) + 1; i += 32) stage[i] = 0u;
-      __syncwarp();
-    }
-  return kept_total;
+  if (MODE == 0) return dx_warp_sum(mykept);
+  __syncwarp();
+  const uint32_t kept = wb.total() >> 1;
+  if (lane == 0 && wb.cbits) stage[wb.nst] = wb.carry;
+  __syncwarp();
+  // MSB-first inside BYTES: the staged big-endian words go out byte-swapped; only the bytes in use
+  const uint32_t nbytes = ((kept + 3u) >> 2) - wb.flushed*4u;
+  copy_out<true>(gptr + (size_t) wb.flushed*4u,stage,nbytes,lane);
+  __syncwarp();
+  return kept;
 }
 
 __device__ __forceinline__ uint32_t well_bytes(const EncArgs &a, int64_t e)
@@ -337,62 +403,59 @@ __device__ __forceinline__ uint32_t well_bytes(const EncArgs &a, int64_t e)
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(kEncThreads)
+__global__ void __launch_bounds__(kEncThreads,2)
 k_qv_code(EncArgs a)
 { extern __shared__ uint32_t smem[];
   uint32_t *stab  = smem;                                          // [6][256]
-  uint32_t *stage = smem + 6*256 + (threadIdx.x >> 5)*kStageWords; // per warp (MODE 1 only)
+  uint32_t *stage = smem + 6*256 + (threadIdx.x >> 5)*kWarpWords;  // per warp: stage, then the item queue
+  uint32_t *queue = stage + kStageWords + 4;
   for (int i = threadIdx.x; i < 6*256; i += kEncThreads) stab[i] = a.tab[i];
-  if (MODE == 1)
-    for (int i = threadIdx.x; i < kEncWarps*kStageWords; i += kEncThreads) smem[6*256 + i] = 0;
   __syncthreads();
 
   const int lane = threadIdx.x & 31;
   const int64_t nunits = a.ent.n * 5;
+  unsigned long long next = 0;
+  if (lane == 0) next = atomicAdd(a.ticket,1ull);
   while (true)
-    { unsigned long long u0 = 0;
-      if (lane == 0) u0 = atomicAdd(a.ticket,(unsigned long long) kFetch);
-      u0 = __shfl_sync(DX_FULL,u0,0);
-      if ((int64_t) u0 >= nunits) break;
-      for (int f = 0; f < kFetch; f++)
-        { const int64_t u = (int64_t) u0 + f;
-          if (u >= nunits) break;
-          const int64_t e = u / 5;
-          const int     s = (int) (u - e*5);                       // 0 del 1 tag 2 ins 3 mrg 4 sub
-          const int32_t rlen = a.ent.rlen[e];
-          const uint8_t *l0  = a.text + a.ent.line0[e];
-          const uint8_t *line = l0 + (int64_t) s*((int64_t) rlen + 1);
-          uint8_t *gptr = NULL;
-          if (MODE == 1)
-            { int64_t o = a.off[e];
-              for (int k = 0; k <= s; k++) o += a.bytes[e*6 + k];
-              gptr = a.out + o;
+    { const int64_t u = (int64_t) __shfl_sync(DX_FULL,next,0);
+      if (u >= nunits) break;
+      if (lane == 0) next = atomicAdd(a.ticket,1ull);              // in flight while this unit is coded
+      const int64_t e = u / 5;
+      const int     s = (int) (u - e*5);                           // 0 del 1 tag 2 ins 3 mrg 4 sub
+      const int32_t rlen = a.ent.rlen[e];
+      const uint8_t *l0  = a.text + a.ent.line0[e];
+      const uint8_t *line = l0 + (int64_t) s*((int64_t) rlen + 1);
+      uint8_t *gptr = NULL;
+      if (MODE == 1)
+        { int64_t o = a.off[e];
+          for (int k = 0; k <= s; k++) o += a.bytes[e*6 + k];
+          gptr = a.out + o;
+        }
+      if (s == 1)
+        { uint32_t kept = code_tags<MODE>(a,l0,line,rlen,lane,stage,gptr);
+          if (MODE == 0 && lane == 0) a.bytes[e*6 + 2] = (kept + 3u) >> 2;
+        }
+      else
+        { uint32_t bits, plast;
+          code_stream<MODE>(a,stab,line,rlen,s,lane,stage,queue,gptr,bits,plast);
+          if (MODE == 0 && lane == 0)
+            { a.bytes[e*6 + 1 + s] = stream_words(bits,plast,rlen)*4u;
+              if (s == 0) a.bytes[e*6] = well_bytes(a,e) + 12u;
             }
-          if (s == 1)
-            { uint32_t kept = code_tags<MODE>(a,l0,line,rlen,lane,stage,gptr);
-              if (MODE == 0 && lane == 0) a.bytes[e*6 + 2] = (kept + 3u) >> 2;
-            }
-          else
-            { uint32_t bits, plast;
-              code_stream<MODE>(a,stab,line,rlen,s,lane,stage,gptr,bits,plast);
-              if (MODE == 0 && lane == 0)
-                { a.bytes[e*6 + 1 + s] = stream_words(bits,plast,rlen)*4u;
-                  if (s == 0) a.bytes[e*6] = well_bytes(a,e) + 12u;
-                }
-              if (MODE == 1 && s == 0 && lane == 0)
-                { // entry header: well-delta bytes, beg, end, qv (dexqv.c:128-139)
-                  uint8_t *h = a.out + a.off[e];
-                  int32_t lwell = (e == 0) ? a.lwell_in : a.ent.well[e-1];
-                  const int32_t well = a.ent.well[e];
-                  while (well - lwell >= 255) { *h++ = 0xff; lwell += 255; }
-                  *h++ = (uint8_t) (well - lwell);
-                  const int32_t f3[3] = { a.ent.beg[e], a.ent.end[e], a.ent.qv[e] };
-                  for (int k = 0; k < 3; k++)
-                    for (int b = 0; b < 4; b++)
-                      *h++ = (uint8_t) ((uint32_t) f3[k] >> (8*b));
-                }
+          if (MODE == 1 && s == 0 && lane == 0)
+            { // entry header: well-delta bytes, beg, end, qv (dexqv.c:128-139)
+              uint8_t *h = a.out + a.off[e];
+              int32_t lwell = (e == 0) ? a.lwell_in : a.ent.well[e-1];
+              const int32_t well = a.ent.well[e];
+              while (well - lwell >= 255) { *h++ = 0xff; lwell += 255; }
+              *h++ = (uint8_t) (well - lwell);
+              const int32_t f3[3] = { a.ent.beg[e], a.ent.end[e], a.ent.qv[e] };
+              for (int k = 0; k < 3; k++)
+                for (int b = 0; b < 4; b++)
+                  *h++ = (uint8_t) ((uint32_t) f3[k] >> (8*b));
             }
         }
+      __syncwarp();
     }
 }
 
@@ -455,9 +518,10 @@ int dxk_qv_encode(dx_ctx *ctx, const uint8_t *d_text, size_t text_n, QvEntries e
   a.delchar = delchar; a.subchar = subchar; a.lossy = lossy; a.lwell_in = lwell_in;
   a.bytes = d_bytes; a.off = d_off; a.out = d_out; a.ticket = d_ticket;
 
-  const int grid = ctx->sm_count * 3;
-  const size_t smem0 = 6*256*4;
-  const size_t smem1 = 6*256*4 + (size_t) kEncWarps*kStageWords*4;
+  const int grid = ctx->sm_count * 2;
+  const size_t smem1 = 6*256*4 + (size_t) kEncWarps*kWarpWords*4;
+  const size_t smem0 = smem1;
+  DX_CUDA(ctx,cudaFuncSetAttribute(k_qv_code<0>,cudaFuncAttributeMaxDynamicSharedMemorySize,(int) smem0));
   DX_CUDA(ctx,cudaFuncSetAttribute(k_qv_code<1>,cudaFuncAttributeMaxDynamicSharedMemorySize,(int) smem1));
 
   DX_PROF_BEGIN(ctx); k_qv_code<0><<<grid,kEncThreads,smem0,ctx->stream>>>(a);
