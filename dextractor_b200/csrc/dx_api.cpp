@@ -11,7 +11,24 @@
 #include <stdlib.h>
 #include <string.h>
 #include <vector>
+#include <algorithm>
+#include <chrono>
 #include "dx_internal.h"
+
+// wall-clock marks of the host phases of a call, printed with DEXB200_DEBUG set
+struct DxPhases
+{ bool on; std::chrono::steady_clock::time_point t0; char buf[512]; size_t len;
+  DxPhases() : on(getenv("DEXB200_DEBUG") != NULL), len(0) { buf[0] = 0; t0 = std::chrono::steady_clock::now(); }
+  void mark(const char *what)
+  { if (!on) return;
+    auto t1 = std::chrono::steady_clock::now();
+    len += (size_t) snprintf(buf+len,sizeof(buf)-len," %s %.3f",what,
+                             std::chrono::duration<double,std::milli>(t1-t0).count());
+    if (len >= sizeof(buf)) len = sizeof(buf)-1;
+    t0 = t1;
+  }
+  void report(const char *call) { if (on) fprintf(stderr,"[dexb200 debug] %s host phases (ms):%s\n",call,buf); }
+};
 
 // ================================================================================================
 //  errors, context, arena
@@ -1011,7 +1028,30 @@ struct QvPlan
   int          plen;
   dx_qv_coding coding;
   size_t       text_len;
+  // entries discovered AND decoded in one pass (speculative decode into a scratch image):
+  bool         spec;
+  uint8_t     *d_tmp;         // the scratch image (lines only)
+  size_t       tmp_n;
+  std::vector<int64_t> src;   // per entry: offset of its lines in d_tmp, -1 = not decoded yet
 };
+
+// ticket order for the one-warp-per-entry decoder: the long entries first (they would otherwise be
+// the tail of the launch), the rest in file order
+static void lpt_order(const std::vector<CandInfo> &info, std::vector<int32_t> &order)
+{ const size_t N = info.size();
+  std::vector<std::pair<int32_t,int32_t> > big;
+  order.clear(); order.reserve(N);
+  for (size_t i = 0; i < N; i++)
+    { const int32_t rl = le32(info[i].field+4) - le32(info[i].field);
+      if (rl >= 32768) big.push_back(std::make_pair(-rl,(int32_t) i));
+    }
+  std::sort(big.begin(),big.end());
+  for (size_t k = 0; k < big.size(); k++) order.push_back(big[k].second);
+  for (size_t i = 0; i < N; i++)
+    { const int32_t rl = le32(info[i].field+4) - le32(info[i].field);
+      if (rl < 32768) order.push_back((int32_t) i);
+    }
+}
 
 struct QvWalkUser
 { const uint8_t *d_in; size_t n; const QvPlan *plan;
@@ -1060,7 +1100,7 @@ static int qv_walk_one(dx_ctx *ctx, void *user, int64_t q, int64_t *end, int64_t
 }
 
 static int plan_undexqv(dx_ctx *ctx, const uint8_t *d_in, size_t n, const int64_t *h_entry_off,
-                        int64_t nentries, int32_t well_in, bool need_streams, QvPlan &plan)
+                        int64_t nentries, int32_t well_in, bool need_streams, int upper, QvPlan &plan)
 { int rc;
   std::vector<uint8_t> head;
   if ((rc = peek(ctx,d_in,n,0,2 + 16384 + 100000,head)) != DX_OK) return rc;
@@ -1076,8 +1116,10 @@ static int plan_undexqv(dx_ctx *ctx, const uint8_t *d_in, size_t n, const int64_
   if (plan.coding.flip)
     return dx_fail(ctx,DX_E_KEY,"foreign-endian .dexqv is not supported");
   const size_t first = 2 + used;
+  DxPhases ph;
   plan.plen = (int) strlen(prefix.data());
   plan.d_soff = NULL; plan.d_start = NULL; plan.d_rlen = NULL; plan.d_tab = NULL; plan.d_tab2 = NULL;
+  plan.spec = false; plan.d_tmp = NULL; plan.tmp_n = 0; plan.src.clear();
 
   { QvDecTables2 *h2 = (QvDecTables2 *) malloc(sizeof(QvDecTables2));
     if (h2 == NULL) return DX_E_NOMEM;
@@ -1168,7 +1210,9 @@ static int plan_undexqv(dx_ctx *ctx, const uint8_t *d_in, size_t n, const int64_
     }
   else
     { int64_t *d_q = NULL, nc = 0;
+      ph.mark("tables");
       if ((rc = dxk_index_positions(ctx,DX_PRED_QVCAND,d_in,n,first + 1,&d_q,&nc)) != DX_OK) return rc;
+      ph.mark("index");
       const size_t N = (size_t) nc;
       int64_t  *d_fs    = (int64_t *) dx_arena_get(ctx,N*8);
       int32_t  *d_rlen  = (int32_t *) dx_arena_get(ctx,N*4);
@@ -1183,25 +1227,112 @@ static int plan_undexqv(dx_ctx *ctx, const uint8_t *d_in, size_t n, const int64_
       fs.resize(N);
       for (size_t i = 0; i < N; i++) fs[i] = q[i] + 12;
       if ((rc = upload(ctx,d_fs,fs.data(),N)) != DX_OK) return rc;
-      if ((rc = qv_walk(ctx,d_in,n,plan,d_fs,d_rlen,nc,d_soffc,d_stat)) != DX_OK) return rc;
+      std::vector<CandInfo> info;
+      if ((rc = download(ctx,d_info,N,info)) != DX_OK) return rc;
+      ph.mark("context");
+      std::vector<int64_t> tmp_off(N + 1,0);
+      if (need_streams && plan.v2 && plan.ver == 5 && getenv("DEXB200_NO_SPEC") == NULL)
+        { // decode every candidate right away into a scratch image laid out by the candidates'
+          // own lengths; the chain below decides which of them are entries
+          for (size_t i = 0; i < N; i++)
+            { int64_t rl = (int64_t) le32(info[i].field+4) - le32(info[i].field);
+              if (rl < 0 || rl >= (1 << 24)) rl = 0;
+              tmp_off[i+1] = tmp_off[i] + 5*(rl + 1);
+            }
+          plan.tmp_n = (size_t) tmp_off[N];
+          plan.d_tmp = (uint8_t *) dx_arena_get(ctx,plan.tmp_n + 64);
+          QvDecEntry *d_cent = (QvDecEntry *) dx_arena_get(ctx,N*sizeof(QvDecEntry));
+          if (!plan.d_tmp || !d_cent) return DX_E_NOMEM;
+          std::vector<QvDecEntry> cent(N);
+          for (size_t i = 0; i < N; i++)
+            { memset(&cent[i],0,sizeof(QvDecEntry));
+              cent[i].out_off = -1; cent[i].text_off = tmp_off[i];
+            }
+          if ((rc = upload(ctx,d_cent,cent.data(),N)) != DX_OK) return rc;
+          // A candidate that is not an entry decodes garbage for as long as its (random) length
+          // field says.  Bound it: an entry may contain a few false candidates, so candidate i must
+          // end before the fields of the kSpan-th candidate after it, not counting candidates
+          // closer than 64 bytes to the previous counted one (clusters in zero-rich data).  An
+          // entry that breaks this rule is reported bad and found again by the chain's slow path.
+          const int kSpan = 4;
+          std::vector<int64_t> limit(N);
+          { std::vector<size_t> nextfar(N);               // next candidate >= 64 bytes further on
+            size_t j = 0;
+            for (size_t i = 0; i < N; i++)
+              { if (j <= i) j = i + 1;
+                while (j < N && q[j] - q[i] < 64) j++;
+                nextfar[i] = j;
+              }
+            for (size_t i = 0; i < N; i++)
+              { size_t k = i;
+                for (int h = 0; h < kSpan && k < N; h++) k = nextfar[k];
+                limit[i] = (k < N) ? q[k] : (int64_t) n;
+              }
+          }
+          // ... and a candidate whose length field cannot fit before its limit even at the
+          // shortest code of the two streams that are never run-length coded is not decoded at all
+          { int minbits = 0;
+            for (int k = 2; k <= 3; k++)
+              { int mn = 32;
+                for (int x = 0; x < 256; x++)
+                  if (plan.coding.tab[k].lens[x] > 0 && plan.coding.tab[k].lens[x] < mn) mn = plan.coding.tab[k].lens[x];
+                minbits += (mn == 32) ? 0 : mn;
+              }
+            std::vector<int32_t> rl;
+            size_t skipped = 0;
+            if ((rc = download(ctx,d_rlen,N,rl)) != DX_OK) return rc;
+            for (size_t i = 0; i < N; i++)
+              if (rl[i] > 0 && q[i] + 12 + (((int64_t) rl[i]*minbits) >> 3) > limit[i])
+                { rl[i] = -1; skipped++; }
+            if (skipped)
+              if ((rc = upload(ctx,d_rlen,rl.data(),N)) != DX_OK) return rc;
+            if (getenv("DEXB200_DEBUG") != NULL)
+              fprintf(stderr,"[dexb200 debug] undexqv: %zu of %zu candidates cannot fit (min %d bits/position)\n",
+                      skipped,N,minbits);
+          }
+          std::vector<int32_t> order;
+          lpt_order(info,order);
+          int64_t *d_limit = (int64_t *) dx_arena_get(ctx,N*8);
+          int32_t *d_order = (int32_t *) dx_arena_get(ctx,N*4);
+          if (!d_limit || !d_order) return DX_E_NOMEM;
+          if ((rc = upload(ctx,d_limit,limit.data(),N)) != DX_OK) return rc;
+          if ((rc = upload(ctx,d_order,order.data(),N)) != DX_OK) return rc;
+          const dx_qv_coding &cd = plan.coding;
+          if ((rc = dxk_qv_decode5x(ctx,d_in,n,plan.d_tab4,cd.delchar,cd.subchar,upper,2,nc,d_fs,d_rlen,
+                                    d_cent,NULL,0,plan.d_tmp,d_soffc,d_stat,d_limit,d_order)) != DX_OK) return rc;
+          plan.spec = true;
+        }
+      else if ((rc = qv_walk(ctx,d_in,n,plan,d_fs,d_rlen,nc,d_soffc,d_stat)) != DX_OK) return rc;
+      ph.mark("launch");
       std::vector<int64_t> soff;
       std::vector<int32_t> stat;
-      std::vector<CandInfo> info;
       if ((rc = download(ctx,d_soffc,N*6,soff)) != DX_OK) return rc;
       if ((rc = download(ctx,d_stat,N,stat)) != DX_OK) return rc;
-      if ((rc = download(ctx,d_info,N,info)) != DX_OK) return rc;
+      ph.mark("decode+download");
       std::vector<int64_t> end(N);
       for (size_t i = 0; i < N; i++) end[i] = stat[i] ? -1 : soff[6*i+5];
       QvWalkUser user = { d_in, n, &plan, {} };
       std::vector<ChainEntry> chain;
       if ((rc = resolve_chain(ctx,d_in,n,first,12,q,end,info,qv_walk_one,&user,chain)) != DX_OK)
         return rc;
+      ph.mark("chain");
       const size_t M = chain.size();
+      if (getenv("DEXB200_DEBUG") != NULL)
+        { int64_t sumrl = 0, maxrl = 0;
+          for (size_t i = 0; i < N; i++)
+            { const int64_t rl = (int64_t) le32(info[i].field+4) - le32(info[i].field);
+              sumrl += rl; if (rl > maxrl) maxrl = rl;
+            }
+          fprintf(stderr,"[dexb200 debug] undexqv: %zu candidates (sum rlen %lld, max %lld), %zu entries, spec %d\n",
+                  N,(long long) sumrl,(long long) maxrl,M,(int) plan.spec);
+        }
       std::vector<int64_t> so(M*6), st(M);
       std::vector<int32_t> rl(M);
       hdrs.resize(M);
+      if (plan.spec) plan.src.resize(M);
       for (size_t i = 0; i < M; i++)
         { const ChainEntry &c = chain[i];
+          if (plan.spec) plan.src[i] = (c.cand >= 0) ? tmp_off[(size_t) c.cand] : -1;
           const int64_t *src = (c.cand >= 0) ? &soff[6*(size_t) c.cand]
                                              : &user.side[6*(size_t) (-2 - c.cand)];
           memcpy(&so[6*i],src,48);
@@ -1241,6 +1372,8 @@ static int plan_undexqv(dx_ctx *ctx, const uint8_t *d_in, size_t n, const int64_
       at += (size_t) (5*(rlen + 1));
     }
   plan.text_len = at;
+  ph.mark("layout");
+  ph.report("plan_undexqv");
   return DX_OK;
 }
 
@@ -1254,7 +1387,7 @@ extern "C" int dx_undexqv_dev(dx_ctx *ctx, const uint8_t *d_in, size_t n, int up
   cudaSetDevice(ctx->device);
   dx_arena_reset(ctx);
   QvPlan plan;
-  if ((rc = plan_undexqv(ctx,d_in,n,h_entry_off,nentries,well_in,true,plan)) != DX_OK) return rc;
+  if ((rc = plan_undexqv(ctx,d_in,n,h_entry_off,nentries,well_in,true,upper,plan)) != DX_OK) return rc;
   if (plan.text_len > cap)
     return dx_fail(ctx,DX_E_CAP,"output needs %zu bytes, buffer has %zu",plan.text_len,cap);
   const size_t N = plan.ent.size();
@@ -1264,7 +1397,38 @@ extern "C" int dx_undexqv_dev(dx_ctx *ctx, const uint8_t *d_in, size_t n, int up
   if ((rc = upload(ctx,d_ent,plan.ent.data(),N)) != DX_OK) return rc;
   DX_CUDA(ctx,cudaMemsetAsync(d_stat,0,4,ctx->stream));
   const dx_qv_coding &cd = plan.coding;
-  if (plan.v2 && plan.ver >= 4)
+  if (plan.spec)
+    { // the lines are already decoded (scratch image): write the headers and move them into place;
+      // entries the candidate filter missed (rare) are decoded now
+      int64_t *d_src = (int64_t *) dx_arena_get(ctx,N*8);
+      if (!d_src) return DX_E_NOMEM;
+      if ((rc = upload(ctx,d_src,plan.src.data(),N)) != DX_OK) return rc;
+      if ((rc = dxk_qv_assemble(ctx,plan.d_tmp,plan.tmp_n,d_ent,d_src,(int64_t) N,plan.d_prefix,plan.plen,
+                                d_out)) != DX_OK) return rc;
+      std::vector<size_t> miss;
+      for (size_t i = 0; i < N; i++) if (plan.src[i] < 0) miss.push_back(i);
+      rc = DX_OK;
+      if (!miss.empty())
+        { const size_t K = miss.size();
+          std::vector<int64_t> st, stall;
+          std::vector<int32_t> rl, rlall;
+          if ((rc = download(ctx,plan.d_start,N,stall)) != DX_OK) return rc;
+          if ((rc = download(ctx,plan.d_rlen,N,rlall)) != DX_OK) return rc;
+          std::vector<QvDecEntry> me(K);
+          st.resize(K); rl.resize(K);
+          for (size_t k = 0; k < K; k++) { st[k] = stall[miss[k]]; rl[k] = rlall[miss[k]]; me[k] = plan.ent[miss[k]]; }
+          int64_t *d_st = (int64_t *) dx_arena_get(ctx,K*8);
+          int32_t *d_rl = (int32_t *) dx_arena_get(ctx,K*4);
+          QvDecEntry *d_me = (QvDecEntry *) dx_arena_get(ctx,K*sizeof(QvDecEntry));
+          if (!d_st || !d_rl || !d_me) return DX_E_NOMEM;
+          if ((rc = upload(ctx,d_st,st.data(),K)) != DX_OK) return rc;
+          if ((rc = upload(ctx,d_rl,rl.data(),K)) != DX_OK) return rc;
+          if ((rc = upload(ctx,d_me,me.data(),K)) != DX_OK) return rc;
+          rc = dxk_qv_decode5(ctx,d_in,n,plan.d_tab4,cd.delchar,cd.subchar,upper,1,(int64_t) K,d_st,d_rl,d_me,
+                              plan.d_prefix,plan.plen,d_out,NULL,d_stat);
+        }
+    }
+  else if (plan.v2 && plan.ver >= 4)
     rc = (plan.ver == 5 ? dxk_qv_decode5 : dxk_qv_decode4)(ctx,d_in,n,plan.d_tab4,cd.delchar,cd.subchar,upper,1,(int64_t) N,
                         plan.d_start,plan.d_rlen,d_ent,plan.d_prefix,plan.plen,d_out,NULL,d_stat);
   else if (plan.v2)
@@ -1291,7 +1455,7 @@ extern "C" int dx_undexqv_size_dev(dx_ctx *ctx, const uint8_t *d_in, size_t n, s
   cudaSetDevice(ctx->device);
   dx_arena_reset(ctx);
   QvPlan plan;
-  if ((rc = plan_undexqv(ctx,d_in,n,NULL,0,0,false,plan)) != DX_OK) return rc;
+  if ((rc = plan_undexqv(ctx,d_in,n,NULL,0,0,false,0,plan)) != DX_OK) return rc;
   *out_len = plan.text_len;
   return DX_OK;
 }

@@ -180,6 +180,19 @@ int dxk_qv_decode5(dx_ctx *ctx, const uint8_t *d_in, size_t n, const QvDecTables
                    const int64_t *d_start, const int32_t *d_rlen, const QvDecEntry *d_ent,
                    const char *d_prefix, int plen, uint8_t *d_out, int64_t *d_soff, int32_t *d_status);
 
+// ... with a per-entry byte limit (an entry that would read past it is reported as bad) and a
+// ticket -> entry order (long entries first); either may be NULL
+int dxk_qv_decode5x(dx_ctx *ctx, const uint8_t *d_in, size_t n, const QvDecTables4 *d_tab,
+                    int delchar, int subchar, int upper, int write, int64_t count,
+                    const int64_t *d_start, const int32_t *d_rlen, const QvDecEntry *d_ent,
+                    const char *d_prefix, int plen, uint8_t *d_out, int64_t *d_soff, int32_t *d_status,
+                    const int64_t *d_limit, const int32_t *d_order);
+
+// move speculatively decoded lines (scratch image d_tmp, entry e at d_src[e], < 0 = skip) to their
+// final place and write the header lines
+int dxk_qv_assemble(dx_ctx *ctx, const uint8_t *d_tmp, size_t tmp_n, const QvDecEntry *d_ent,
+                    const int64_t *d_src, int64_t count, const char *d_prefix, int plen, uint8_t *d_out);
+
 // dx_pack.cu : .fasta/.arrow <-> 2-bit images
 struct FaEntries                // one fasta/arrow entry (structure of arrays in HBM)
 { int64_t  n;

@@ -50,7 +50,8 @@ struct Dec5Args
 { const uint8_t *in;
   int64_t        n;
   const QvDecTables4 *tab;
-  int32_t        delchar, subchar, upper, write;
+  int32_t        delchar, subchar, upper, write;   // write: 0 walk, 1 text + header, 2 lines only
+                                                   //        (speculative, per-entry status)
   int64_t        count;
   const int64_t *start;        // first stream byte of each entry (after beg/end/qv)
   const int32_t *rlen;
@@ -59,6 +60,8 @@ struct Dec5Args
   uint8_t       *out;
   int64_t       *soff;         // [count][6] or NULL
   int32_t       *status;       // [count] (walk) or [1] (decode)
+  const int64_t *limit;        // per entry: first byte the entry may not reach (NULL: the image end)
+  const int32_t *order;        // ticket -> entry (long entries first), NULL: identity
   unsigned long long *ticket;
   unsigned long long *dbg;     // optional counters [table][0 rounds, 1 windows, 2 streams, 3 restarts]
 };
@@ -155,7 +158,8 @@ struct StreamOut { uint32_t bytes, kept, bad; };
 // stream occupies in the file; kept = symbol items != rc.  `dst` != NULL: the line is written.
 template <bool RUN>
 __device__ __noinline__ StreamOut decode_stream(const Dec5Args &a, int slot, int64_t so, int32_t rlen,
-                                                int symtab, int runtab, int32_t rci, uint8_t *dst)
+                                                int symtab, int runtab, int32_t rci, uint8_t *dst,
+                                                int64_t budget)
 { Shared5 &sm = *reinterpret_cast<Shared5 *>(dx_dec5_smem);
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   StreamOut res; res.bytes = 0; res.kept = 0; res.bad = 0;
@@ -241,6 +245,7 @@ __device__ __noinline__ StreamOut decode_stream(const Dec5Args &a, int slot, int
 
       // ---- rounds: adopt the predecessor's exit; two fingers until the old path is met ----------
       uint32_t rounds = 0, restarts = 0;
+      bool giveup = false;
       while (true)
         { int changed = 0;
           uint32_t want = __shfl_up_sync(DX_FULL,myexit,1);
@@ -295,6 +300,12 @@ __device__ __noinline__ StreamOut decode_stream(const Dec5Args &a, int slot, int
             }
           rounds++;
           if (!__any_sync(DX_FULL,changed)) break;
+          if (a.limit != NULL && rounds >= 12u) { giveup = true; break; }
+        }
+      if (giveup)                     // speculative modes: this does not look like a code stream (a false
+        { bd = 1;                     // candidate); a true entry given up here is found by the slow path
+          res.bytes = wword*4u;
+          break;
         }
       if (a.dbg != NULL)
         { if (lane == 0) { atomicAdd(&a.dbg[symtab*4],(unsigned long long) rounds);
@@ -391,7 +402,7 @@ __device__ __noinline__ StreamOut decode_stream(const Dec5Args &a, int slot, int
       done  += total;
       carry  = __shfl_sync(DX_FULL,myexit,nact-1) - ((nact*kS) << 1);
       wword += nact*kSW;
-      if (so + (int64_t) wword*4 > a.n + 8)           // ran off the image: corrupt / false start
+      if (so + (int64_t) wword*4 > budget + 8)           // ran off the image / its budget: corrupt or false start
         { bd = 1;
           res.bytes = wword*4u;
           break;
@@ -484,8 +495,10 @@ k_qv_decode5(Dec5Args a)
   while (true)
     { unsigned long long tk = 0;
       if (lane == 0) tk = atomicAdd(a.ticket,1ull);
-      const int64_t e = (int64_t) __shfl_sync(DX_FULL,tk,0);
-      if (e >= a.count) break;
+      const int64_t t = (int64_t) __shfl_sync(DX_FULL,tk,0);
+      if (t >= a.count) break;
+      const int64_t e = (a.order != NULL) ? (int64_t) a.order[t] : t;
+      const int64_t lim = (a.limit != NULL) ? a.limit[e] : a.n;
       const int32_t L = a.rlen[e];
       int64_t at = a.start[e];
       int64_t o[6];
@@ -493,7 +506,7 @@ k_qv_decode5(Dec5Args a)
       if (a.write)
         { const QvDecEntry en = a.ent[e];
           line = a.out + en.text_off;
-          if (lane == 0)
+          if (lane == 0 && a.write == 1)
             { uint8_t *h = a.out + en.out_off;          // "%s/%d/%d_%d RQ=0.%d\n" (undexqv.c:182)
               int hl = 0;
               for (int k = 0; k < a.plen; k++) h[hl++] = (uint8_t) a.prefix[k];
@@ -509,46 +522,133 @@ k_qv_decode5(Dec5Args a)
       const int64_t stride = (int64_t) L + 1;
       uint32_t bad = 0;
       StreamOut r;
-
-      o[0] = at;
-      if (a.delchar >= 0) r = decode_stream<true >(a,0,at,L,0,1,a.delchar,line);
-      else                r = decode_stream<false>(a,0,at,L,0,1,-1,line);
-      at += r.bytes; bad |= r.bad;
-      o[1] = at;
-      const uint32_t clen = (a.delchar < 0) ? (uint32_t) L : r.kept;
-      if (a.write && at + (int64_t) ((clen + 3) >> 2) <= a.n)
-        { __syncwarp();                                      // the del line is complete in global memory
-          write_tags(a,line,a.in + at,L,line + stride);
+      for (int k = 0; k < 6; k++) o[k] = at;
+      if (L < 0)                                             // ruled out by the host
+        { if (lane == 0 && a.write != 1) a.status[e] = 1;
+          continue;
         }
-      at += (clen + 3) >> 2;
-      o[2] = at;
-      r = decode_stream<false>(a,1,at,L,2,0,-1,a.write ? line + 2*stride : NULL);
-      at += r.bytes; bad |= r.bad;
-      o[3] = at;
-      r = decode_stream<false>(a,2,at,L,3,0,-1,a.write ? line + 3*stride : NULL);
-      at += r.bytes; bad |= r.bad;
-      o[4] = at;
-      if (a.subchar >= 0) r = decode_stream<true >(a,3,at,L,4,5,a.subchar,a.write ? line + 4*stride : NULL);
-      else                r = decode_stream<false>(a,3,at,L,4,5,-1,a.write ? line + 4*stride : NULL);
-      at += r.bytes; bad |= r.bad;
-      o[5] = at;
+
+      // a candidate that turns out not to be an entry (speculative modes) is dropped at the first sign
+      do
+        { o[0] = at;
+          if (a.delchar >= 0) r = decode_stream<true >(a,0,at,L,0,1,a.delchar,line,lim);
+          else                r = decode_stream<false>(a,0,at,L,0,1,-1,line,lim);
+          at += r.bytes; bad |= r.bad;
+          o[1] = at;
+          if (bad && a.write != 1) break;
+          const uint32_t clen = (a.delchar < 0) ? (uint32_t) L : r.kept;
+          if (a.write && at + (int64_t) ((clen + 3) >> 2) <= a.n)
+            { __syncwarp();                                      // the del line is complete in global memory
+              write_tags(a,line,a.in + at,L,line + stride);
+            }
+          at += (clen + 3) >> 2;
+          o[2] = at;
+          r = decode_stream<false>(a,1,at,L,2,0,-1,a.write ? line + 2*stride : NULL,lim);
+          at += r.bytes; bad |= r.bad;
+          o[3] = at;
+          if (bad && a.write != 1) break;
+          r = decode_stream<false>(a,2,at,L,3,0,-1,a.write ? line + 3*stride : NULL,lim);
+          at += r.bytes; bad |= r.bad;
+          o[4] = at;
+          if (bad && a.write != 1) break;
+          if (a.subchar >= 0) r = decode_stream<true >(a,3,at,L,4,5,a.subchar,a.write ? line + 4*stride : NULL,lim);
+          else                r = decode_stream<false>(a,3,at,L,4,5,-1,a.write ? line + 4*stride : NULL,lim);
+          at += r.bytes; bad |= r.bad;
+          o[5] = at;
+        }
+      while (false);
       if (lane == 0)
-        { if (at > a.n) bad = 1;
+        { if (at > lim) bad = 1;
           if (a.soff != NULL)
             for (int k = 0; k < 6; k++) a.soff[e*6 + k] = o[k];
-          if (a.write) { if (bad) atomicExch(a.status,1); }
+          if (a.write == 1) { if (bad) atomicExch(a.status,1); }
           else a.status[e] = (int32_t) bad;
         }
       __syncwarp();
     }
 }
 
+
+// ---- assembling the output of a speculative decode -------------------------------------------------
+// The entries of a .dexqv whose boundaries had to be discovered are decoded BEFORE the chain of
+// entries is verified, into a scratch image whose layout depends on the candidates alone (lines
+// only).  Once the host has accepted the chain, one warp per entry writes the header line
+// (undexqv.c:182) and moves the five lines to their place in the text.
+struct AsmArgs
+{ const uint8_t *tmp; const uint8_t *tmp_end16;
+  const QvDecEntry *ent; const int64_t *src; int64_t count;
+  const char *prefix; int32_t plen;
+  uint8_t *out;
+};
+
+__global__ void __launch_bounds__(256)
+k_qv_assemble(AsmArgs a)
+{ const uint32_t lane = threadIdx.x & 31u;
+  const int64_t nwarp = ((int64_t) gridDim.x * blockDim.x) >> 5;
+  for (int64_t e = ((int64_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5; e < a.count; e += nwarp)
+    { const int64_t so = a.src[e];
+      if (so < 0) continue;                                  // decoded in place by k_qv_decode5
+      const QvDecEntry en = a.ent[e];
+      if (lane == 0)
+        { uint8_t *h = a.out + en.out_off;
+          int hl = 0;
+          for (int k = 0; k < a.plen; k++) h[hl++] = (uint8_t) a.prefix[k];
+          h[hl++] = '/'; hl += fmt_int5(h+hl,en.well);
+          h[hl++] = '/'; hl += fmt_int5(h+hl,en.beg);
+          h[hl++] = '_'; hl += fmt_int5(h+hl,en.end);
+          const char *rq = " RQ=0.";
+          for (int k = 0; k < 6; k++) h[hl++] = (uint8_t) rq[k];
+          hl += fmt_int5(h+hl,en.qv);
+          h[hl++] = '\n';
+        }
+      const int64_t n = 5*((int64_t) en.end - en.beg + 1);
+      uint8_t *dst = a.out + en.text_off;
+      const uint8_t *src = a.tmp + so;
+      int64_t head = (16 - (int64_t) (reinterpret_cast<uintptr_t>(dst) & 15)) & 15;
+      if (head > n) head = n;
+      if ((int64_t) lane < head) dst[lane] = src[lane];
+      const int64_t nvec = (n - head) >> 4;
+      for (int64_t i = lane; i < nvec; i += 32)
+        dx_stg16(dst + head + i*16,dx_ld16_any(src + head + i*16,a.tmp_end16));
+      const int64_t done = head + nvec*16;
+      if ((int64_t) lane < n - done) dst[done + lane] = src[done + lane];
+    }
+}
+
 }  // namespace
+
+int dxk_qv_assemble(dx_ctx *ctx, const uint8_t *d_tmp, size_t tmp_n, const QvDecEntry *d_ent,
+                    const int64_t *d_src, int64_t count, const char *d_prefix, int plen, uint8_t *d_out)
+{ if (count == 0) return DX_OK;
+  AsmArgs a;
+  a.tmp = d_tmp; a.tmp_end16 = d_tmp + ((tmp_n + 15) & ~(size_t) 15);
+  a.ent = d_ent; a.src = d_src; a.count = count; a.prefix = d_prefix; a.plen = plen; a.out = d_out;
+  int64_t grid = (count + 7) / 8;
+  if (grid > (int64_t) ctx->sm_count * 8) grid = (int64_t) ctx->sm_count * 8;
+  DX_PROF_BEGIN(ctx); k_qv_assemble<<<(unsigned) grid,256,0,ctx->stream>>>(a);
+  DX_LAUNCHED(ctx,"k_qv_assemble");
+  return DX_OK;
+}
+
+int dxk_qv_decode5x(dx_ctx *ctx, const uint8_t *d_in, size_t n, const QvDecTables4 *d_tab,
+                    int delchar, int subchar, int upper, int write, int64_t count,
+                    const int64_t *d_start, const int32_t *d_rlen, const QvDecEntry *d_ent,
+                    const char *d_prefix, int plen, uint8_t *d_out, int64_t *d_soff, int32_t *d_status,
+                    const int64_t *d_limit, const int32_t *d_order);
 
 int dxk_qv_decode5(dx_ctx *ctx, const uint8_t *d_in, size_t n, const QvDecTables4 *d_tab,
                    int delchar, int subchar, int upper, int write, int64_t count,
                    const int64_t *d_start, const int32_t *d_rlen, const QvDecEntry *d_ent,
                    const char *d_prefix, int plen, uint8_t *d_out, int64_t *d_soff, int32_t *d_status)
+{ return dxk_qv_decode5x(ctx,d_in,n,d_tab,delchar,subchar,upper,write,count,d_start,d_rlen,d_ent,d_prefix,plen,
+                         d_out,d_soff,d_status,NULL,NULL);
+}
+
+int dxk_qv_decode5x(dx_ctx *ctx, const uint8_t *d_in, size_t n, const QvDecTables4 *d_tab,
+                    int delchar, int subchar, int upper, int write, int64_t count,
+                    const int64_t *d_start, const int32_t *d_rlen, const QvDecEntry *d_ent,
+                    const char *d_prefix, int plen, uint8_t *d_out, int64_t *d_soff, int32_t *d_status,
+                    const int64_t *d_limit, const int32_t *d_order)
 { if (count == 0) return DX_OK;
   unsigned long long *d_ticket = (unsigned long long *) dx_arena_get(ctx,8);
   if (d_ticket == NULL) return DX_E_NOMEM;
@@ -559,8 +659,9 @@ int dxk_qv_decode5(dx_ctx *ctx, const uint8_t *d_in, size_t n, const QvDecTables
   a.count = count; a.start = d_start; a.rlen = d_rlen; a.ent = d_ent;
   a.prefix = d_prefix; a.plen = plen; a.out = d_out; a.soff = d_soff; a.status = d_status;
   a.ticket = d_ticket;
+  a.limit = d_limit; a.order = d_order;
   a.dbg = NULL;
-  if (getenv("DEXB200_DEBUG") != NULL)
+  if (getenv("DEXB200_DEBUG_DEC") != NULL)
     { a.dbg = (unsigned long long *) dx_arena_get(ctx,32*8);
       if (a.dbg == NULL) return DX_E_NOMEM;
       DX_CUDA(ctx,cudaMemsetAsync(a.dbg,0,32*8,ctx->stream));
@@ -570,7 +671,7 @@ int dxk_qv_decode5(dx_ctx *ctx, const uint8_t *d_in, size_t n, const QvDecTables
   int64_t grid = (count + kWarps - 1) / kWarps;
   if (grid > ctx->sm_count) grid = ctx->sm_count;
   DX_PROF_BEGIN(ctx); k_qv_decode5<<<(unsigned) grid,kThreads,smem,ctx->stream>>>(a);
-  DX_LAUNCHED(ctx,write ? "k_qv_decode5" : "k_qv_walk5");
+  DX_LAUNCHED(ctx,write == 1 ? "k_qv_decode5" : write == 2 ? "k_qv_decode5_spec" : "k_qv_walk5");
   if (a.dbg != NULL)
     { unsigned long long h[32];
       DX_CUDA(ctx,cudaMemcpyAsync(h,a.dbg,sizeof(h),cudaMemcpyDeviceToHost,ctx->stream));

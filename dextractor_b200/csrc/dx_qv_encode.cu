@@ -157,58 +157,57 @@ struct LaneSink
 };
 
 // ---- plain stream: one Huffman item per symbol (Encode, QV.c:386-443) --------------------------------
+// One row (32 lanes x 16 bytes) per iteration, the next row's chunk already in flight.  The code is
+// kept small on purpose: the kernel is instruction-cache bound when every loop is unrolled.
 template <int MODE>
 __device__ void code_plain(const EncArgs &a, const uint32_t *sym, const uint8_t *line, int32_t rlen,
                            uint32_t lossmask, int lane, WarpBits &wb, uint32_t &total_bits,
                            uint32_t &plast_out)
 { LineWalk lw; lw.set(line,rlen);
   uint32_t mybits = 0;                                   // MODE 0: lane-local sum over the line
-  for (int32_t c0 = 0; c0 < lw.nchunk; c0 += 128)
-    { uint4 v[4];
+  uint4 nxt = (lane < lw.nchunk) ? dx_ldg16(lw.base + (int64_t) lane*16) : make_uint4(0,0,0,0);
+#pragma unroll 1
+  for (int32_t c0 = 0; c0 < lw.nchunk; c0 += 32)
+    { const int32_t c = c0 + lane;
+      const uint4 v = nxt;
+      nxt = (c + 32 < lw.nchunk) ? dx_ldg16(lw.base + (int64_t) (c + 32)*16) : make_uint4(0,0,0,0);
+      const uint32_t valid = lw.valid(c);
+      const uint32_t w[4] = { v.x & lossmask, v.y & lossmask, v.z & lossmask, v.w & lossmask };
+      uint32_t e[16];
+      uint32_t bits = 0, esc = 0;
 #pragma unroll
-      for (int j = 0; j < 4; j++)
-        { const int32_t c = c0 + j*32 + lane;
-          v[j] = (c < lw.nchunk) ? dx_ldg16(lw.base + (int64_t) c*16) : make_uint4(0,0,0,0);
+      for (int i = 0; i < 16; i++)
+        { const uint32_t x = (w[i >> 2] >> ((i & 3)*8)) & 0xffu;
+          uint32_t t = sym[x];
+          if (!((valid >> i) & 1u)) t = 0;
+          e[i] = t;
+          bits += E_LEN(t);
+          esc  |= t;
         }
+      if (MODE == 0) { mybits += bits; continue; }
+      const uint32_t inc = dx_warp_incl_sum(bits,lane);
+      const uint32_t row = __shfl_sync(DX_FULL,inc,31);
+      wb.reserve<false>(row,lane);
+      LaneSink sk;
+      sk.start(wb.bitpos() + inc - bits);
+      if (!__any_sync(DX_FULL,E_ESC(esc) != 0u))
+        {
 #pragma unroll
-      for (int j = 0; j < 4; j++)
-        { const int32_t c = c0 + j*32 + lane;
-          if (c0 + j*32 >= lw.nchunk) break;                        // warp-uniform
-          const uint32_t valid = lw.valid(c);
-          const uint32_t w[4] = { v[j].x & lossmask, v[j].y & lossmask, v[j].z & lossmask, v[j].w & lossmask };
-          uint32_t e[16];
-          uint32_t bits = 0, esc = 0;
-#pragma unroll
+          for (int i = 0; i < 16; i += 2)                  // codes <= 16 bits: two per step
+            { const uint32_t l1 = E_LEN(e[i+1]);
+              sk.put(wb.stage,(E_BITS(e[i]) << l1) | E_BITS(e[i+1]),E_LEN(e[i]) + l1);
+            }
+        }
+      else                                                 // a literal somewhere in the row (rare)
+        {
+#pragma unroll 1
           for (int i = 0; i < 16; i++)
-            { const uint32_t x = (w[i >> 2] >> ((i & 3)*8)) & 0xffu;
-              uint32_t t = sym[x];
-              if (valid != 0xffffu && !((valid >> i) & 1u)) t = 0;
-              e[i] = t;
-              bits += E_LEN(t);
-              esc  |= t;
+            { uint32_t t = sym[dx_byte_of(v,i) & lossmask & 0xffu];
+              if (!((valid >> i) & 1u)) t = 0;
+              sk.put(wb.stage,E_BITS(t),E_LEN(t));
             }
-          if (MODE == 0) { mybits += bits; continue; }
-          const uint32_t inc = dx_warp_incl_sum(bits,lane);
-          const uint32_t row = __shfl_sync(DX_FULL,inc,31);
-          wb.reserve<false>(row,lane);
-          LaneSink sk;
-          sk.start(wb.bitpos() + inc - bits);
-          if (!E_ESC(esc))
-            {
-#pragma unroll
-              for (int i = 0; i < 16; i += 2)              // codes <= 16 bits: two per step
-                { const uint32_t l1 = E_LEN(e[i+1]);
-                  sk.put(wb.stage,(E_BITS(e[i]) << l1) | E_BITS(e[i+1]),E_LEN(e[i]) + l1);
-                }
-            }
-          else
-            {
-#pragma unroll
-              for (int i = 0; i < 16; i++)
-                sk.put(wb.stage,E_BITS(e[i]),E_LEN(e[i]));
-            }
-          sk.finish(wb,lane);
         }
+      sk.finish(wb,lane);
     }
   if (MODE == 0) total_bits = dx_warp_sum(mybits);
   else           total_bits = wb.total();
@@ -227,62 +226,55 @@ __device__ void code_run(const EncArgs &a, const uint32_t *sym, const uint32_t *
   uint32_t qhead = 0, qtail = 0;                         // ring positions (warp-uniform)
   int32_t  prevpos = -1;                                 // last position that was not the run character
   uint32_t mybits = 0;
-
-  // code n (<= 32) queued items, lane i takes item qhead + i
-  auto batch = [&](uint32_t n)
-    { uint32_t R = 0, E = 0, r = 0, bits = 0;
-      int32_t p = 0;
-      if ((uint32_t) lane < n)
-        { const uint32_t it = queue[(qhead + lane) & (kQueue-1)];
-          p = (int32_t) (it >> 8);
-          const int32_t pp = (lane == 0) ? prevpos : (int32_t) (queue[(qhead + lane - 1) & (kQueue-1)] >> 8);
-          r = (uint32_t) (p - pp - 1);
-          R = run[min(r,255u)];
-          E = sym[it & 0xffu];
-          bits = E_LEN(R) + (E_ESC(R) ? 16u : 0u) + E_LEN(E);
-        }
-      prevpos = __shfl_sync(DX_FULL,p,n-1);
-      qhead += n;
-      if (MODE == 0) { mybits += bits; return; }
-      const uint32_t inc = dx_warp_incl_sum(bits,lane);
-      const uint32_t row = __shfl_sync(DX_FULL,inc,31);
-      wb.reserve<false>(row,lane);
-      LaneSink sk;
-      sk.start(wb.bitpos() + inc - bits);
-      sk.put(wb.stage,E_BITS(R) & 0xffffu,E_LEN(R));
-      if (E_ESC(R)) sk.put(wb.stage,r & 0xffffu,16);
-      sk.put(wb.stage,E_BITS(E),E_LEN(E));
-      sk.finish(wb,lane);
-    };
-
-  for (int32_t c0 = 0; c0 < lw.nchunk; c0 += 128)
-    { uint4 v[4];
-#pragma unroll
-      for (int j = 0; j < 4; j++)
-        { const int32_t c = c0 + j*32 + lane;
-          v[j] = (c < lw.nchunk) ? dx_ldg16(lw.base + (int64_t) c*16) : make_uint4(0,0,0,0);
-        }
-#pragma unroll
-      for (int j = 0; j < 4; j++)
-        { const int32_t c = c0 + j*32 + lane;
-          if (c0 + j*32 >= lw.nchunk) break;                        // warp-uniform
+  uint4 nxt = (lane < lw.nchunk) ? dx_ldg16(lw.base + (int64_t) lane*16) : make_uint4(0,0,0,0);
+#pragma unroll 1
+  for (int32_t c0 = 0; c0 < lw.nchunk + 32; c0 += 32)    // one extra round drains the queue
+    { const bool last = (c0 >= lw.nchunk);
+      if (!last)
+        { const int32_t c = c0 + lane;
+          const uint4 v = nxt;
+          nxt = (c + 32 < lw.nchunk) ? dx_ldg16(lw.base + (int64_t) (c + 32)*16) : make_uint4(0,0,0,0);
           const int32_t p0 = c*16 - lw.skew;
-          uint32_t m = lw.valid(c) & ~dx_eq_mask16(v[j],rc);
+          uint32_t m = lw.valid(c) & ~dx_eq_mask16(v,rc);
           const uint32_t cnt = __popc(m);
           const uint32_t inc = dx_warp_incl_sum(cnt,lane);
-          const uint32_t row = __shfl_sync(DX_FULL,inc,31);
           uint32_t at = qtail + inc - cnt;
           while (m)
             { const int i = __ffs(m) - 1; m &= m - 1;
-              queue[at & (kQueue-1)] = ((uint32_t) (p0 + i) << 8) | dx_byte_of(v[j],i);
+              queue[at & (kQueue-1)] = ((uint32_t) (p0 + i) << 8) | dx_byte_of(v,i);
               at++;
             }
-          qtail += row;
+          qtail += __shfl_sync(DX_FULL,inc,31);
           __syncwarp();
-          while (qtail - qhead >= 32u) batch(32u);
+        }
+      // code the queued items 32 at a time, lane i takes item qhead + i
+#pragma unroll 1
+      while (qtail - qhead >= 32u || (last && qtail != qhead))
+        { const uint32_t n = min(32u,qtail - qhead);
+          uint32_t R = 0, E = 0, r = 0, bits = 0;
+          int32_t p = 0;
+          if ((uint32_t) lane < n)
+            { const uint32_t it = queue[(qhead + lane) & (kQueue-1)];
+              p = (int32_t) (it >> 8);
+              const int32_t pp = (lane == 0) ? prevpos : (int32_t) (queue[(qhead + lane - 1) & (kQueue-1)] >> 8);
+              r = (uint32_t) (p - pp - 1);
+              R = run[min(r,255u)];
+              E = sym[it & 0xffu];
+              bits = E_LEN(R) + (E_ESC(R) ? 16u : 0u) + E_LEN(E);
+            }
+          prevpos = __shfl_sync(DX_FULL,p,n-1);
+          qhead += n;
+          if (MODE == 0) { mybits += bits; continue; }
+          const uint32_t inc = dx_warp_incl_sum(bits,lane);
+          wb.reserve<false>(__shfl_sync(DX_FULL,inc,31),lane);
+          LaneSink sk;
+          sk.start(wb.bitpos() + inc - bits);
+          sk.put(wb.stage,E_BITS(R) & 0xffffu,E_LEN(R));
+          if (E_ESC(R)) sk.put(wb.stage,r & 0xffffu,16);
+          sk.put(wb.stage,E_BITS(E),E_LEN(E));
+          sk.finish(wb,lane);
         }
     }
-  if (qtail != qhead) batch(qtail - qhead);
 
   // trailing run of the run character (QV.c:475-487 when k reaches rlen inside a run)
   uint32_t Rt = 0, rt = 0;
@@ -290,12 +282,12 @@ __device__ void code_run(const EncArgs &a, const uint32_t *sym, const uint32_t *
   if (trailing)
     { rt = (uint32_t) (rlen-1-prevpos);
       Rt = run[min(rt,255u)];
-      const uint32_t bits = (lane == 0) ? E_LEN(Rt) + (E_ESC(Rt) ? 16u : 0u) : 0u;
-      if (MODE == 0) mybits += bits;
+      const uint32_t tb = E_LEN(Rt) + (E_ESC(Rt) ? 16u : 0u);
+      if (MODE == 0) mybits += (lane == 0) ? tb : 0u;
       else
         { wb.reserve<false>(32u,lane);
           LaneSink sk;
-          sk.start(wb.bitpos() + (lane == 0 ? 0u : E_LEN(Rt) + (E_ESC(Rt) ? 16u : 0u)));
+          sk.start(wb.bitpos() + (lane == 0 ? 0u : tb));
           if (lane == 0)
             { sk.put(wb.stage,E_BITS(Rt) & 0xffffu,E_LEN(Rt));
               if (E_ESC(Rt)) sk.put(wb.stage,rt & 0xffffu,16);
@@ -357,6 +349,7 @@ __device__ uint32_t code_tags(const EncArgs &a, const uint8_t *del, const uint8_
   LineWalk lw; lw.set(tag,rlen);
   WarpBits wb; wb.init(stage,gptr);
   uint32_t mykept = 0;
+#pragma unroll 1
   for (int32_t c0 = 0; c0 < lw.nchunk; c0 += 32)
     { const int32_t c = c0 + lane;
       const int32_t p0 = c*16 - lw.skew;

@@ -15,7 +15,6 @@
 
 namespace {
 
-constexpr int kFetch       = 4;          // entries (lines of one stream) claimed per ticket
 
 // ---- delChar ---------------------------------------------------------------------------------
 
@@ -97,17 +96,19 @@ k_probe_sub(const uint8_t *text, QvEntries ent, uint64_t tot_in, const uint64_t 
 // this kernel ATOMS-bound.  Here every THREAD owns a private set of one-byte counters in shared
 // memory and increments them with plain load / add / store (no atomics, and no bank conflicts:
 // counter b of thread t lives in word (b>>2)*T + t, byte b&3).  A counter that wraps to 0 adds
-// 256 to a CTA-wide 64-bit histogram (one rare atomic per 256 hits); what is left in the byte
-// counters is summed when the CTA moves on to the next stream and at the end.
+// 256 to a CTA-wide 64-bit histogram (one rare atomic per 256 hits).  When a warp moves on to the
+// next stream (tickets are handed out in stream-major order) it sums its 32 lanes' counters with
+// shuffles and adds them to the CTA-wide histogram of the stream it leaves; there is no CTA
+// barrier before the end of the kernel.
 //
-//   RUN = false  streams without a run character: every byte is counted.  768 threads x 256 B.
+//   RUN = false  streams without a run character: every byte is counted; the bytes of a 16-byte
+//                chunk that lie outside the line are zeroed and counted in bin 0, which is
+//                corrected by the (known) number of such bytes.  768 threads x 256 B.
 //   RUN = true   del / sub with a run character: run bytes are skipped by a SWAR compare (their
-//                count is recovered by subtraction on the host) and, from entry e_del / e_sub on,
-//                the run length before every other symbol is counted too.  384 threads x 512 B.
-//
-// Work is handed out as (stream, block of kFetch entries) tickets in stream-major order, one line
-// per warp at a time; a warp whose ticket belongs to a later stream waits at a CTA barrier until
-// all warps have left the current stream, then the CTA flushes its counters.
+//                count is recovered by subtraction on the host); the (position, symbol) pairs of
+//                the other bytes are compacted into a per-warp queue and counted 32 at a time,
+//                together with the run length before each (position minus the queue
+//                neighbour's position), from entry e_del / e_sub on.  384 threads x 512 B.
 
 struct HistArgs
 { const uint8_t *text;
@@ -120,11 +121,16 @@ struct HistArgs
   unsigned long long *ghist;       // [6][256]
 };
 
+constexpr int kHistQueue = 544;    // a row adds <= 512 items to < 32 left over
+
 template <bool RUN> struct HistCfg
 { static constexpr int kThreads = RUN ? 384 : 768;
   static constexpr int kBins    = RUN ? 512 : 256;
   static constexpr int kRows    = kBins / 4;
-  static constexpr size_t kSmem = (size_t) kRows * kThreads * 4 + (size_t) kBins * 8;
+  static constexpr int kStreams = RUN ? 2 : 4;
+  static constexpr size_t kCnt  = (size_t) kRows * kThreads * 4;
+  static constexpr size_t kWide = (size_t) kStreams * kBins * 8;
+  static constexpr size_t kSmem = kCnt + kWide + (RUN ? (size_t) (kThreads/32) * kHistQueue * 4 : 0);
 };
 
 template <int T>
@@ -135,35 +141,29 @@ __device__ __forceinline__ void bump(uint8_t *mine, unsigned long long *wide, ui
   if (c == 256u) atomicAdd(&wide[b],256ull);
 }
 
+// the warp adds its lanes' byte counters to the CTA-wide histogram and clears them
 template <bool RUN>
-__device__ void hist_flush(const HistArgs &a, int s, uint32_t *cnt, unsigned long long *wide)
+__device__ __noinline__ void hist_warp_flush(uint32_t *cnt, unsigned long long *wide, uint32_t pad)
 { typedef HistCfg<RUN> C;
-  constexpr int G = C::kThreads / C::kRows;            // threads per row of 4 bins
-  __syncthreads();
-  { const int r = threadIdx.x / G, k0 = threadIdx.x % G;
-    uint32_t a0 = 0, a1 = 0;
-    uint32_t *row = cnt + (size_t) r * C::kThreads;
-    for (int k = k0; k < C::kThreads; k += G)
-      { const uint32_t w = row[k];
-        row[k] = 0;
-        a0 += w & 0x00ff00ffu;
-        a1 += (w >> 8) & 0x00ff00ffu;
-      }
-    if (a0 & 0xffffu) atomicAdd(&wide[4*r],  (unsigned long long) (a0 & 0xffffu));
-    if (a1 & 0xffffu) atomicAdd(&wide[4*r+1],(unsigned long long) (a1 & 0xffffu));
-    if (a0 >> 16)     atomicAdd(&wide[4*r+2],(unsigned long long) (a0 >> 16));
-    if (a1 >> 16)     atomicAdd(&wide[4*r+3],(unsigned long long) (a1 >> 16));
-  }
-  __syncthreads();
-  for (int b = threadIdx.x; b < C::kBins; b += C::kThreads)
-    { const unsigned long long v = wide[b];
-      wide[b] = 0;
-      if (v)
-        { const int tab = (b < 256) ? s : (s == 0 ? 4 : 5);
-          atomicAdd(&a.ghist[tab*256 + (b & 255)],v);
+  const int lane = threadIdx.x & 31;
+  __syncwarp();
+#pragma unroll 1
+  for (int r = 0; r < C::kRows; r++)
+    { uint32_t *w = cnt + (size_t) r * C::kThreads + threadIdx.x;
+      const uint32_t v = *w;
+      *w = 0;
+      uint32_t a0 = v & 0x00ff00ffu, a1 = (v >> 8) & 0x00ff00ffu;     // 32 x 255 fits 16 bits
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1)
+        { a0 += __shfl_xor_sync(DX_FULL,a0,d);
+          a1 += __shfl_xor_sync(DX_FULL,a1,d);
         }
+      const uint32_t mine = (lane == 0) ? (a0 & 0xffffu) : (lane == 1) ? (a1 & 0xffffu)
+                          : (lane == 2) ? (a0 >> 16) : (a1 >> 16);
+      if (lane < 4 && mine) atomicAdd(&wide[4*r + lane],(unsigned long long) mine);
     }
-  __syncthreads();
+  if (lane == 0 && pad) atomicAdd(&wide[0],0ull - (unsigned long long) pad);   // bytes outside the lines
+  __syncwarp();
 }
 
 template <bool RUN>
@@ -173,98 +173,134 @@ k_qv_hist(HistArgs a)
   constexpr int T = C::kThreads;
   extern __shared__ __align__(16) uint8_t dx_hist_smem[];
   uint32_t *cnt = reinterpret_cast<uint32_t *>(dx_hist_smem);                  // [kRows][T] words
-  unsigned long long *wide = reinterpret_cast<unsigned long long *>(dx_hist_smem + (size_t) C::kRows*T*4);
+  unsigned long long *wide = reinterpret_cast<unsigned long long *>(dx_hist_smem + C::kCnt);
+  uint32_t *queue = reinterpret_cast<uint32_t *>(dx_hist_smem + C::kCnt + C::kWide) +
+                    (threadIdx.x >> 5) * kHistQueue;
   for (int i = threadIdx.x; i < C::kRows*T; i += T) cnt[i] = 0;
-  for (int i = threadIdx.x; i < C::kBins; i += T) wide[i] = 0;
+  for (int i = threadIdx.x; i < C::kStreams*C::kBins; i += T) wide[i] = 0;
   __syncthreads();
 
   const int lane = threadIdx.x & 31;
   uint8_t *mine = dx_hist_smem + 4*threadIdx.x;
-  const int lineidx[4] = { 0, 2, 3, 4 };
-  const int64_t nb = (a.ent.n + kFetch - 1) / kFetch;
-  const int64_t total = nb * a.ns;
+  const int64_t nlines = a.ent.n;
+  const int64_t total = nlines * a.ns;
   int cur = 0;
+  uint32_t pad = 0;                                      // bytes counted in bin 0 that are not text
+  unsigned long long next = 0;
+  if (lane == 0) next = atomicAdd(a.ticket,1ull);
 
   while (true)
-    { unsigned long long u = 0;
-      if (lane == 0) u = atomicAdd(a.ticket,1ull);
-      u = __shfl_sync(DX_FULL,u,0);
-      const int si = ((int64_t) u >= total) ? a.ns : (int) ((int64_t) u / nb);
-      while (cur < si)                                   // every warp passes every stream boundary
-        { hist_flush<RUN>(a,a.sidx[cur],cnt,wide);
-          cur++;
+    { const int64_t u = (int64_t) __shfl_sync(DX_FULL,next,0);
+      const int si = (u >= total) ? a.ns : (int) (u / nlines);
+      if (si != cur)
+        { hist_warp_flush<RUN>(cnt,wide + (size_t) cur*C::kBins,pad);
+          pad = 0; cur = si;
         }
       if (si >= a.ns) break;
+      if (lane == 0) next = atomicAdd(a.ticket,1ull);
+      unsigned long long *wd = wide + (size_t) si*C::kBins;
       const int s = a.sidx[si];
-      const int64_t e0 = ((int64_t) u - (int64_t) si*nb) * kFetch;
-      const int64_t e1 = min(a.ent.n,e0 + kFetch);
-      for (int64_t e = e0; e < e1; e++)
-        { const int32_t rlen = a.ent.rlen[e];
-          if (rlen == 0) continue;
-          const uint8_t *line = a.text + a.ent.line0[e] + (int64_t) lineidx[s]*((int64_t) rlen + 1);
-          const int skew = (int) (reinterpret_cast<uintptr_t>(line) & 15);
-          const uint8_t *base = line - skew;                       // 16-byte aligned
-          const int32_t nchunk = (skew + rlen + 15) >> 4;
-          const uint32_t rc = RUN ? (uint32_t) a.rc[si] : 0u;
-          const bool runs = RUN && (e >= a.efirst[si]);
-          int32_t prev = -1;                                       // last non-run position so far
+      const int64_t e = u - (int64_t) si*nlines;
+      const int32_t rlen = a.ent.rlen[e];
+      if (rlen == 0) continue;
+      const int lineidx = (s == 0) ? 0 : s + 1;                   // del | tag | ins | mrg | sub
+      const uint8_t *line = a.text + a.ent.line0[e] + (int64_t) lineidx*((int64_t) rlen + 1);
+      const int skew = (int) (reinterpret_cast<uintptr_t>(line) & 15);
+      const uint8_t *base = line - skew;                           // 16-byte aligned
+      const int32_t nchunk = (skew + rlen + 15) >> 4;
+      uint4 nxt = (lane < nchunk) ? dx_ldg16(base + (int64_t) lane*16) : make_uint4(0,0,0,0);
 
-          for (int32_t c0 = 0; c0 < nchunk; c0 += 128)
-            { uint4 v[4];
+      if (!RUN)
+        { pad += (uint32_t) (nchunk*16 - rlen);
+#pragma unroll 1
+          for (int32_t c0 = 0; c0 < nchunk; c0 += 32)
+            { const int32_t c = c0 + lane;
+              uint4 v = nxt;
+              nxt = (c + 32 < nchunk) ? dx_ldg16(base + (int64_t) (c + 32)*16) : make_uint4(0,0,0,0);
+              if (c >= nchunk) continue;
+              const int32_t p0 = c*16 - skew;                      // line position of byte 0
+              if (p0 < 0 || p0 + 16 > rlen)                        // first / last chunk: zero the rest
+                { const uint32_t valid = dx_range16(max(0,-p0),min(16,rlen - p0));
+                  uint32_t k[4];
 #pragma unroll
-              for (int j = 0; j < 4; j++)
-                { const int32_t c = c0 + j*32 + lane;
-                  v[j] = (c < nchunk) ? dx_ldg16(base + (int64_t) c*16) : make_uint4(0,0,0,0);
-                }
-#pragma unroll
-              for (int j = 0; j < 4; j++)
-                { const int32_t c = c0 + j*32 + lane;
-                  if (c0 + j*32 >= nchunk) break;                    // warp-uniform
-                  const int32_t p0 = c*16 - skew;                   // line position of byte 0
-                  uint32_t valid = 0;
-                  if (c < nchunk)
-                    valid = dx_range16(max(0,-p0),min(16,rlen - p0));
-                  if (!RUN)
-                    { const uint32_t w[4] = { v[j].x, v[j].y, v[j].z, v[j].w };
-                      if (valid == 0xffffu)
-                        {
-#pragma unroll
-                          for (int i = 0; i < 16; i++)
-                            bump<T>(mine,wide,(w[i >> 2] >> ((i & 3)*8)) & 0xffu);
-                        }
-                      else
-                        { uint32_t m = valid;
-                          while (m)
-                            { const int i = __ffs(m) - 1; m &= m - 1;
-                              bump<T>(mine,wide,dx_byte_of(v[j],i));
-                            }
-                        }
+                  for (int q = 0; q < 4; q++)
+                    { const uint32_t n4 = (valid >> (4*q)) & 15u;
+                      k[q] = ((n4 & 1u) ? 0xffu : 0u) | ((n4 & 2u) ? 0xff00u : 0u) |
+                             ((n4 & 4u) ? 0xff0000u : 0u) | ((n4 & 8u) ? 0xff000000u : 0u);
                     }
-                  else
-                    { uint32_t m = valid & ~dx_eq_mask16(v[j],rc);         // bytes that are not the run character
-                      int32_t pv = -1;
-                      if (runs)
-                        { const int32_t mylast = m ? p0 + (31 - __clz(m)) : -1;
-                          const int32_t inc = dx_warp_incl_max(mylast,lane);
-                          int32_t before = __shfl_up_sync(DX_FULL,inc,1);
-                          if (lane == 0) before = -1;
-                          pv = max(prev,before);
-                          prev = max(prev,__shfl_sync(DX_FULL,inc,31));
-                        }
-                      while (m)
-                        { const int i = __ffs(m) - 1; m &= m - 1;
-                          bump<T>(mine,wide,dx_byte_of(v[j],i));
-                          if (runs)
-                            { const int32_t p = p0 + i;
-                              bump<T>(mine,wide,256u + (uint32_t) min(p - pv - 1,255));
-                              pv = p;
-                            }
-                        }
-                    }
+                  v.x &= k[0]; v.y &= k[1]; v.z &= k[2]; v.w &= k[3];
                 }
+              const uint32_t w[4] = { v.x, v.y, v.z, v.w };
+#pragma unroll
+              for (int i = 0; i < 16; i++)
+                bump<T>(mine,wd,(w[i >> 2] >> ((i & 3)*8)) & 0xffu);
             }
-          if (runs && lane == 0 && prev < rlen-1)                  // trailing run (QV.c:713-720)
-            bump<T>(mine,wide,256u + (uint32_t) min(rlen-1-prev,255));
+        }
+      else
+        { const uint32_t rc = (uint32_t) a.rc[si];
+          const bool runs = (e >= a.efirst[si]);
+          int32_t prevpos = -1;                                    // last position that is not rc
+          uint32_t qn = 0;                                         // queued items (warp-uniform)
+#pragma unroll 1
+          for (int32_t c0 = 0; c0 < nchunk + 32; c0 += 32)        // one extra round drains the queue
+            { const bool last = (c0 >= nchunk);
+              if (!last)
+                { const int32_t c = c0 + lane;
+                  const uint4 v = nxt;
+                  nxt = (c + 32 < nchunk) ? dx_ldg16(base + (int64_t) (c + 32)*16) : make_uint4(0,0,0,0);
+                  const int32_t p0 = c*16 - skew;
+                  uint32_t m = 0;
+                  if (c < nchunk)
+                    m = dx_range16(max(0,-p0),min(16,rlen - p0)) & ~dx_eq_mask16(v,rc);
+                  const uint32_t k = __popc(m);
+                  const uint32_t inc = dx_warp_incl_sum(k,lane);
+                  uint32_t at = qn + inc - k;
+                  while (m)
+                    { const int i = __ffs(m) - 1; m &= m - 1;
+                      queue[at++] = ((uint32_t) (p0 + i) << 8) | dx_byte_of(v,i);
+                    }
+                  qn += __shfl_sync(DX_FULL,inc,31);
+                  __syncwarp();
+                }
+              uint32_t done = 0;
+#pragma unroll 1
+              while (qn - done >= 32u || (last && done < qn))
+                { const uint32_t n = min(32u,qn - done);
+                  int32_t p = 0;
+                  if ((uint32_t) lane < n)
+                    { const uint32_t it = queue[done + lane];
+                      p = (int32_t) (it >> 8);
+                      bump<T>(mine,wd,it & 0xffu);
+                      if (runs)
+                        { const int32_t pp = (lane == 0) ? prevpos : (int32_t) (queue[done + lane - 1] >> 8);
+                          bump<T>(mine,wd,256u + (uint32_t) min(p - pp - 1,255));
+                        }
+                    }
+                  prevpos = __shfl_sync(DX_FULL,p,n-1);
+                  done += n;
+                }
+              // keep what is left (< 32 items) at the front of the queue
+              __syncwarp();
+              const uint32_t left = qn - done;
+              uint32_t keep = 0;
+              if ((uint32_t) lane < left) keep = queue[done + lane];
+              __syncwarp();
+              if ((uint32_t) lane < left) queue[lane] = keep;
+              qn = left;
+              __syncwarp();
+            }
+          if (runs && lane == 0 && prevpos < rlen-1)              // trailing run (QV.c:713-720)
+            bump<T>(mine,wd,256u + (uint32_t) min(rlen-1-prevpos,255));
+        }
+    }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C::kStreams*C::kBins; i += T)
+    { const unsigned long long v = wide[i];
+      const int si = i / C::kBins, b = i % C::kBins;
+      if (v && si < a.ns)
+        { const int s = a.sidx[si];
+          const int tab = (b < 256) ? s : (s == 0 ? 4 : 5);
+          atomicAdd(&a.ghist[tab*256 + (b & 255)],v);
         }
     }
 }
