@@ -67,6 +67,37 @@ void dx_arena_reset(dx_ctx *ctx)
     }
   for (int i = 0; i < ctx->nblk; i++)
     ctx->blk[i].top = 0;
+  ctx->hpin_top = 0;
+}
+
+// Pinned host scratch.  Pointers stay valid until the next dx_arena_reset: when the block is too
+// small a bigger one REPLACES it only if nothing has been handed out yet, else a one-off
+// allocation is chained behind it (freed at the next reset).
+struct DxPinExtra { void *p; DxPinExtra *next; };
+
+void *dx_hpin_get(dx_ctx *ctx, size_t bytes)
+{ bytes = round_up(bytes > 0 ? bytes : 1,64);
+  if (ctx->hpin_top == 0)
+    { while (ctx->hpin_extra)
+        { DxPinExtra *e = (DxPinExtra *) ctx->hpin_extra; ctx->hpin_extra = e->next; cudaFreeHost(e->p); free(e); }
+      if (ctx->hpin_cap < bytes || ctx->hpin_cap < ctx->hpin_want)
+        { if (ctx->hpin) cudaFreeHost(ctx->hpin);
+          ctx->hpin = NULL; ctx->hpin_cap = 0;
+          size_t want = round_up((bytes > ctx->hpin_want ? bytes : ctx->hpin_want)*2,(size_t) 1 << 20);
+          if (cudaMallocHost((void **) &ctx->hpin,want) != cudaSuccess)
+            { cudaGetLastError(); dx_fail(ctx,DX_E_NOMEM,"pinned host allocation of %zu bytes failed",want); return NULL; }
+          ctx->hpin_cap = want;
+        }
+    }
+  if (ctx->hpin_top + bytes <= ctx->hpin_cap)
+    { void *p = ctx->hpin + ctx->hpin_top; ctx->hpin_top += bytes; return p; }
+  DxPinExtra *e = (DxPinExtra *) malloc(sizeof(DxPinExtra));
+  if (e == NULL || cudaMallocHost(&e->p,bytes) != cudaSuccess)
+    { cudaGetLastError(); free(e); dx_fail(ctx,DX_E_NOMEM,"pinned host allocation of %zu bytes failed",bytes); return NULL; }
+  e->next = (DxPinExtra *) ctx->hpin_extra; ctx->hpin_extra = e;
+  ctx->hpin_top += bytes;                               // past the block: every later request is a one-off too
+  if (ctx->hpin_top > ctx->hpin_want) ctx->hpin_want = ctx->hpin_top;
+  return e->p;
 }
 
 void *dx_arena_get(dx_ctx *ctx, size_t bytes)
@@ -187,6 +218,9 @@ extern "C" void dx_close(dx_ctx *ctx)
   if (ctx->io_in)    cudaFree(ctx->io_in);
   if (ctx->io_out)   cudaFree(ctx->io_out);
   if (ctx->qv_store) cudaFree(ctx->qv_store);
+  if (ctx->hpin)     cudaFreeHost(ctx->hpin);
+  while (ctx->hpin_extra)
+    { DxPinExtra *e = (DxPinExtra *) ctx->hpin_extra; ctx->hpin_extra = e->next; cudaFreeHost(e->p); free(e); }
   if (ctx->prof)
     { char tmp[16]; ctx->prof_on = 0; dx_profile_report(ctx,tmp,sizeof(tmp));
       delete (DxProf *) ctx->prof;
@@ -1299,7 +1333,7 @@ static int plan_undexqv(dx_ctx *ctx, const uint8_t *d_in, size_t n, const int64_
           if ((rc = upload(ctx,d_order,order.data(),N)) != DX_OK) return rc;
           const dx_qv_coding &cd = plan.coding;
           if ((rc = dxk_qv_decode5x(ctx,d_in,n,plan.d_tab4,cd.delchar,cd.subchar,upper,2,nc,d_fs,d_rlen,
-                                    d_cent,NULL,0,plan.d_tmp,d_soffc,d_stat,d_limit,d_order)) != DX_OK) return rc;
+                                    d_cent,NULL,0,plan.d_tmp,d_soffc,d_stat,d_limit,d_order,NULL)) != DX_OK) return rc;
           plan.spec = true;
         }
       else if ((rc = qv_walk(ctx,d_in,n,plan,d_fs,d_rlen,nc,d_soffc,d_stat)) != DX_OK) return rc;
@@ -1377,6 +1411,214 @@ static int plan_undexqv(dx_ctx *ctx, const uint8_t *d_in, size_t n, const int64_
   return DX_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+//  The usual case of dx_undexqv_dev with everything but the verification of the entry chain on the
+//  device (dx_qv_plan.cu): well numbers and text offsets are prefix sums, the host sees a few
+//  bytes per entry through pinned memory.  Returns *handled = false (nothing written) when the
+//  file needs the general path below: decode tables that do not fit the one-warp-per-entry
+//  kernel, or an entry the candidate filter missed.
+// ------------------------------------------------------------------------------------------------
+static int undexqv_fast(dx_ctx *ctx, const uint8_t *d_in, size_t n, int upper, uint8_t *d_out, size_t cap,
+                        size_t *out_len, const int64_t *h_entry_off, int64_t nentries, int32_t well_in,
+                        bool *handled)
+{ int rc;
+  *handled = false;
+  DxPhases ph;
+  { const char *force = getenv("DEXB200_DECODER");
+    if (force != NULL || getenv("DEXB200_NO_SPEC") != NULL || getenv("DEXB200_NO_FAST") != NULL) return DX_OK;
+  }
+  std::vector<uint8_t> head;
+  if ((rc = peek(ctx,d_in,n,0,2 + 16384 + 100000,head)) != DX_OK) return rc;
+  if (head.size() < 2) return DX_OK;
+  uint16_t key; memcpy(&key,head.data(),2);
+  if (!(key == 0x55aa || key == 0xaa55)) return DX_OK;
+  dx_qv_coding coding;
+  std::vector<char> prefix(100001);
+  size_t used = 0;
+  if (dx_qv_read_coding(head.data()+2,head.size()-2,&coding,prefix.data(),(int) prefix.size(),&used) != DX_OK ||
+      coding.flip)
+    return DX_OK;
+  const size_t first = 2 + used;
+  const int plen = (int) strlen(prefix.data());
+  QvDecTables4 *h4 = (QvDecTables4 *) dx_hpin_get(ctx,sizeof(QvDecTables4));
+  if (h4 == NULL) return DX_E_NOMEM;
+  if (!build_dec_tables4(&coding,h4)) return DX_OK;
+  QvDecTables4 *d_tab4 = (QvDecTables4 *) dx_arena_get(ctx,sizeof(QvDecTables4));
+  char *d_prefix = (char *) dx_arena_get(ctx,(size_t) plen + 1);
+  int32_t *d_flag = (int32_t *) dx_arena_get(ctx,16);
+  if (!d_tab4 || !d_prefix || !d_flag) return DX_E_NOMEM;
+  DX_CUDA(ctx,cudaMemcpyAsync(d_tab4,h4,sizeof(QvDecTables4),cudaMemcpyHostToDevice,ctx->stream));
+  char *h_prefix = (char *) dx_hpin_get(ctx,(size_t) plen + 1);
+  if (h_prefix == NULL) return DX_E_NOMEM;
+  memcpy(h_prefix,prefix.data(),(size_t) plen + 1);
+  DX_CUDA(ctx,cudaMemcpyAsync(d_prefix,h_prefix,(size_t) plen + 1,cudaMemcpyHostToDevice,ctx->stream));
+  DX_CUDA(ctx,cudaMemsetAsync(d_flag,0,16,ctx->stream));
+  int32_t *d_stat1 = d_flag + 1;                        // decode status of the final launch
+  ph.mark("tables");
+
+  auto alloc_plan = [&](size_t N, QvPlanArrays &pa) -> bool
+    { pa.fs   = (int64_t *)  dx_arena_get(ctx,N*8);
+      pa.rlen = (int32_t *)  dx_arena_get(ctx,N*4);
+      pa.delta= (uint32_t *) dx_arena_get(ctx,N*4);
+      pa.beg  = (int32_t *)  dx_arena_get(ctx,N*4);
+      pa.end  = (int32_t *)  dx_arena_get(ctx,N*4);
+      pa.qv   = (int32_t *)  dx_arena_get(ctx,N*4);
+      return pa.fs && pa.rlen && pa.delta && pa.beg && pa.end && pa.qv;
+    };
+  struct Tail { int64_t total; int32_t flag; int32_t pad; };
+  Tail *h_tail = (Tail *) dx_hpin_get(ctx,sizeof(Tail));
+  if (h_tail == NULL) return DX_E_NOMEM;
+
+  if (h_entry_off != NULL)
+    { // ---- entry starts known -------------------------------------------------------------------
+      const size_t N = (size_t) nentries;
+      if (N == 0) { *out_len = 0; *handled = true; return DX_OK; }
+      QvPlanArrays pa;
+      int64_t *d_estart = (int64_t *) dx_arena_get(ctx,N*8);
+      int64_t *d_wpre   = (int64_t *) dx_arena_get(ctx,(N+1)*8);
+      int64_t *d_opre   = (int64_t *) dx_arena_get(ctx,(N+1)*8);
+      uint32_t *d_len   = (uint32_t *) dx_arena_get(ctx,N*4);
+      int32_t *d_well   = (int32_t *) dx_arena_get(ctx,N*4);
+      QvDecEntry *d_ent = (QvDecEntry *) dx_arena_get(ctx,N*sizeof(QvDecEntry));
+      if (!alloc_plan(N,pa) || !d_estart || !d_wpre || !d_opre || !d_len || !d_well || !d_ent) return DX_E_NOMEM;
+      DX_CUDA(ctx,cudaMemcpyAsync(d_estart,h_entry_off,N*8,cudaMemcpyHostToDevice,ctx->stream));
+      if ((rc = dxk_qv_known_prep(ctx,d_in,n,d_estart,(int64_t) N,pa,d_flag)) != DX_OK) return rc;
+      if ((rc = dxk_scan_u32(ctx,pa.delta,(int64_t) N,d_wpre)) != DX_OK) return rc;
+      if ((rc = dxk_qv_text_len(ctx,(int64_t) N,NULL,pa,d_wpre,NULL,well_in,plen,d_len,d_well,d_flag)) != DX_OK) return rc;
+      if ((rc = dxk_scan_u32(ctx,d_len,(int64_t) N,d_opre)) != DX_OK) return rc;
+      if ((rc = dxk_qv_build_ent(ctx,(int64_t) N,NULL,pa,d_well,d_opre,d_len,NULL,d_ent,NULL,NULL,NULL)) != DX_OK) return rc;
+      DX_CUDA(ctx,cudaMemcpyAsync(&h_tail->total,d_opre+N,8,cudaMemcpyDeviceToHost,ctx->stream));
+      DX_CUDA(ctx,cudaMemcpyAsync(&h_tail->flag,d_flag,4,cudaMemcpyDeviceToHost,ctx->stream));
+      DX_CUDA(ctx,cudaStreamSynchronize(ctx->stream));
+      ph.mark("plan");
+      if (h_tail->flag == 1) return dx_fail(ctx,DX_E_TRUNC,"compressed image ends inside an entry header");
+      if (h_tail->flag == 2) return dx_fail(ctx,DX_E_FORMAT,"unusable read length in an entry header");
+      if ((size_t) h_tail->total > cap)
+        return dx_fail(ctx,DX_E_CAP,"output needs %lld bytes, buffer has %zu",(long long) h_tail->total,cap);
+      if ((rc = dxk_qv_decode5(ctx,d_in,n,d_tab4,coding.delchar,coding.subchar,upper,1,(int64_t) N,pa.fs,pa.rlen,
+                               d_ent,d_prefix,plen,d_out,NULL,d_stat1)) != DX_OK) return rc;
+      DX_CUDA(ctx,cudaMemcpyAsync(&h_tail->flag,d_stat1,4,cudaMemcpyDeviceToHost,ctx->stream));
+      DX_CUDA(ctx,cudaStreamSynchronize(ctx->stream));
+      ph.mark("decode");
+      ph.report("undexqv (index known)");
+      if (h_tail->flag) return dx_fail(ctx,DX_E_TRUNC,"Could not read more bits (Decode)");
+      *out_len = (size_t) h_tail->total;
+      *handled = true;
+      return DX_OK;
+    }
+
+  // ---- entry starts unknown: candidates, speculative decode, verified chain --------------------------
+  int64_t *d_q = NULL, nc = 0;
+  if ((rc = dxk_index_positions(ctx,DX_PRED_QVCAND,d_in,n,first + 1,&d_q,&nc)) != DX_OK) return rc;
+  ph.mark("index");
+  const size_t N = (size_t) nc;
+  if (N == 0) return DX_OK;                             // empty or all entries missed: general path
+  int minbits = 0;
+  for (int k = 2; k <= 3; k++)
+    { int mn = 32;
+      for (int x = 0; x < 256; x++)
+        if (coding.tab[k].lens[x] > 0 && coding.tab[k].lens[x] < mn) mn = coding.tab[k].lens[x];
+      minbits += (mn == 32) ? 0 : mn;
+    }
+  QvPlanArrays pa;
+  uint32_t *d_tlen  = (uint32_t *) dx_arena_get(ctx,N*4);
+  int64_t  *d_limit = (int64_t *)  dx_arena_get(ctx,N*8);
+  int32_t  *d_ffrun = (int32_t *)  dx_arena_get(ctx,N*4);
+  uint8_t  *d_last  = (uint8_t *)  dx_arena_get(ctx,N);
+  int64_t  *d_toff  = (int64_t *)  dx_arena_get(ctx,(N+1)*8);
+  int64_t  *d_soff  = (int64_t *)  dx_arena_get(ctx,N*48);
+  int32_t  *d_stat  = (int32_t *)  dx_arena_get(ctx,N*4);
+  int32_t  *d_order = (int32_t *)  dx_arena_get(ctx,N*4);
+  if (!alloc_plan(N,pa) || !d_tlen || !d_limit || !d_ffrun || !d_last || !d_toff || !d_soff || !d_stat || !d_order)
+    return DX_E_NOMEM;
+  if ((rc = dxk_qv_cand_prep(ctx,d_in,n,first,d_q,nc,4,minbits,pa,d_tlen,d_limit,d_ffrun,d_last)) != DX_OK) return rc;
+  if ((rc = dxk_scan_u32(ctx,d_tlen,nc,d_toff)) != DX_OK) return rc;
+  int64_t *h_q     = (int64_t *) dx_hpin_get(ctx,N*8);
+  int32_t *h_ffrun = (int32_t *) dx_hpin_get(ctx,N*4);
+  uint8_t *h_last  = (uint8_t *) dx_hpin_get(ctx,N);
+  int32_t *h_rlen  = (int32_t *) dx_hpin_get(ctx,N*4);
+  int32_t *h_order = (int32_t *) dx_hpin_get(ctx,N*4);
+  int64_t *h_soff  = (int64_t *) dx_hpin_get(ctx,N*48);
+  int32_t *h_stat  = (int32_t *) dx_hpin_get(ctx,N*4);
+  int32_t *h_cand  = (int32_t *) dx_hpin_get(ctx,N*4);
+  int32_t *h_well  = (int32_t *) dx_hpin_get(ctx,N*4);
+  if (!h_q || !h_ffrun || !h_last || !h_rlen || !h_order || !h_soff || !h_stat || !h_cand || !h_well) return DX_E_NOMEM;
+  DX_CUDA(ctx,cudaMemcpyAsync(h_q,d_q,N*8,cudaMemcpyDeviceToHost,ctx->stream));
+  DX_CUDA(ctx,cudaMemcpyAsync(h_ffrun,d_ffrun,N*4,cudaMemcpyDeviceToHost,ctx->stream));
+  DX_CUDA(ctx,cudaMemcpyAsync(h_last,d_last,N,cudaMemcpyDeviceToHost,ctx->stream));
+  DX_CUDA(ctx,cudaMemcpyAsync(h_rlen,pa.rlen,N*4,cudaMemcpyDeviceToHost,ctx->stream));
+  DX_CUDA(ctx,cudaMemcpyAsync(&h_tail->total,d_toff+N,8,cudaMemcpyDeviceToHost,ctx->stream));
+  DX_CUDA(ctx,cudaStreamSynchronize(ctx->stream));
+  ph.mark("prep");
+  { size_t k = 0;                                        // long entries first, the rest in file order
+    std::vector<std::pair<int32_t,int32_t> > big;
+    for (size_t i = 0; i < N; i++) if (h_rlen[i] >= 32768) big.push_back(std::make_pair(-h_rlen[i],(int32_t) i));
+    std::sort(big.begin(),big.end());
+    for (size_t b = 0; b < big.size(); b++) h_order[k++] = big[b].second;
+    for (size_t i = 0; i < N; i++) if (h_rlen[i] < 32768) h_order[k++] = (int32_t) i;
+  }
+  DX_CUDA(ctx,cudaMemcpyAsync(d_order,h_order,N*4,cudaMemcpyHostToDevice,ctx->stream));
+  const size_t tmp_n = (size_t) h_tail->total;
+  uint8_t *d_tmp = (uint8_t *) dx_arena_get(ctx,tmp_n + 64);
+  if (d_tmp == NULL) return DX_E_NOMEM;
+  if ((rc = dxk_qv_decode5x(ctx,d_in,n,d_tab4,coding.delchar,coding.subchar,upper,2,nc,pa.fs,pa.rlen,NULL,NULL,0,
+                            d_tmp,d_soff,d_stat,d_limit,d_order,d_toff)) != DX_OK) return rc;
+  DX_CUDA(ctx,cudaMemcpyAsync(h_soff,d_soff,N*48,cudaMemcpyDeviceToHost,ctx->stream));
+  DX_CUDA(ctx,cudaMemcpyAsync(h_stat,d_stat,N*4,cudaMemcpyDeviceToHost,ctx->stream));
+  DX_CUDA(ctx,cudaStreamSynchronize(ctx->stream));
+  ph.mark("decode");
+
+  // the chain (see resolve_chain): a candidate is the next entry iff the bytes between the end of
+  // the previous entry and its fields are 0xff ... 0xff, d with d != 0xff
+  size_t M = 0;
+  { int64_t cur = (int64_t) first;
+    int32_t well = well_in;
+    size_t i = 0;
+    while (cur < (int64_t) n)
+      { while (i < N && h_q[i] - 1 < cur) i++;
+        while (i < N && h_last[i] == 0xff && h_q[i] - 1 - cur <= h_ffrun[i]) i++;
+        if (i >= N || h_stat[i] != 0) return DX_OK;                     // general path
+        const int64_t gap = h_q[i] - 1 - cur;
+        if (gap > h_ffrun[i] || h_last[i] == 0xff) return DX_OK;
+        const int64_t end = h_soff[6*i + 5];
+        if (end > (int64_t) n || end <= cur) return DX_OK;
+        well += 255 * (int32_t) gap + h_last[i];
+        h_cand[M] = (int32_t) i; h_well[M] = well; M++;
+        cur = end;
+        i++;
+      }
+  }
+  ph.mark("chain");
+  int32_t *d_cand = (int32_t *) dx_arena_get(ctx,M*4 + 4);
+  int32_t *d_wells = (int32_t *) dx_arena_get(ctx,M*4 + 4);
+  int32_t *d_well = (int32_t *) dx_arena_get(ctx,M*4 + 4);
+  uint32_t *d_len = (uint32_t *) dx_arena_get(ctx,M*4 + 4);
+  int64_t *d_opre = (int64_t *) dx_arena_get(ctx,(M+1)*8);
+  int64_t *d_src  = (int64_t *) dx_arena_get(ctx,M*8 + 8);
+  QvDecEntry *d_ent = (QvDecEntry *) dx_arena_get(ctx,(M+1)*sizeof(QvDecEntry));
+  if (!d_cand || !d_wells || !d_well || !d_len || !d_opre || !d_src || !d_ent) return DX_E_NOMEM;
+  if (M > 0)
+    { DX_CUDA(ctx,cudaMemcpyAsync(d_cand,h_cand,M*4,cudaMemcpyHostToDevice,ctx->stream));
+      DX_CUDA(ctx,cudaMemcpyAsync(d_wells,h_well,M*4,cudaMemcpyHostToDevice,ctx->stream));
+    }
+  if ((rc = dxk_qv_text_len(ctx,(int64_t) M,d_cand,pa,NULL,d_wells,0,plen,d_len,d_well,d_flag)) != DX_OK) return rc;
+  if ((rc = dxk_scan_u32(ctx,d_len,(int64_t) M,d_opre)) != DX_OK) return rc;
+  if ((rc = dxk_qv_build_ent(ctx,(int64_t) M,d_cand,pa,d_well,d_opre,d_len,d_toff,d_ent,d_src,NULL,NULL)) != DX_OK) return rc;
+  DX_CUDA(ctx,cudaMemcpyAsync(&h_tail->total,d_opre+M,8,cudaMemcpyDeviceToHost,ctx->stream));
+  DX_CUDA(ctx,cudaMemcpyAsync(&h_tail->flag,d_flag,4,cudaMemcpyDeviceToHost,ctx->stream));
+  DX_CUDA(ctx,cudaStreamSynchronize(ctx->stream));
+  if (h_tail->flag) return dx_fail(ctx,DX_E_FORMAT,"unusable read length in an entry header");
+  if ((size_t) h_tail->total > cap)
+    return dx_fail(ctx,DX_E_CAP,"output needs %lld bytes, buffer has %zu",(long long) h_tail->total,cap);
+  if ((rc = dxk_qv_assemble(ctx,d_tmp,tmp_n,d_ent,d_src,(int64_t) M,d_prefix,plen,d_out)) != DX_OK) return rc;
+  DX_CUDA(ctx,cudaStreamSynchronize(ctx->stream));
+  ph.mark("assemble");
+  ph.report("undexqv (entries discovered)");
+  *out_len = (size_t) h_tail->total;
+  *handled = true;
+  return DX_OK;
+}
+
 extern "C" int dx_undexqv_dev(dx_ctx *ctx, const uint8_t *d_in, size_t n, int upper,
                               uint8_t *d_out, size_t cap, size_t *out_len,
                               const int64_t *h_entry_off, int64_t nentries, int32_t well_in)
@@ -1386,6 +1628,12 @@ extern "C" int dx_undexqv_dev(dx_ctx *ctx, const uint8_t *d_in, size_t n, int up
   if ((rc = check_buf(ctx,d_in,"image")) != DX_OK) return rc;
   cudaSetDevice(ctx->device);
   dx_arena_reset(ctx);
+  { bool handled = false;
+    if (d_out != NULL && (rc = undexqv_fast(ctx,d_in,n,upper,d_out,cap,out_len,h_entry_off,nentries,well_in,
+                                            &handled)) != DX_OK) return rc;
+    if (handled) return DX_OK;
+    dx_arena_reset(ctx);
+  }
   QvPlan plan;
   if ((rc = plan_undexqv(ctx,d_in,n,h_entry_off,nentries,well_in,true,upper,plan)) != DX_OK) return rc;
   if (plan.text_len > cap)

@@ -6,8 +6,10 @@
 //   DX_PRED_FASTA_HDR  every '>' that starts a line
 //   DX_PRED_QVCAND     every offset whose next 12 bytes look like the beg/end/qv fields of a
 //                      .dexqv entry header (dexqv.c:137-139) -- candidates only, verified later
-// Three launches: per-tile counts, an exclusive scan of the counts, an ordered write.
+// One launch (decoupled look-back over 16 KB tiles); the exact three-launch form -- per-tile counts,
+// an exclusive scan of the counts, an ordered write -- remains as the fallback for dense inputs.
 
+#include <stdlib.h>
 #include "dx_internal.h"
 #include "dx_common.cuh"
 
@@ -32,7 +34,14 @@ __device__ __forceinline__ uint32_t chunk_hits(const uint8_t *buf, size_t n, siz
 { uint4 v = dx_ldg16(buf + at);                    // the buffer is padded to a 16-byte multiple
   uint32_t hits;
   if (PRED == DX_PRED_NEWLINE)
-    hits = dx_eq_mask16(v,'\n');
+    { // newlines are rare: one exact "is any byte a newline" test for the whole chunk first
+      const uint32_t k = 0x0a0a0a0au;
+      const uint32_t a = v.x ^ k, b = v.y ^ k, c = v.z ^ k, d = v.w ^ k;
+      const uint32_t z = ((a - 0x01010101u) & ~a) | ((b - 0x01010101u) & ~b) |
+                         ((c - 0x01010101u) & ~c) | ((d - 0x01010101u) & ~d);
+      if ((z & 0x80808080u) == 0) return 0;
+      hits = dx_eq_mask16(v,'\n');
+    }
   else if (PRED == DX_PRED_FASTA_HDR)
     { uint32_t gt = dx_eq_mask16(v,'>');
       if (gt == 0) return 0;
@@ -230,9 +239,109 @@ __global__ void k_qv_entries(const uint8_t *text, const int64_t *nl, int64_t nen
   ent.flag[e] = ok ? 0 : 1;
 }
 
+// ---- single pass: count, scan and write in one launch ------------------------------------------
+// Tiles are taken in ticket order; a tile publishes its count in a 64-bit status word (state in the
+// top two bits: 1 = tile aggregate, 2 = inclusive prefix) and finds its own prefix by looking back
+// over its predecessors' words, 32 at a time (decoupled look-back).  The text is read once.
+// Positions beyond `cap` are counted but not written; the host then repeats with the exact
+// two-pass kernels above.
+constexpr int kSThreads = 256;
+constexpr int kSChunks  = 32;                                     // 16-byte chunks per thread
+constexpr int kSBytes   = kSThreads * kSChunks * 16;              // 128 KB: a look-back hop skips 4 MB
+
 template <int PRED>
-int index_positions(dx_ctx *ctx, const uint8_t *buf, size_t n, size_t first,
-                    int64_t **d_pos, int64_t *count)
+__global__ void __launch_bounds__(kSThreads,4)
+k_pred_single(const uint8_t *buf, size_t n, size_t first, int64_t ntiles,
+              unsigned long long *status, unsigned long long *ticket, int64_t *pos, int64_t cap,
+              int64_t *count_out)
+{ __shared__ uint32_t wsum[kSChunks][kSThreads/32];      // per chunk row and warp: hits, then hits before
+  __shared__ uint32_t rowpre[kSChunks];                  // hits of the tile before chunk row j
+  __shared__ unsigned long long s_prefix;
+  __shared__ unsigned int s_tile;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) s_tile = (unsigned int) atomicAdd(ticket,1ull);
+  __syncthreads();
+  const int64_t tile = (int64_t) s_tile;
+  const size_t base = (size_t) tile * kSBytes;
+
+  uint32_t hits[kSChunks];
+#pragma unroll
+  for (int j = 0; j < kSChunks; j++)
+    { const size_t at = base + ((size_t) j * kSThreads + threadIdx.x) * 16;
+      hits[j] = (at < n) ? chunk_hits<PRED>(buf,n,first,at) : 0;
+    }
+#pragma unroll
+  for (int j = 0; j < kSChunks; j++)
+    { const uint32_t c = dx_warp_sum(__popc(hits[j]));
+      if (lane == 0) wsum[j][warp] = c;
+    }
+  __syncthreads();
+  { // thread (j, w): hits of row j in the warps before w; the last warp's thread also has the row total
+    const int j = threadIdx.x >> 3, w = threadIdx.x & 7;
+    uint32_t before = 0;
+    for (int k = 0; k < w; k++) before += wsum[j][k];
+    const uint32_t mine = wsum[j][w];
+    __syncthreads();
+    wsum[j][w] = before;
+    if (w == 7) rowpre[j] = before + mine;
+  }
+  __syncthreads();
+  if (warp == 0)
+    { const uint32_t v = rowpre[lane];
+      const uint32_t iv = dx_warp_incl_sum(v,lane);
+      const uint32_t total = __shfl_sync(DX_FULL,iv,31);
+      rowpre[lane] = iv - v;
+      unsigned long long prefix = 0;
+      volatile unsigned long long *st = status;
+      if (tile > 0)
+        { if (lane == 0) st[tile] = (1ull << 62) | total;
+          int64_t j = tile - 1;
+          while (true)
+            { const int64_t idx = j - lane;
+              unsigned long long x = (2ull << 62);                    // before the first tile: inclusive 0
+              if (idx >= 0)
+                { x = st[idx];
+                  while ((x >> 62) == 0) x = st[idx];
+                }
+              const uint32_t incl = __ballot_sync(DX_FULL,(x >> 62) == 2);
+              const int stop = incl ? __ffs(incl) - 1 : 31;           // nearest predecessor with a full prefix
+              unsigned long long part = (lane <= stop) ? (x & ((1ull << 62) - 1)) : 0ull;
+#pragma unroll
+              for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(DX_FULL,part,d);
+              prefix += part;
+              if (incl) break;
+              j -= 32;
+            }
+        }
+      if (lane == 0)
+        { __threadfence();
+          st[tile] = (2ull << 62) | (prefix + total);
+          s_prefix = prefix;
+          if (tile == ntiles - 1) *count_out = (int64_t) (prefix + total);
+        }
+    }
+  __syncthreads();
+  const int64_t mybase = (int64_t) s_prefix;
+#pragma unroll
+  for (int j = 0; j < kSChunks; j++)
+    { uint32_t h = hits[j];
+      if (!__any_sync(DX_FULL,h != 0)) continue;
+      const uint32_t c = __popc(h);
+      const uint32_t inc = dx_warp_incl_sum(c,lane);
+      const size_t at = base + ((size_t) j * kSThreads + threadIdx.x) * 16;
+      int64_t r = mybase + rowpre[j] + wsum[j][warp] + inc - c;
+      while (h)
+        { const int i = __ffs(h) - 1;
+          h &= h - 1;
+          if (r < cap) pos[r] = (int64_t) (at + i);
+          r++;
+        }
+    }
+}
+
+template <int PRED>
+int index_positions_exact(dx_ctx *ctx, const uint8_t *buf, size_t n, size_t first,
+                          int64_t **d_pos, int64_t *count)
 { const int64_t ntiles = (int64_t) ((n + kTileBytes - 1) / kTileBytes);
   *d_pos = NULL; *count = 0;
   if (ntiles == 0) return DX_OK;
@@ -253,6 +362,35 @@ int index_positions(dx_ctx *ctx, const uint8_t *buf, size_t n, size_t first,
   DX_PROF_BEGIN(ctx); k_pred_write<PRED><<<(unsigned) ntiles,kTileThreads,0,ctx->stream>>>(buf,n,first,d_pre,pos);
   DX_LAUNCHED(ctx,"k_pred_write");
   *d_pos = pos;
+  return DX_OK;
+}
+
+template <int PRED>
+int index_positions(dx_ctx *ctx, const uint8_t *buf, size_t n, size_t first,
+                    int64_t **d_pos, int64_t *count)
+{ const int64_t ntiles = (int64_t) ((n + kSBytes - 1) / kSBytes);
+  *d_pos = NULL; *count = 0;
+  if (ntiles == 0) return DX_OK;
+  // expected density: 6 newlines per .quiva entry, one header per fasta entry, one candidate per
+  // .dexqv entry; anything denser falls back to the exact two-pass index
+  const int64_t cap = (int64_t) (n / (PRED == DX_PRED_NEWLINE ? 64 : 256)) + 4096;
+  unsigned long long *d_status = (unsigned long long *) dx_arena_get(ctx,(size_t) (ntiles + 2)*8);
+  int64_t *pos = (int64_t *) dx_arena_get(ctx,(size_t) cap*8);
+  if (d_status == NULL || pos == NULL) return DX_E_NOMEM;
+  DX_CUDA(ctx,cudaMemsetAsync(d_status,0,(size_t) (ntiles + 2)*8,ctx->stream));
+  unsigned long long *d_ticket = d_status + ntiles;
+  int64_t *d_count = (int64_t *) (d_status + ntiles + 1);
+  DX_PROF_BEGIN(ctx);
+  k_pred_single<PRED><<<(unsigned) ntiles,kSThreads,0,ctx->stream>>>(buf,n,first,ntiles,d_status,d_ticket,
+                                                                       pos,cap,d_count);
+  DX_LAUNCHED(ctx,"k_pred_single");
+  int64_t total = 0;
+  DX_CUDA(ctx,cudaMemcpyAsync(&total,d_count,8,cudaMemcpyDeviceToHost,ctx->stream));
+  DX_CUDA(ctx,cudaStreamSynchronize(ctx->stream));
+  if (total > cap || getenv("DEXB200_EXACT_INDEX") != NULL)
+    return index_positions_exact<PRED>(ctx,buf,n,first,d_pos,count);
+  *count = total;
+  *d_pos = (total > 0) ? pos : NULL;
   return DX_OK;
 }
 
@@ -297,6 +435,12 @@ __global__ void k_field_rlen(const uint8_t *buf, const int64_t *q, int64_t count
 }
 
 }  // namespace
+
+int dxk_scan_u32(dx_ctx *ctx, const uint32_t *d_in, int64_t n, int64_t *d_prefix)
+{ DX_PROF_BEGIN(ctx); k_tile_scan<<<1,1024,0,ctx->stream>>>(d_in,n,d_prefix);
+  DX_LAUNCHED(ctx,"k_scan_u32");
+  return DX_OK;
+}
 
 int dxk_cand_context(dx_ctx *ctx, const uint8_t *d_in, size_t n, size_t first, const int64_t *d_q,
                      int64_t count, int fieldbytes, CandInfo *d_info)

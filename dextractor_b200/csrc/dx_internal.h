@@ -89,6 +89,10 @@ struct dx_ctx
   int          prof_on;
   void        *prof;           // std::vector<DxProfRec>*
 
+  // pinned host scratch for the small per-call transfers (bump allocated, reset per call)
+  uint8_t     *hpin;    size_t hpin_cap, hpin_top, hpin_want;
+  void        *hpin_extra;     // one-off blocks handed out when hpin was too small
+
   // framing of the last scanned .quiva buffer (reused by the encode pass)
   const uint8_t *qv_text;
   size_t         qv_n;
@@ -102,6 +106,7 @@ int   dx_cuda_fail(dx_ctx *ctx, cudaError_t e, const char *what);
 void  dx_arena_reset(dx_ctx *ctx);
 void *dx_arena_get(dx_ctx *ctx, size_t bytes);        // 256-byte aligned; NULL + error on failure
 int   dx_arena_reserve(dx_ctx *ctx, size_t bytes);    // make sure this much is available
+void *dx_hpin_get(dx_ctx *ctx, size_t bytes);         // pinned host scratch; NULL + error on failure
 
 #define DX_CUDA(ctx, call) do { cudaError_t e__ = (call); \
     if (e__ != cudaSuccess) return dx_cuda_fail(ctx, e__, #call); } while (0)
@@ -186,12 +191,33 @@ int dxk_qv_decode5x(dx_ctx *ctx, const uint8_t *d_in, size_t n, const QvDecTable
                     int delchar, int subchar, int upper, int write, int64_t count,
                     const int64_t *d_start, const int32_t *d_rlen, const QvDecEntry *d_ent,
                     const char *d_prefix, int plen, uint8_t *d_out, int64_t *d_soff, int32_t *d_status,
-                    const int64_t *d_limit, const int32_t *d_order);
+                    const int64_t *d_limit, const int32_t *d_order, const int64_t *d_toff);
 
 // move speculatively decoded lines (scratch image d_tmp, entry e at d_src[e], < 0 = skip) to their
 // final place and write the header lines
 int dxk_qv_assemble(dx_ctx *ctx, const uint8_t *d_tmp, size_t tmp_n, const QvDecEntry *d_ent,
                     const int64_t *d_src, int64_t count, const char *d_prefix, int plen, uint8_t *d_out);
+
+// dx_qv_plan.cu : per-entry planning of a .dexqv decode on the device
+struct QvPlanArrays              // one row per entry (or candidate), all in HBM
+{ int64_t  *fs;                  // first stream byte (after beg/end/qv)
+  int32_t  *rlen;                // end - beg; -1 = candidate ruled out
+  uint32_t *delta;               // well delta (known-offset path)
+  int32_t  *beg, *end, *qv;
+};
+int dxk_qv_known_prep(dx_ctx *ctx, const uint8_t *d_in, size_t n, const int64_t *d_estart, int64_t count,
+                      QvPlanArrays pa, int32_t *d_flag);
+int dxk_qv_cand_prep(dx_ctx *ctx, const uint8_t *d_in, size_t n, size_t first, const int64_t *d_q, int64_t count,
+                     int span, int minbits, QvPlanArrays pa, uint32_t *d_tlen, int64_t *d_limit,
+                     int32_t *d_ffrun, uint8_t *d_last);
+int dxk_qv_text_len(dx_ctx *ctx, int64_t count, const int32_t *d_cand, QvPlanArrays pa, const int64_t *d_wpre,
+                    const int32_t *d_wells, int32_t well_in, int plen, uint32_t *d_len, int32_t *d_well_out,
+                    int32_t *d_flag);
+int dxk_qv_build_ent(dx_ctx *ctx, int64_t count, const int32_t *d_cand, QvPlanArrays pa, const int32_t *d_well,
+                     const int64_t *d_opre, const uint32_t *d_len, const int64_t *d_toff, QvDecEntry *d_ent,
+                     int64_t *d_src, int64_t *d_fs_out, int32_t *d_rlen_out);
+// exclusive scan of n 32-bit values into n+1 64-bit prefixes (one CTA)
+int dxk_scan_u32(dx_ctx *ctx, const uint32_t *d_in, int64_t n, int64_t *d_prefix);
 
 // dx_pack.cu : .fasta/.arrow <-> 2-bit images
 struct FaEntries                // one fasta/arrow entry (structure of arrays in HBM)

@@ -56,6 +56,7 @@ struct Dec5Args
   const int64_t *start;        // first stream byte of each entry (after beg/end/qv)
   const int32_t *rlen;
   const QvDecEntry *ent;       // write mode: output placement
+  const int64_t *toff;         // write == 2 without ent: where the entry's lines go
   const char    *prefix; int32_t plen;
   uint8_t       *out;
   int64_t       *soff;         // [count][6] or NULL
@@ -503,7 +504,9 @@ k_qv_decode5(Dec5Args a)
       int64_t at = a.start[e];
       int64_t o[6];
       uint8_t *line = NULL;
-      if (a.write)
+      if (a.write == 2 && a.ent == NULL)
+        line = a.out + a.toff[e];
+      else if (a.write)
         { const QvDecEntry en = a.ent[e];
           line = a.out + en.text_off;
           if (lane == 0 && a.write == 1)
@@ -634,21 +637,21 @@ int dxk_qv_decode5x(dx_ctx *ctx, const uint8_t *d_in, size_t n, const QvDecTable
                     int delchar, int subchar, int upper, int write, int64_t count,
                     const int64_t *d_start, const int32_t *d_rlen, const QvDecEntry *d_ent,
                     const char *d_prefix, int plen, uint8_t *d_out, int64_t *d_soff, int32_t *d_status,
-                    const int64_t *d_limit, const int32_t *d_order);
+                    const int64_t *d_limit, const int32_t *d_order, const int64_t *d_toff);
 
 int dxk_qv_decode5(dx_ctx *ctx, const uint8_t *d_in, size_t n, const QvDecTables4 *d_tab,
                    int delchar, int subchar, int upper, int write, int64_t count,
                    const int64_t *d_start, const int32_t *d_rlen, const QvDecEntry *d_ent,
                    const char *d_prefix, int plen, uint8_t *d_out, int64_t *d_soff, int32_t *d_status)
 { return dxk_qv_decode5x(ctx,d_in,n,d_tab,delchar,subchar,upper,write,count,d_start,d_rlen,d_ent,d_prefix,plen,
-                         d_out,d_soff,d_status,NULL,NULL);
+                         d_out,d_soff,d_status,NULL,NULL,NULL);
 }
 
 int dxk_qv_decode5x(dx_ctx *ctx, const uint8_t *d_in, size_t n, const QvDecTables4 *d_tab,
                     int delchar, int subchar, int upper, int write, int64_t count,
                     const int64_t *d_start, const int32_t *d_rlen, const QvDecEntry *d_ent,
                     const char *d_prefix, int plen, uint8_t *d_out, int64_t *d_soff, int32_t *d_status,
-                    const int64_t *d_limit, const int32_t *d_order)
+                    const int64_t *d_limit, const int32_t *d_order, const int64_t *d_toff)
 { if (count == 0) return DX_OK;
   unsigned long long *d_ticket = (unsigned long long *) dx_arena_get(ctx,8);
   if (d_ticket == NULL) return DX_E_NOMEM;
@@ -659,7 +662,7 @@ int dxk_qv_decode5x(dx_ctx *ctx, const uint8_t *d_in, size_t n, const QvDecTable
   a.count = count; a.start = d_start; a.rlen = d_rlen; a.ent = d_ent;
   a.prefix = d_prefix; a.plen = plen; a.out = d_out; a.soff = d_soff; a.status = d_status;
   a.ticket = d_ticket;
-  a.limit = d_limit; a.order = d_order;
+  a.limit = d_limit; a.order = d_order; a.toff = d_toff;
   a.dbg = NULL;
   if (getenv("DEXB200_DEBUG_DEC") != NULL)
     { a.dbg = (unsigned long long *) dx_arena_get(ctx,32*8);
