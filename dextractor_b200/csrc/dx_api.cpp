@@ -429,9 +429,23 @@ static int pk_walk_one(dx_ctx *ctx, void *user, int64_t q, int64_t *end, int64_t
   return DX_OK;
 }
 
+static int dexta_impl(dx_ctx *ctx, int kind, const uint8_t *d_text, size_t n,
+                      uint8_t *d_out, size_t cap, size_t *out_len, bool exact, bool *redo);
+
 extern "C" int dx_dexta_dev(dx_ctx *ctx, int kind, const uint8_t *d_text, size_t n,
                             uint8_t *d_out, size_t cap, size_t *out_len)
-{ if (ctx == NULL || out_len == NULL || (kind != DX_FASTA && kind != DX_ARROW)) return DX_E_ARG;
+{ // first the vectorised kernels, which take the symbol counts from the line lattice and verify them
+  // while packing; a file whose lines do not form the lattice is redone with the exact counts
+  bool redo = false;
+  int rc = dexta_impl(ctx,kind,d_text,n,d_out,cap,out_len,getenv("DEXB200_EXACT_PACK") != NULL,&redo);
+  if (rc == DX_OK && redo) rc = dexta_impl(ctx,kind,d_text,n,d_out,cap,out_len,true,&redo);
+  return rc;
+}
+
+static int dexta_impl(dx_ctx *ctx, int kind, const uint8_t *d_text, size_t n,
+                      uint8_t *d_out, size_t cap, size_t *out_len, bool exact, bool *redo)
+{ *redo = false;
+  if (ctx == NULL || out_len == NULL || (kind != DX_FASTA && kind != DX_ARROW)) return DX_E_ARG;
   *out_len = 0;
   ctx->err_line = 0;
   int rc;
@@ -481,12 +495,25 @@ extern "C" int dx_dexta_dev(dx_ctx *ctx, int kind, const uint8_t *d_text, size_t
   if (!ent.hdr || !ent.seq || !ent.region || !ent.off || !ent.rlen || !ent.width || !ent.well ||
       !ent.beg || !ent.end || !ent.aux || !ent.flag || !ent.bytes) return DX_E_NOMEM;
 
-  if ((rc = dxk_fa_measure(ctx,kind,d_text,n,d_hdr,ent)) != DX_OK) return rc;
+  int32_t *d_flags = (int32_t *) dx_arena_get(ctx,32);            // [0] any flag, [1] pack error, [2..3] ticket
+  if (d_flags == NULL) return DX_E_NOMEM;
+  DX_CUDA(ctx,cudaMemsetAsync(d_flags,0,32,ctx->stream));
+  int32_t anyflag = 1;
+  if (exact)
+    { if ((rc = dxk_fa_measure(ctx,kind,d_text,n,d_hdr,ent)) != DX_OK) return rc; }
+  else
+    { if ((rc = dxk_fa_measure2(ctx,kind,d_text,n,d_hdr,ent,d_flags)) != DX_OK) return rc;
+      DX_CUDA(ctx,cudaMemcpyAsync(&anyflag,d_flags,4,cudaMemcpyDeviceToHost,ctx->stream));
+      DX_CUDA(ctx,cudaStreamSynchronize(ctx->stream));
+    }
 
   // entries the device could not settle: non-canonical headers go through the host's sscanf
   std::vector<int32_t> flag;
-  if ((rc = download(ctx,ent.flag,N,flag)) != DX_OK) return rc;
-  for (size_t e = 0; e < N; e++)
+  if (anyflag)
+    { if ((rc = download(ctx,ent.flag,N,flag)) != DX_OK) return rc; }
+  else
+    flag.assign(N,0);
+  for (size_t e = 0; e < N && anyflag; e++)
     { if (flag[e] & 4)
         return dx_fail(ctx,DX_E_TOOLONG,"%s line is too long (> 99998 chars) or unterminated (entry %zu)",
                        kind == DX_FASTA ? "Fasta" : "Arrow",e+1);
@@ -536,8 +563,18 @@ extern "C" int dx_dexta_dev(dx_ctx *ctx, int kind, const uint8_t *d_text, size_t
   memcpy(fh.data()+2,&plen,4);
   memcpy(fh.data()+6,head.data(),(size_t) plen);
   if ((rc = upload(ctx,d_out,fh.data(),hbytes)) != DX_OK) return rc;
-  if ((rc = dxk_fa_pack(ctx,kind,d_text,n,ent,0,d_out + hbytes)) != DX_OK) return rc;
-  DX_CUDA(ctx,cudaStreamSynchronize(ctx->stream));
+  if (exact)
+    { if ((rc = dxk_fa_pack(ctx,kind,d_text,n,ent,0,d_out + hbytes)) != DX_OK) return rc;
+      DX_CUDA(ctx,cudaStreamSynchronize(ctx->stream));
+    }
+  else
+    { int32_t err = 0;
+      if ((rc = dxk_fa_pack2(ctx,kind,d_text,ent,0,d_out + hbytes,d_flags + 1,
+                             (unsigned long long *) (d_flags + 2))) != DX_OK) return rc;
+      DX_CUDA(ctx,cudaMemcpyAsync(&err,d_flags + 1,4,cudaMemcpyDeviceToHost,ctx->stream));
+      DX_CUDA(ctx,cudaStreamSynchronize(ctx->stream));
+      if (err) { *redo = true; return DX_OK; }
+    }
   *out_len = hbytes + (size_t) body;
   return DX_OK;
 }
@@ -674,6 +711,95 @@ static int plan_undexta(dx_ctx *ctx, int kind, const uint8_t *d_in, size_t n, in
   return DX_OK;
 }
 
+// The usual case of dx_undexta_dev (current key, native byte order, width >= 16) with everything but
+// the verification of the entry chain on the device.  *handled = false: take the general path.
+// d_out == NULL: only the size of the text is wanted.
+static int undexta_fast(dx_ctx *ctx, int kind, const uint8_t *d_in, size_t n, int width, int upper,
+                        uint8_t *d_out, size_t cap, size_t *out_len, bool *handled)
+{ int rc;
+  *handled = false;
+  if (width < 16 || getenv("DEXB200_NO_FAST") != NULL) return DX_OK;
+  std::vector<uint8_t> head;
+  if ((rc = peek(ctx,d_in,n,0,6,head)) != DX_OK) return rc;
+  if (head.size() < 6) return DX_OK;
+  uint16_t key; memcpy(&key,head.data(),2);
+  int32_t  plen; memcpy(&plen,head.data()+2,4);
+  if (key != 0x55aa || plen < 0 || (size_t) plen + 6 > n) return DX_OK;
+  const size_t first = 6 + (size_t) plen;
+  const int fieldbytes = (kind == DX_FASTA) ? 12 : 16;
+  char *d_prefix = (char *) dx_arena_get(ctx,(size_t) plen + 1);
+  if (d_prefix == NULL) return DX_E_NOMEM;
+  DX_CUDA(ctx,cudaMemcpyAsync(d_prefix,d_in + 6,(size_t) plen,cudaMemcpyDeviceToDevice,ctx->stream));
+
+  int64_t *d_q = NULL, nc = 0;
+  if ((rc = dxk_index_positions(ctx,kind == DX_FASTA ? DX_PRED_QVCAND : DX_PRED_ARCAND,
+                                d_in,n,first + 1,&d_q,&nc)) != DX_OK) return rc;
+  const size_t N = (size_t) nc;
+  if (N == 0) return DX_OK;
+  int64_t *d_end   = (int64_t *) dx_arena_get(ctx,N*8);
+  int32_t *d_ffrun = (int32_t *) dx_arena_get(ctx,N*4);
+  uint8_t *d_last  = (uint8_t *) dx_arena_get(ctx,N);
+  if (!d_end || !d_ffrun || !d_last) return DX_E_NOMEM;
+  if ((rc = dxk_pk_cand_prep(ctx,d_in,n,first,fieldbytes,d_q,nc,d_end,d_ffrun,d_last)) != DX_OK) return rc;
+  int64_t *h_q     = (int64_t *) dx_hpin_get(ctx,N*8);
+  int64_t *h_end   = (int64_t *) dx_hpin_get(ctx,N*8);
+  int32_t *h_ffrun = (int32_t *) dx_hpin_get(ctx,N*4);
+  uint8_t *h_last  = (uint8_t *) dx_hpin_get(ctx,N);
+  int32_t *h_cand  = (int32_t *) dx_hpin_get(ctx,N*4);
+  int32_t *h_well  = (int32_t *) dx_hpin_get(ctx,N*4);
+  int64_t *h_total = (int64_t *) dx_hpin_get(ctx,8);
+  if (!h_q || !h_end || !h_ffrun || !h_last || !h_cand || !h_well || !h_total) return DX_E_NOMEM;
+  DX_CUDA(ctx,cudaMemcpyAsync(h_q,d_q,N*8,cudaMemcpyDeviceToHost,ctx->stream));
+  DX_CUDA(ctx,cudaMemcpyAsync(h_end,d_end,N*8,cudaMemcpyDeviceToHost,ctx->stream));
+  DX_CUDA(ctx,cudaMemcpyAsync(h_ffrun,d_ffrun,N*4,cudaMemcpyDeviceToHost,ctx->stream));
+  DX_CUDA(ctx,cudaMemcpyAsync(h_last,d_last,N,cudaMemcpyDeviceToHost,ctx->stream));
+  DX_CUDA(ctx,cudaStreamSynchronize(ctx->stream));
+
+  size_t M = 0;                                          // the chain (see resolve_chain)
+  { int64_t cur = (int64_t) first;
+    int32_t well = 0;
+    size_t i = 0;
+    while (cur < (int64_t) n)
+      { while (i < N && h_q[i] - 1 < cur) i++;
+        while (i < N && h_last[i] == 0xff && h_q[i] - 1 - cur <= h_ffrun[i]) i++;
+        if (i >= N || h_end[i] < 0) return DX_OK;
+        const int64_t gap = h_q[i] - 1 - cur;
+        if (gap > h_ffrun[i] || h_last[i] == 0xff) return DX_OK;
+        if (h_end[i] > (int64_t) n || h_end[i] <= cur) return DX_OK;
+        well += 255 * (int32_t) gap + h_last[i];
+        h_cand[M] = (int32_t) i; h_well[M] = well; M++;
+        cur = h_end[i];
+        i++;
+      }
+  }
+  int32_t *d_cand = (int32_t *) dx_arena_get(ctx,M*4 + 4);
+  int32_t *d_well = (int32_t *) dx_arena_get(ctx,M*4 + 4);
+  uint32_t *d_len = (uint32_t *) dx_arena_get(ctx,M*4 + 4);
+  int64_t *d_opre = (int64_t *) dx_arena_get(ctx,(M+1)*8);
+  PkDecEntry *d_ent = (PkDecEntry *) dx_arena_get(ctx,(M+1)*sizeof(PkDecEntry));
+  unsigned long long *d_ticket = (unsigned long long *) dx_arena_get(ctx,8);
+  if (!d_cand || !d_well || !d_len || !d_opre || !d_ent || !d_ticket) return DX_E_NOMEM;
+  DX_CUDA(ctx,cudaMemsetAsync(d_ticket,0,8,ctx->stream));
+  if (M > 0)
+    { DX_CUDA(ctx,cudaMemcpyAsync(d_cand,h_cand,M*4,cudaMemcpyHostToDevice,ctx->stream));
+      DX_CUDA(ctx,cudaMemcpyAsync(d_well,h_well,M*4,cudaMemcpyHostToDevice,ctx->stream));
+    }
+  if ((rc = dxk_pk_layout(ctx,kind,d_in,d_q,d_cand,d_well,(int64_t) M,fieldbytes,plen,width,d_len,d_opre,d_ent)) != DX_OK)
+    return rc;
+  DX_CUDA(ctx,cudaMemcpyAsync(h_total,d_opre+M,8,cudaMemcpyDeviceToHost,ctx->stream));
+  DX_CUDA(ctx,cudaStreamSynchronize(ctx->stream));
+  const size_t total = (size_t) *h_total;
+  if (d_out != NULL)
+    { if (total > cap) return dx_fail(ctx,DX_E_CAP,"output needs %zu bytes, buffer has %zu",total,cap);
+      if ((rc = dxk_unpack2(ctx,kind,upper,width,d_in,n,d_ent,(int64_t) M,d_prefix,plen,d_out,d_ticket)) != DX_OK)
+        return rc;
+      DX_CUDA(ctx,cudaStreamSynchronize(ctx->stream));
+    }
+  *out_len = total;
+  *handled = true;
+  return DX_OK;
+}
+
 extern "C" int dx_undexta_dev(dx_ctx *ctx, int kind, const uint8_t *d_in, size_t n, int width,
                               int upper, uint8_t *d_out, size_t cap, size_t *out_len)
 { if (ctx == NULL || out_len == NULL || (kind != DX_FASTA && kind != DX_ARROW)) return DX_E_ARG;
@@ -682,6 +808,12 @@ extern "C" int dx_undexta_dev(dx_ctx *ctx, int kind, const uint8_t *d_in, size_t
   if ((rc = check_buf(ctx,d_in,"image")) != DX_OK) return rc;
   cudaSetDevice(ctx->device);
   dx_arena_reset(ctx);
+  { bool handled = false;
+    if (d_out != NULL && (rc = undexta_fast(ctx,kind,d_in,n,width,upper,d_out,cap,out_len,&handled)) != DX_OK)
+      return rc;
+    if (handled) return DX_OK;
+    dx_arena_reset(ctx);
+  }
   PkPlan plan;
   if ((rc = plan_undexta(ctx,kind,d_in,n,width,plan)) != DX_OK) return rc;
   if (plan.text_len > cap)
@@ -708,6 +840,11 @@ extern "C" int dx_undexta_size_dev(dx_ctx *ctx, int kind, const uint8_t *d_in, s
   if ((rc = check_buf(ctx,d_in,"image")) != DX_OK) return rc;
   cudaSetDevice(ctx->device);
   dx_arena_reset(ctx);
+  { bool handled = false;
+    if ((rc = undexta_fast(ctx,kind,d_in,n,width,0,NULL,0,out_len,&handled)) != DX_OK) return rc;
+    if (handled) return DX_OK;
+    dx_arena_reset(ctx);
+  }
   PkPlan plan;
   if ((rc = plan_undexta(ctx,kind,d_in,n,width,plan)) != DX_OK) return rc;
   *out_len = plan.text_len;
@@ -1743,11 +1880,7 @@ extern "C" int dx_undexta_size_host(dx_ctx *ctx, int kind, const uint8_t *h_in, 
 { if (ctx == NULL || h_in == NULL || out_len == NULL) return DX_E_ARG;
   int rc;
   if ((rc = stage_in(ctx,h_in,n)) != DX_OK) return rc;
-  dx_arena_reset(ctx);
-  PkPlan plan;
-  if ((rc = plan_undexta(ctx,kind,ctx->io_in,n,width,plan)) != DX_OK) return rc;
-  *out_len = plan.text_len;
-  return DX_OK;
+  return dx_undexta_size_dev(ctx,kind,ctx->io_in,n,width,out_len);
 }
 
 extern "C" int dx_undexta_host(dx_ctx *ctx, int kind, const uint8_t *h_in, size_t n, int width,

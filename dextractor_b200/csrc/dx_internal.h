@@ -239,7 +239,13 @@ int dxk_fa_offsets(dx_ctx *ctx, int kind, FaEntries ent, int32_t lwell_in, int64
 int dxk_fa_pack(dx_ctx *ctx, int kind, const uint8_t *d_text, size_t n, FaEntries ent,
                 int32_t lwell_in, uint8_t *d_out);
 
-struct PkDecEntry               // host-built table for the unpack kernel
+// dx_pack2.cu : vectorised forms (used first; the kernels above remain for unusual layouts)
+int dxk_fa_measure2(dx_ctx *ctx, int kind, const uint8_t *d_text, size_t n, const int64_t *d_hdr,
+                    FaEntries ent, int32_t *d_anyflag);
+int dxk_fa_pack2(dx_ctx *ctx, int kind, const uint8_t *d_text, FaEntries ent, int32_t lwell_in, uint8_t *d_out,
+                 int32_t *d_err, unsigned long long *d_ticket);
+
+struct PkDecEntry               // table for the unpack kernel
 { int64_t bin_off;              // first payload byte in the image
   int64_t out_off;              // header text start in the output
   int64_t text_off;             // first sequence character in the output
@@ -251,6 +257,13 @@ int dxk_pk_walk(dx_ctx *ctx, int fieldbytes, const uint8_t *d_in, size_t n, cons
 int dxk_unpack(dx_ctx *ctx, int kind, int upper, int width, const uint8_t *d_in,
                const PkDecEntry *d_ent, int64_t count, const char *d_prefix, int plen,
                uint8_t *d_out);
+int dxk_unpack2(dx_ctx *ctx, int kind, int upper, int width, const uint8_t *d_in, size_t n, const PkDecEntry *d_ent,
+                int64_t count, const char *d_prefix, int plen, uint8_t *d_out, unsigned long long *d_ticket);
+int dxk_pk_cand_prep(dx_ctx *ctx, const uint8_t *d_in, size_t n, size_t first, int fieldbytes, const int64_t *d_q,
+                     int64_t count, int64_t *d_end, int32_t *d_ffrun, uint8_t *d_last);
+int dxk_pk_layout(dx_ctx *ctx, int kind, const uint8_t *d_in, const int64_t *d_q, const int32_t *d_cand,
+                  const int32_t *d_well, int64_t count, int fieldbytes, int plen, int width, uint32_t *d_len,
+                  int64_t *d_opre, PkDecEntry *d_ent);
 // candidate bookkeeping shared by the .dexta/.dexar/.dexqv chain resolvers: for each candidate
 // field position q, the number of 0xff bytes directly before q-1 (capped) and the byte at q-1
 struct CandInfo { int32_t ffrun; uint8_t last; uint8_t pad[3]; uint8_t field[16]; };

@@ -23,6 +23,7 @@
 
 #include "dx_internal.h"
 #include "dx_common.cuh"
+#include "dx_bits.cuh"
 
 namespace {
 
@@ -55,106 +56,6 @@ __device__ __forceinline__ uint32_t base2(uint32_t c)        // Number_Read, DB.
 { c |= 0x20u;
   return (c == 'c') ? 1u : (c == 'g') ? 2u : (c == 't') ? 3u : 0u;
 }
-
-// Everything one warp needs to walk one line in rows of 32 chunks x 16 bytes.
-struct LineWalk
-{ const uint8_t *base;      // 16-byte aligned address at or before the line
-  int32_t skew, rlen, nchunk;
-  __device__ __forceinline__ void set(const uint8_t *line, int32_t len)
-  { skew = (int32_t) (reinterpret_cast<uintptr_t>(line) & 15);
-    base = line - skew; rlen = len; nchunk = (skew + len + 15) >> 4;
-  }
-  __device__ __forceinline__ uint32_t valid(int32_t c) const
-  { if (c >= nchunk) return 0;
-    const int32_t p0 = c*16 - skew;
-    return dx_range16(max(0,-p0),min(16,rlen - p0));
-  }
-};
-
-// staged words -> global at any byte alignment; SWAP: the stage holds MSB-first words that are
-// to appear in the file as a byte string (the 2-bit packed tags), so every word is byte-swapped
-template <bool SWAP>
-__device__ __forceinline__ void copy_out(uint8_t *gdst, const uint32_t *ssrc, uint32_t n, int lane)
-{ const uint8_t *sb = reinterpret_cast<const uint8_t *>(ssrc);
-  uint32_t head = (4u - (uint32_t) (reinterpret_cast<uintptr_t>(gdst) & 3u)) & 3u;
-  if (head > n) head = n;
-  if ((uint32_t) lane < head)
-    gdst[lane] = sb[SWAP ? (lane ^ 3) : lane];
-  const uint32_t body = (n - head) >> 2;
-  uint32_t *gw = reinterpret_cast<uint32_t *>(gdst + head);
-  const uint32_t sh = head * 8u;                   // source is `head` bytes ahead of a word
-  for (uint32_t i = lane; i < body; i += 32)
-    { uint32_t lo = ssrc[i], hi = ssrc[i+1];
-      if (SWAP) { lo = __byte_perm(lo,0,0x0123); hi = __byte_perm(hi,0,0x0123); }
-      gw[i] = __funnelshift_r(lo,hi,sh);          // sh == 0 -> lo
-    }
-  const uint32_t done = head + 4u*body;
-  if ((uint32_t) lane < n - done)
-    gdst[done + lane] = sb[SWAP ? ((done + lane) ^ 3u) : (done + lane)];
-}
-
-// ---- the warp's output: completed words in shared memory, the trailing partial word in a register
-struct WarpBits
-{ uint32_t *stage;          // [kStageWords + 4]
-  uint32_t  nst;            // completed words staged                        (warp-uniform)
-  uint32_t  carry, cbits;   // trailing partial word, top aligned; its bits  (warp-uniform)
-  uint32_t  flushed;        // words already written to global               (warp-uniform)
-  uint8_t  *gptr;           // global address of word 0 of the stream
-
-  __device__ __forceinline__ void init(uint32_t *st, uint8_t *g)
-  { stage = st; nst = 0; carry = 0; cbits = 0; flushed = 0; gptr = g; }
-  __device__ __forceinline__ uint32_t bitpos() const { return nst*32u + cbits; }       // in the stage
-  __device__ __forceinline__ uint32_t total() const { return (flushed + nst)*32u + cbits; }
-
-  // make room for `bits` more bits
-  template <bool SWAP>
-  __device__ __forceinline__ void reserve(uint32_t bits, int lane)
-  { if (nst + ((cbits + bits + 31u) >> 5) + 1u > (uint32_t) kStageWords)
-      { __syncwarp();
-        copy_out<SWAP>(gptr + (size_t) flushed*4u,stage,nst*4u,lane);
-        __syncwarp();
-        flushed += nst; nst = 0;
-      }
-  }
-};
-
-// one lane's bit string inside a row: pieces are shifted through a 64-bit register; every word the
-// lane completes is stored, what is left over joins its neighbours in finish()
-struct LaneSink
-{ uint64_t acc; uint32_t nacc, widx, fw;
-  __device__ __forceinline__ void start(uint32_t pos)
-  { widx = fw = pos >> 5; nacc = pos & 31u; acc = 0; }
-  __device__ __forceinline__ void put(uint32_t *stage, uint32_t bits, uint32_t len)    // len <= 32
-  { acc = (acc << len) | bits;
-    nacc += len;
-    if (nacc >= 32u)
-      { nacc -= 32u;
-        stage[widx++] = (uint32_t) (acc >> nacc);
-      }
-  }
-  // warp-collective: merge the partial words, update the warp state
-  __device__ __forceinline__ void finish(WarpBits &wb, int lane)
-  { uint32_t t = nacc ? (uint32_t) (acc << (32u - nacc)) : 0u;          // my trailing partial word
-    if (lane == 0 && widx == fw) t |= wb.carry;                          // still in the carry's word
-    // segmented inclusive OR-scan keyed by the word the partial belongs to (keys ascend by lane)
-    const uint32_t kprev = __shfl_up_sync(DX_FULL,widx,1);
-    const uint32_t heads = __ballot_sync(DX_FULL,lane == 0 || kprev != widx);
-    const int seg = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));   // first lane of my segment
-    uint32_t sc = t;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1)
-      { const uint32_t o = __shfl_up_sync(DX_FULL,sc,d);
-        if (lane - d >= seg) sc |= o;
-      }
-    uint32_t before = __shfl_up_sync(DX_FULL,sc,1);                      // what is already in my first word
-    if (lane == 0) before = wb.carry;
-    if (widx != fw && before) wb.stage[fw] |= before;                    // I completed that word
-    wb.carry = __shfl_sync(DX_FULL,sc,31);
-    const uint32_t endw = __shfl_sync(DX_FULL,widx,31), endb = __shfl_sync(DX_FULL,nacc,31);
-    wb.nst = endw; wb.cbits = endb;
-    if (endb == 0) wb.carry = 0;
-  }
-};
 
 // ---- plain stream: one Huffman item per symbol (Encode, QV.c:386-443) --------------------------------
 // One row (32 lanes x 16 bytes) per iteration, the next row's chunk already in flight.  The code is
@@ -315,7 +216,7 @@ __device__ void code_stream(const EncArgs &a, const uint32_t *stab, const uint8_
   const int32_t rc = (kind == 0) ? a.delchar : (kind == 4) ? a.subchar : -1;
   const uint32_t lossmask = !a.lossy ? 0xffffffffu : (kind == 2) ? 0xfefefefeu
                                                     : (kind == 3) ? 0xfcfcfcfcu : 0xffffffffu;
-  WarpBits wb; wb.init(stage,gptr);
+  WarpBits wb; wb.init(stage,gptr,kStageWords);
   if (rc < 0) code_plain<MODE>(a,stab + kind*256,line,rlen,lossmask,lane,wb,total_bits,plast_out);
   else        code_run<MODE>(a,stab + kind*256,stab + (kind == 0 ? 1 : 5)*256,(uint32_t) rc,line,rlen,lane,
                              queue,wb,total_bits,plast_out);
@@ -347,7 +248,7 @@ __device__ uint32_t code_tags(const EncArgs &a, const uint8_t *del, const uint8_
                               int32_t rlen, int lane, uint32_t *stage, uint8_t *gptr)
 { if (MODE == 0 && a.delchar < 0) return (uint32_t) rlen;      // every tag is kept
   LineWalk lw; lw.set(tag,rlen);
-  WarpBits wb; wb.init(stage,gptr);
+  WarpBits wb; wb.init(stage,gptr,kStageWords);
   uint32_t mykept = 0;
 #pragma unroll 1
   for (int32_t c0 = 0; c0 < lw.nchunk; c0 += 32)

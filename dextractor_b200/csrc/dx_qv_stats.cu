@@ -141,6 +141,23 @@ __device__ __forceinline__ void bump(uint8_t *mine, unsigned long long *wide, ui
   if (c == 256u) atomicAdd(&wide[b],256ull);
 }
 
+// two counters at once: both loads are issued before either store, so the two read-modify-write
+// chains overlap (the kernel is bound by that latency); a == b is folded into the second store
+template <int T>
+__device__ __forceinline__ void bump2(uint8_t *mine, unsigned long long *wide, uint32_t a, uint32_t b)
+{ uint8_t *pa = mine + (a & ~3u) * T + (a & 3u);
+  uint8_t *pb = mine + (b & ~3u) * T + (b & 3u);
+  const uint32_t ca = *pa, cb = *pb;
+  const uint32_t same = (a == b) ? 1u : 0u;
+  const uint32_t na = ca + 1u, nb = cb + 1u + same;
+  *pa = (uint8_t) na;
+  *pb = (uint8_t) nb;
+  if ((na == 256u && !same) || nb >= 256u)
+    { if (na == 256u && !same) atomicAdd(&wide[a],256ull);
+      if (nb >= 256u) atomicAdd(&wide[b],256ull);
+    }
+}
+
 // the warp adds its lanes' byte counters to the CTA-wide histogram and clears them
 template <bool RUN>
 __device__ __noinline__ void hist_warp_flush(uint32_t *cnt, unsigned long long *wide, uint32_t pad)
@@ -232,8 +249,8 @@ k_qv_hist(HistArgs a)
                 }
               const uint32_t w[4] = { v.x, v.y, v.z, v.w };
 #pragma unroll
-              for (int i = 0; i < 16; i++)
-                bump<T>(mine,wd,(w[i >> 2] >> ((i & 3)*8)) & 0xffu);
+              for (int i = 0; i < 8; i++)                            // byte i of the low half with byte i of the high half
+                bump2<T>(mine,wd,(w[i >> 2] >> ((i & 3)*8)) & 0xffu,(w[2 + (i >> 2)] >> ((i & 3)*8)) & 0xffu);
             }
         }
       else
@@ -270,11 +287,12 @@ k_qv_hist(HistArgs a)
                   if ((uint32_t) lane < n)
                     { const uint32_t it = queue[done + lane];
                       p = (int32_t) (it >> 8);
-                      bump<T>(mine,wd,it & 0xffu);
-                      if (runs)
+                      if (runs)                                        // symbol and run bins never coincide
                         { const int32_t pp = (lane == 0) ? prevpos : (int32_t) (queue[done + lane - 1] >> 8);
-                          bump<T>(mine,wd,256u + (uint32_t) min(p - pp - 1,255));
+                          bump2<T>(mine,wd,it & 0xffu,256u + (uint32_t) min(p - pp - 1,255));
                         }
+                      else
+                        bump<T>(mine,wd,it & 0xffu);
                     }
                   prevpos = __shfl_sync(DX_FULL,p,n-1);
                   done += n;
