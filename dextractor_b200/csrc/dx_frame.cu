@@ -115,7 +115,8 @@ k_pred_count(const uint8_t *buf, size_t n, size_t first, uint32_t *tile_count)
     }
 }
 
-// exclusive scan of ntiles 32-bit counts into 64-bit offsets; one CTA. total at prefix[ntiles].
+// exclusive scan of ntiles 32-bit counts into 64-bit offsets; one CTA, 8 consecutive values per
+// thread per round.  total at prefix[ntiles].
 __global__ void __launch_bounds__(1024)
 k_tile_scan(const uint32_t *count, int64_t ntiles, int64_t *prefix)
 { __shared__ uint64_t wsum[32];
@@ -123,9 +124,12 @@ k_tile_scan(const uint32_t *count, int64_t ntiles, int64_t *prefix)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) carry = 0;
   __syncthreads();
-  for (int64_t b = 0; b < ntiles; b += 1024)
-    { int64_t i = b + threadIdx.x;
-      uint64_t v = (i < ntiles) ? count[i] : 0;
+  for (int64_t b = 0; b < ntiles; b += 8192)
+    { const int64_t i0 = b + (int64_t) threadIdx.x * 8;
+      uint32_t c[8];
+      uint64_t v = 0;
+#pragma unroll
+      for (int k = 0; k < 8; k++) { c[k] = (i0 + k < ntiles) ? count[i0 + k] : 0u; v += c[k]; }
       uint64_t inc = dx_warp_incl_sum64(v,lane);
       if (lane == 31) wsum[warp] = inc;
       __syncthreads();
@@ -136,9 +140,13 @@ k_tile_scan(const uint32_t *count, int64_t ntiles, int64_t *prefix)
         }
       __syncthreads();
       uint64_t excl = carry + wsum[warp] + inc - v;
-      if (i < ntiles) prefix[i] = (int64_t) excl;
+#pragma unroll
+      for (int k = 0; k < 8; k++)
+        { if (i0 + k < ntiles) prefix[i0 + k] = (int64_t) excl;
+          excl += c[k];
+        }
       __syncthreads();
-      if (threadIdx.x == 1023) carry = excl + v;
+      if (threadIdx.x == 1023) carry = excl;
       __syncthreads();
     }
   if (threadIdx.x == 0) prefix[ntiles] = (int64_t) carry;

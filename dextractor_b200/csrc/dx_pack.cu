@@ -171,40 +171,16 @@ k_fa_measure(int kind, const uint8_t *text, int64_t n, const int64_t *hdr, FaEnt
 
 // ---- offsets --------------------------------------------------------------------------------------
 
-__global__ void __launch_bounds__(1024)
-k_fa_offsets(int kind, FaEntries ent, int32_t lwell_in)
-{ __shared__ uint64_t wsum[32];
-  __shared__ uint64_t carry;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+// encoded bytes of every entry: well-delta bytes + fields + payload (dexta.c:187-204); the offsets
+// are their exclusive scan (dxk_scan_u32)
+__global__ void k_fa_bytes(int kind, FaEntries ent, int32_t lwell_in)
+{ const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ent.n) return;
   const uint32_t fields = (kind == DX_FASTA) ? 12u : 16u;
-  if (threadIdx.x == 0) carry = 0;
-  __syncthreads();
-  for (int64_t b = 0; b < ent.n; b += 1024)
-    { const int64_t i = b + threadIdx.x;
-      uint64_t v = 0;
-      if (i < ent.n)
-        { const int32_t lw = (i == 0) ? lwell_in : ent.well[i-1];
-          const int32_t d  = ent.well[i] - lw;
-          const uint32_t wb = 1u + (d >= 255 ? (uint32_t) d / 255u : 0u);
-          v = wb + fields + (((uint32_t) ent.rlen[i] + 3u) >> 2);
-          ent.bytes[i] = (uint32_t) v;
-        }
-      const uint64_t inc = dx_warp_incl_sum64(v,lane);
-      if (lane == 31) wsum[warp] = inc;
-      __syncthreads();
-      if (warp == 0)
-        { const uint64_t w = wsum[lane];
-          const uint64_t wi = dx_warp_incl_sum64(w,lane);
-          wsum[lane] = wi - w;
-        }
-      __syncthreads();
-      const uint64_t excl = carry + wsum[warp] + inc - v;
-      if (i < ent.n) ent.off[i] = (int64_t) excl;
-      __syncthreads();
-      if (threadIdx.x == 1023) carry = excl + v;
-      __syncthreads();
-    }
-  if (threadIdx.x == 0) ent.off[ent.n] = (int64_t) carry;
+  const int32_t lw = (i == 0) ? lwell_in : ent.well[i-1];
+  const int32_t d  = ent.well[i] - lw;
+  const uint32_t wb = 1u + (d >= 255 ? (uint32_t) d / 255u : 0u);
+  ent.bytes[i] = wb + fields + (((uint32_t) ent.rlen[i] + 3u) >> 2);
 }
 
 // ---- pack -------------------------------------------------------------------------------------------
@@ -481,8 +457,10 @@ int dxk_fa_measure(dx_ctx *ctx, int kind, const uint8_t *d_text, size_t n, const
 int dxk_fa_offsets(dx_ctx *ctx, int kind, FaEntries ent, int32_t lwell_in, int64_t *h_total)
 { *h_total = 0;
   if (ent.n == 0) return DX_OK;
-  DX_PROF_BEGIN(ctx); k_fa_offsets<<<1,1024,0,ctx->stream>>>(kind,ent,lwell_in);
-  DX_LAUNCHED(ctx,"k_fa_offsets");
+  DX_PROF_BEGIN(ctx); k_fa_bytes<<<(unsigned) ((ent.n + 255)/256),256,0,ctx->stream>>>(kind,ent,lwell_in);
+  DX_LAUNCHED(ctx,"k_fa_bytes");
+  int rc = dxk_scan_u32(ctx,ent.bytes,ent.n,ent.off);
+  if (rc != DX_OK) return rc;
   DX_CUDA(ctx,cudaMemcpyAsync(h_total,ent.off+ent.n,8,cudaMemcpyDeviceToHost,ctx->stream));
   DX_CUDA(ctx,cudaStreamSynchronize(ctx->stream));
   return DX_OK;

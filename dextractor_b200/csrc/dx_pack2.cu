@@ -121,54 +121,39 @@ __device__ bool parse_header2(int kind, const uint8_t *t, int64_t p, int64_t end
 // unterminated, 8 symbol count assumed from the line lattice (verified by the packer)
 __global__ void __launch_bounds__(kP2Threads)
 k_fa_measure2(int kind, const uint8_t *text, int64_t n, const int64_t *hdr, FaEntries ent, int32_t *anyflag)
-{ const int lane = threadIdx.x & 31;
-  const int64_t nwarp = ((int64_t) gridDim.x * blockDim.x) >> 5;
-  for (int64_t e = ((int64_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5; e < ent.n; e += nwarp)
-    { const int64_t h0 = hdr[e];
-      const int64_t stop = (e+1 < ent.n) ? hdr[e+1] : n;
-      int64_t h1 = -1;                                               // end of the header line
-      for (int64_t b = h0; b < stop && h1 < 0; b += 32)
-        { const bool nl = (b + lane < stop) && text[b + lane] == '\n';
-          const uint32_t m = __ballot_sync(DX_FULL,nl);
-          if (m) h1 = b + __ffs(m) - 1;
-        }
-      int32_t flag = 0;
-      if (h1 < 0) { h1 = stop - 1; flag |= 4; }                     // unterminated header line
-      if (h1 - h0 > kLineLimit) flag |= 4;
-      const int64_t seq = h1 + 1, region = stop - seq;
-      int64_t first_nl = -1;                                         // end of the first sequence line
-      for (int64_t b = seq; b < stop && first_nl < 0; b += 32)
-        { const bool nl = (b + lane < stop) && text[b + lane] == '\n';
-          const uint32_t m = __ballot_sync(DX_FULL,nl);
-          if (m) first_nl = b + __ffs(m) - 1 - seq;
-        }
-      const int64_t W = (first_nl < 0) ? region : first_nl;
-      if (region > 0 && text[stop-1] != '\n') flag |= 4;            // last line unterminated
-      if (W > kLineLimit) flag |= 4;
-      int64_t rlen = 0;
-      if (region > 0)
-        { const int64_t k = region / (W + 1), rem = region % (W + 1);
-          if (W >= 1 && rem != 1)
-            { rlen = k*W + (rem ? rem - 1 : 0); flag |= 8; }
-          else
-            { // blank lines: count the symbols one by one (rare)
-              uint32_t cnt = 0;
-              for (int64_t b = seq + lane; b < stop; b += 32) cnt += (text[b] != '\n');
-              rlen = dx_warp_sum(cnt);
-            }
-        }
-      if (rlen >= (int64_t) 1 << 30 || region >= (int64_t) 1 << 31) flag |= 4;
-      if (lane == 0)
-        { int32_t well = 0, beg = 0, en = 0, aux[2] = { 0, 0 };
-          if (text[h0] != '>' || !parse_header2(kind,text,h0,h1,well,beg,en,aux)) flag |= 1;
-          ent.hdr[e] = h0; ent.seq[e] = seq; ent.region[e] = region;
-          ent.rlen[e] = (int32_t) rlen; ent.width[e] = (int32_t) min(W,(int64_t) 0x7fffffff);
-          ent.well[e] = well; ent.beg[e] = beg; ent.end[e] = en;
-          ent.aux[2*e] = aux[0]; ent.aux[2*e+1] = aux[1];
-          ent.flag[e] = flag;
-          if (flag & 5) atomicOr(anyflag,flag & 5);
-        }
+{ // one THREAD per entry: the work is two short byte scans (header line, first sequence line) and
+  // the header parse, all sequential
+  const int64_t e = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= ent.n) return;
+  const int64_t h0 = hdr[e];
+  const int64_t stop = (e+1 < ent.n) ? hdr[e+1] : n;
+  int32_t flag = 0;
+  int64_t h1 = h0;                                                 // end of the header line
+  while (h1 < stop && text[h1] != '\n' && h1 - h0 <= kLineLimit) h1++;
+  if (h1 >= stop) { h1 = stop - 1; flag |= 4; }                   // unterminated header line
+  else if (text[h1] != '\n') flag |= 4;                           // too long
+  const int64_t seq = h1 + 1, region = stop - seq;
+  int64_t W = 0;                                                   // length of the first sequence line
+  while (seq + W < stop && text[seq + W] != '\n' && W <= kLineLimit) W++;
+  if (region > 0 && text[stop-1] != '\n') flag |= 4;              // last line unterminated
+  if (W > kLineLimit) flag |= 4;
+  int64_t rlen = 0;
+  if (region > 0 && !(flag & 4))
+    { const int64_t k = region / (W + 1), rem = region % (W + 1);
+      if (W >= 1 && rem != 1)
+        { rlen = k*W + (rem ? rem - 1 : 0); flag |= 8; }
+      else
+        { for (int64_t b = seq; b < stop; b++) rlen += (text[b] != '\n'); }   // blank lines (rare)
     }
+  if (rlen >= (int64_t) 1 << 30 || region >= (int64_t) 1 << 31) flag |= 4;
+  int32_t well = 0, beg = 0, en = 0, aux[2] = { 0, 0 };
+  if (text[h0] != '>' || !parse_header2(kind,text,h0,h1,well,beg,en,aux)) flag |= 1;
+  ent.hdr[e] = h0; ent.seq[e] = seq; ent.region[e] = region;
+  ent.rlen[e] = (int32_t) rlen; ent.width[e] = (int32_t) min(W,(int64_t) 0x7fffffff);
+  ent.well[e] = well; ent.beg[e] = beg; ent.end[e] = en;
+  ent.aux[2*e] = aux[0]; ent.aux[2*e+1] = aux[1];
+  ent.flag[e] = flag;
+  if (flag & 5) atomicOr(anyflag,flag & 5);
 }
 
 // ---- pack ----------------------------------------------------------------------------------------------------
@@ -475,8 +460,7 @@ __global__ void k_pk_build_ent(int kind, const uint8_t *in, const int64_t *q, co
 int dxk_fa_measure2(dx_ctx *ctx, int kind, const uint8_t *d_text, size_t n, const int64_t *d_hdr,
                     FaEntries ent, int32_t *d_anyflag)
 { if (ent.n == 0) return DX_OK;
-  int64_t grid = (ent.n + kP2Warps - 1) / kP2Warps;
-  if (grid > (int64_t) ctx->sm_count * 8) grid = (int64_t) ctx->sm_count * 8;
+  const int64_t grid = (ent.n + kP2Threads - 1) / kP2Threads;
   DX_PROF_BEGIN(ctx);
   k_fa_measure2<<<(unsigned) grid,kP2Threads,0,ctx->stream>>>(kind,d_text,(int64_t) n,d_hdr,ent,d_anyflag);
   DX_LAUNCHED(ctx,"k_fa_measure2");

@@ -104,11 +104,14 @@ k_probe_sub(const uint8_t *text, QvEntries ent, uint64_t tot_in, const uint64_t 
 //   RUN = false  streams without a run character: every byte is counted; the bytes of a 16-byte
 //                chunk that lie outside the line are zeroed and counted in bin 0, which is
 //                corrected by the (known) number of such bytes.  768 threads x 256 B.
-//   RUN = true   del / sub with a run character: run bytes are skipped by a SWAR compare (their
-//                count is recovered by subtraction on the host); the (position, symbol) pairs of
-//                the other bytes are compacted into a per-warp queue and counted 32 at a time,
-//                together with the run length before each (position minus the queue
-//                neighbour's position), from entry e_del / e_sub on.  384 threads x 512 B.
+//   RUN = true   del / sub with a run character (k_qv_hist_run): run bytes are skipped by a SWAR
+//                compare (their count is recovered by subtraction on the host); the (position,
+//                symbol) pairs of the other bytes are compacted into a per-warp queue and counted 32
+//                at a time, together with the run length before each (position minus the queue
+//                neighbour's position), from entry e_del / e_sub on.  Here the counters are one
+//                32-bit histogram per WARP: __match_any groups the lanes of a batch that hit the
+//                same bin and one of them adds the group's size, so no two lanes ever write the same
+//                word.  4 KB per warp, 32 warps per SM.
 
 struct HistArgs
 { const uint8_t *text;
@@ -253,63 +256,6 @@ k_qv_hist(HistArgs a)
                 bump2<T>(mine,wd,(w[i >> 2] >> ((i & 3)*8)) & 0xffu,(w[2 + (i >> 2)] >> ((i & 3)*8)) & 0xffu);
             }
         }
-      else
-        { const uint32_t rc = (uint32_t) a.rc[si];
-          const bool runs = (e >= a.efirst[si]);
-          int32_t prevpos = -1;                                    // last position that is not rc
-          uint32_t qn = 0;                                         // queued items (warp-uniform)
-#pragma unroll 1
-          for (int32_t c0 = 0; c0 < nchunk + 32; c0 += 32)        // one extra round drains the queue
-            { const bool last = (c0 >= nchunk);
-              if (!last)
-                { const int32_t c = c0 + lane;
-                  const uint4 v = nxt;
-                  nxt = (c + 32 < nchunk) ? dx_ldg16(base + (int64_t) (c + 32)*16) : make_uint4(0,0,0,0);
-                  const int32_t p0 = c*16 - skew;
-                  uint32_t m = 0;
-                  if (c < nchunk)
-                    m = dx_range16(max(0,-p0),min(16,rlen - p0)) & ~dx_eq_mask16(v,rc);
-                  const uint32_t k = __popc(m);
-                  const uint32_t inc = dx_warp_incl_sum(k,lane);
-                  uint32_t at = qn + inc - k;
-                  while (m)
-                    { const int i = __ffs(m) - 1; m &= m - 1;
-                      queue[at++] = ((uint32_t) (p0 + i) << 8) | dx_byte_of(v,i);
-                    }
-                  qn += __shfl_sync(DX_FULL,inc,31);
-                  __syncwarp();
-                }
-              uint32_t done = 0;
-#pragma unroll 1
-              while (qn - done >= 32u || (last && done < qn))
-                { const uint32_t n = min(32u,qn - done);
-                  int32_t p = 0;
-                  if ((uint32_t) lane < n)
-                    { const uint32_t it = queue[done + lane];
-                      p = (int32_t) (it >> 8);
-                      if (runs)                                        // symbol and run bins never coincide
-                        { const int32_t pp = (lane == 0) ? prevpos : (int32_t) (queue[done + lane - 1] >> 8);
-                          bump2<T>(mine,wd,it & 0xffu,256u + (uint32_t) min(p - pp - 1,255));
-                        }
-                      else
-                        bump<T>(mine,wd,it & 0xffu);
-                    }
-                  prevpos = __shfl_sync(DX_FULL,p,n-1);
-                  done += n;
-                }
-              // keep what is left (< 32 items) at the front of the queue
-              __syncwarp();
-              const uint32_t left = qn - done;
-              uint32_t keep = 0;
-              if ((uint32_t) lane < left) keep = queue[done + lane];
-              __syncwarp();
-              if ((uint32_t) lane < left) queue[lane] = keep;
-              qn = left;
-              __syncwarp();
-            }
-          if (runs && lane == 0 && prevpos < rlen-1)              // trailing run (QV.c:713-720)
-            bump<T>(mine,wd,256u + (uint32_t) min(rlen-1-prevpos,255));
-        }
     }
   __syncthreads();
   for (int i = threadIdx.x; i < C::kStreams*C::kBins; i += T)
@@ -322,6 +268,125 @@ k_qv_hist(HistArgs a)
         }
     }
 }
+
+constexpr int kRunWarps   = 16;
+constexpr int kRunThreads = kRunWarps * 32;
+constexpr int kRunWarpWords = 512 + kHistQueue;          // histogram (256 symbols + 256 run lengths), queue
+
+// the lanes < n of the warp add 1 to bin key[lane]; lanes with equal keys are grouped
+__device__ __forceinline__ void warp_count(uint32_t *hist, uint32_t key, uint32_t n, int lane)
+{ if ((uint32_t) lane < n)
+    { const uint32_t mask = (n >= 32u) ? DX_FULL : ((1u << n) - 1u);
+      const uint32_t peers = __match_any_sync(mask,key);
+      if ((uint32_t) lane == (uint32_t) (__ffs(peers) - 1)) hist[key] += (uint32_t) __popc(peers);
+    }
+  __syncwarp();
+}
+
+__device__ __noinline__ void run_warp_flush(const HistArgs &a, int s, uint32_t *hist, int lane)
+{ __syncwarp();
+  for (int b = lane; b < 512; b += 32)
+    { const uint32_t v = hist[b];
+      hist[b] = 0;
+      if (v)
+        { const int tab = (b < 256) ? s : (s == 0 ? 4 : 5);
+          atomicAdd(&a.ghist[tab*256 + (b & 255)],(unsigned long long) v);
+        }
+    }
+  __syncwarp();
+}
+
+__global__ void __launch_bounds__(kRunThreads,2)
+k_qv_hist_run(HistArgs a)
+{ extern __shared__ __align__(16) uint8_t dx_hist_smem[];
+  const int lane = threadIdx.x & 31;
+  uint32_t *hist  = reinterpret_cast<uint32_t *>(dx_hist_smem) + (threadIdx.x >> 5) * kRunWarpWords;
+  uint32_t *queue = hist + 512;
+  for (int b = lane; b < 512; b += 32) hist[b] = 0;
+  __syncwarp();
+
+  const int64_t nlines = a.ent.n;
+  const int64_t total = nlines * a.ns;
+  int cur = 0;
+  unsigned long long next = 0;
+  if (lane == 0) next = atomicAdd(a.ticket,1ull);
+  while (true)
+    { const int64_t u = (int64_t) __shfl_sync(DX_FULL,next,0);
+      const int si = (u >= total) ? a.ns : (int) (u / nlines);
+      if (si != cur)
+        { run_warp_flush(a,a.sidx[cur],hist,lane);
+          cur = si;
+        }
+      if (si >= a.ns) break;
+      if (lane == 0) next = atomicAdd(a.ticket,1ull);
+      const int s = a.sidx[si];
+      const int64_t e = u - (int64_t) si*nlines;
+      const int32_t rlen = a.ent.rlen[e];
+      if (rlen == 0) continue;
+      const int lineidx = (s == 0) ? 0 : s + 1;                   // del | tag | ins | mrg | sub
+      const uint8_t *line = a.text + a.ent.line0[e] + (int64_t) lineidx*((int64_t) rlen + 1);
+      const int skew = (int) (reinterpret_cast<uintptr_t>(line) & 15);
+      const uint8_t *base = line - skew;                           // 16-byte aligned
+      const int32_t nchunk = (skew + rlen + 15) >> 4;
+      const uint32_t rc = (uint32_t) a.rc[si];
+      const bool runs = (e >= a.efirst[si]);
+      int32_t prevpos = -1;                                        // last position that is not rc
+      uint32_t qn = 0;                                             // queued items (warp-uniform)
+      uint4 nxt = (lane < nchunk) ? dx_ldg16(base + (int64_t) lane*16) : make_uint4(0,0,0,0);
+      uint4 nx2 = (lane + 32 < nchunk) ? dx_ldg16(base + (int64_t) (lane + 32)*16) : make_uint4(0,0,0,0);
+#pragma unroll 1
+      for (int32_t c0 = 0; c0 < nchunk + 32; c0 += 32)            // one extra round drains the queue
+        { const bool last = (c0 >= nchunk);
+          if (!last)
+            { const int32_t c = c0 + lane;
+              const uint4 v = nxt;
+              nxt = nx2;
+              nx2 = (c + 64 < nchunk) ? dx_ldg16(base + (int64_t) (c + 64)*16) : make_uint4(0,0,0,0);
+              const int32_t p0 = c*16 - skew;
+              uint32_t m = 0;
+              if (c < nchunk)
+                m = dx_range16(max(0,-p0),min(16,rlen - p0)) & ~dx_eq_mask16(v,rc);
+              const uint32_t k = __popc(m);
+              const uint32_t inc = dx_warp_incl_sum(k,lane);
+              uint32_t at = qn + inc - k;
+              while (m)
+                { const int i = __ffs(m) - 1; m &= m - 1;
+                  queue[at++] = ((uint32_t) (p0 + i) << 8) | dx_byte_of(v,i);
+                }
+              qn += __shfl_sync(DX_FULL,inc,31);
+              __syncwarp();
+            }
+          uint32_t done = 0;
+#pragma unroll 1
+          while (qn - done >= 32u || (last && done < qn))
+            { const uint32_t n = min(32u,qn - done);
+              uint32_t it = 0, rl = 0;
+              if ((uint32_t) lane < n)
+                { it = queue[done + lane];
+                  const int32_t pp = (lane == 0) ? prevpos : (int32_t) (queue[done + lane - 1] >> 8);
+                  rl = (uint32_t) min((int32_t) (it >> 8) - pp - 1,255);
+                }
+              warp_count(hist,it & 0xffu,n,lane);
+              if (runs) warp_count(hist,256u + rl,n,lane);
+              prevpos = __shfl_sync(DX_FULL,(int32_t) (it >> 8),n-1);
+              done += n;
+            }
+          // keep what is left (< 32 items) at the front of the queue
+          const uint32_t left = qn - done;
+          uint32_t keep = 0;
+          if ((uint32_t) lane < left) keep = queue[done + lane];
+          __syncwarp();
+          if ((uint32_t) lane < left) queue[lane] = keep;
+          qn = left;
+          __syncwarp();
+        }
+      if (runs && prevpos < rlen-1)                                // trailing run (QV.c:713-720)
+        { if (lane == 0) hist[256 + min(rlen-1-prevpos,255)] += 1u;
+          __syncwarp();
+        }
+    }
+}
+
 
 }  // namespace
 
@@ -382,8 +447,8 @@ int dxk_qv_hist(dx_ctx *ctx, const uint8_t *d_text, QvEntries ent, const QvProbe
   if (!attr_done)
     { DX_CUDA(ctx,cudaFuncSetAttribute(k_qv_hist<false>,cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int) HistCfg<false>::kSmem));
-      DX_CUDA(ctx,cudaFuncSetAttribute(k_qv_hist<true>,cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int) HistCfg<true>::kSmem));
+      DX_CUDA(ctx,cudaFuncSetAttribute(k_qv_hist_run,cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int) (kRunWarps*kRunWarpWords*4)));
       attr_done = true;
     }
   if (plain.ns > 0)
@@ -393,7 +458,7 @@ int dxk_qv_hist(dx_ctx *ctx, const uint8_t *d_text, QvEntries ent, const QvProbe
     }
   if (run.ns > 0)
     { DX_PROF_BEGIN(ctx);
-      k_qv_hist<true><<<ctx->sm_count,HistCfg<true>::kThreads,HistCfg<true>::kSmem,ctx->stream>>>(run);
+      k_qv_hist_run<<<ctx->sm_count*2,kRunThreads,kRunWarps*kRunWarpWords*4,ctx->stream>>>(run);
       DX_LAUNCHED(ctx,"k_qv_hist_run");
     }
   DX_CUDA(ctx,cudaMemcpyAsync(h_hist,d_hist,6*256*8,cudaMemcpyDeviceToHost,ctx->stream));
