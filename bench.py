@@ -88,8 +88,10 @@ class ClockSampler:
 _SAMPLES = {}
 
 
-def cpu_reference_sample(sample_mb: float, seed: int = 1):
-    """dexqv + undexqv of a bounded sample with the reference binaries; returns timings."""
+def cpu_reference_sample(sample_mb: float, seed: int = 1, nproc: int = 1):
+    """dexqv + undexqv of a bounded sample with the reference binaries; returns timings.
+    nproc > 1: that many independent copies at once (the reference has no threads; independent
+    files are the only way it uses more cores), throughput = nproc * bytes / wall."""
     import numpy as np
     from dextractor_b200 import synth
     from oracle import orc
@@ -100,16 +102,21 @@ def cpu_reference_sample(sample_mb: float, seed: int = 1):
         _SAMPLES[key] = synth.make_quiva(seed, L)
     text = _SAMPLES[key]
     if orc.have_ref():
-        enc, t_enc = orc.ref_tool("dexqv", text, taskset=0)
-        back, t_dec = orc.ref_tool("undexqv", enc, taskset=0)
+        if nproc > 1:
+            enc, t_enc = orc.ref_tool_parallel("dexqv", text, nproc)
+            back, t_dec = orc.ref_tool_parallel("undexqv", enc, nproc)
+        else:
+            enc, t_enc = orc.ref_tool("dexqv", text, taskset=0)
+            back, t_dec = orc.ref_tool("undexqv", enc, taskset=0)
         kind = "reference"
     else:                                   # the C restatement (oracle/dx_oracle.c)
+        nproc = 1
         t0 = time.perf_counter(); enc = orc.dexqv(text); t_enc = time.perf_counter() - t0
         t0 = time.perf_counter(); back = orc.undexqv(enc); t_dec = time.perf_counter() - t0
         kind = "port"
     assert back == text
-    return {"bytes": len(text), "t_enc": t_enc, "t_dec": t_dec, "kind": kind,
-            "compressed": len(enc)}
+    return {"bytes": len(text) * nproc, "t_enc": t_enc, "t_dec": t_dec, "kind": kind,
+            "compressed": len(enc) * nproc, "cores": nproc, "sample_bytes": len(text)}
 
 
 def run_reference(args):
@@ -117,25 +124,29 @@ def run_reference(args):
     if rank != 0:
         return
     sample_mb = args.ref_sample_mb
+    nproc = max(1, (os.cpu_count() or 1) if args.ref_cores <= 0 else args.ref_cores)
     times = []
     for i in range(args.warmup + args.steps):
-        r = cpu_reference_sample(sample_mb, seed=1)
+        r = cpu_reference_sample(sample_mb, seed=1, nproc=nproc)
         if i >= args.warmup:
             times.append(r)
     t = sum(x["t_enc"] + x["t_dec"] for x in times) / len(times)
     U = times[0]["bytes"]
+    nproc = times[0]["cores"]
     val = 2 * U / t / GB
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": "GB/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8", "data": "synthetic",
-        "config": workload_config(args, U),
-        "cpu_baseline": {"value": val, "unit": "GB/s", "cores": 1, "kind": times[0]["kind"],
-                         "sample": f"{U/1e6:.0f} MB synthetic .quiva per step, dexqv then undexqv "
-                                   f"(reference binaries, 1 thread, files on /dev/shm)",
+        "config": workload_config(args, int(args.size_gb * GB)),
+        "cpu_baseline": {"value": val, "unit": "GB/s", "cores": nproc, "kind": times[0]["kind"],
+                         "sample": f"{nproc} x {times[0]['sample_bytes']/1e6:.0f} MB synthetic .quiva per "
+                                   f"step, dexqv then undexqv (reference binaries, one single-threaded "
+                                   f"process per core on independent copies, files on /dev/shm)",
                          "dexqv_gbs": U / (sum(x['t_enc'] for x in times) / len(times)) / GB,
-                         "undexqv_gbs": U / (sum(x['t_dec'] for x in times) / len(times)) / GB},
+                         "undexqv_gbs": U / (sum(x['t_dec'] for x in times) / len(times)) / GB,
+                         "host_cores_available": os.cpu_count()},
         "e2e": {"value": val, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -163,8 +174,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--size-gb", type=float, default=2.0, help="uncompressed .quiva GB per GPU")
-    ap.add_argument("--ref-sample-mb", type=float, default=64.0)
-    ap.add_argument("--cpu-sample-mb", type=float, default=128.0)
+    ap.add_argument("--ref-sample-mb", type=float, default=64.0, help="per process")
+    ap.add_argument("--ref-cores", type=int, default=0, help="reference arm processes (0 = all cores)")
+    ap.add_argument("--cpu-sample-mb", type=float, default=64.0, help="per process")
     ap.add_argument("--no-extras", action="store_true", help="skip the dexta/undexta side numbers")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
@@ -339,20 +351,31 @@ def main():
 
     enc_ms, _ = timed(step_device)
     dec_known_ms, _ = timed(decode_known)
-    dec_disc_ms, _ = timed(decode_discover, reps=2)
+    decode_discover(); decode_discover()        # the scratch arena settles at this path's size
+    dec_disc_ms, _ = timed(decode_discover)
+    decode_known()
     C = state["img_len"]
 
     # ---- roofline of the dominant kernel (CUDA events inside the library, timed region) -------
     # algorithmic bytes per launch: hist 0.8U ; size U ; emit U+C ; decode C+U ; walk C
-    lines_bytes = U - (U - 5 * (npos + nent))          # the 5 QV lines incl. newlines
-    algo = {"k_qv_hist": 0.8 * lines_bytes, "k_qv_size": lines_bytes, "k_qv_emit": lines_bytes + C,
-            "k_qv_decode": C + U, "k_qv_walk": C, "k_pred_count": U, "k_pred_write": U}
+    lines_bytes = 5 * (npos + nent)                    # the 5 QV lines incl. newlines
+    algo = {"k_qv_hist_plain": 0.4 * lines_bytes, "k_qv_hist_run": 0.4 * lines_bytes,
+            "k_qv_size": lines_bytes, "k_qv_emit": lines_bytes + C,
+            "k_qv_decode5": C + U, "k_qv_decode5_spec": C + lines_bytes, "k_qv_assemble": 2 * U,
+            "k_pred_single": U}
     top = max(prof.items(), key=lambda kv: kv[1][1]) if prof else ("none", (1, 1.0))
     tname, (tcalls, ttot) = top
     tavg = ttot / max(tcalls, 1)
     achieved = algo.get(tname, U) / (tavg * 1e-3) / GB
+    traffic = None                              # dram bytes per launch from the committed ncu capture
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        if tname in tr["kernels"]:
+            traffic = tr["kernels"][tname]["dram_bytes_per_text_byte"] * U
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": tname, "achieved": achieved, "peak": hbm_peak,
-                "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
+                "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic,
                 "peak_source": peak_src, "avg_ms": tavg,
                 "share_of_step": ttot / max(sum(v[1] for v in prof.values()), 1e-9)}
     path = {"dexqv": {"algorithmic_bytes": 1.8 * U + C, "ms": enc_ms,
@@ -445,12 +468,17 @@ def main():
     # ---- CPU baseline beside it (rank 0, N=1 only) ---------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        r = cpu_reference_sample(args.cpu_sample_mb, seed=1)
+        r1 = cpu_reference_sample(args.cpu_sample_mb, seed=1, nproc=1)
+        r = cpu_reference_sample(args.cpu_sample_mb, seed=1, nproc=os.cpu_count() or 1)
         t = r["t_enc"] + r["t_dec"]
-        cpu = {"value": 2 * r["bytes"] / t / GB, "unit": "GB/s", "cores": 1, "kind": r["kind"],
-               "sample": f"{r['bytes']/1e6:.0f} MB synthetic .quiva (same generator family), dexqv "
-                         f"then undexqv, reference binaries single-threaded on /dev/shm",
+        cpu = {"value": 2 * r["bytes"] / t / GB, "unit": "GB/s", "cores": r["cores"], "kind": r["kind"],
+               "sample": f"{r['cores']} x {r['sample_bytes']/1e6:.0f} MB synthetic .quiva (same generator "
+                         f"family), dexqv then undexqv, reference binaries, one single-threaded process per "
+                         f"core on independent copies, /dev/shm",
                "dexqv_gbs": r["bytes"] / r["t_enc"] / GB, "undexqv_gbs": r["bytes"] / r["t_dec"] / GB,
+               "one_core": {"value": 2 * r1["bytes"] / (r1["t_enc"] + r1["t_dec"]) / GB,
+                            "dexqv_gbs": r1["bytes"] / r1["t_enc"] / GB,
+                            "undexqv_gbs": r1["bytes"] / r1["t_dec"] / GB},
                "host_cores_available": os.cpu_count()}
 
     if rank == 0:

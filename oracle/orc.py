@@ -193,3 +193,31 @@ def ref_tool(tool: str, data: bytes, *flags: str, tmpdir: str | None = None,
             return f.read(), dt
     finally:
         shutil.rmtree(d, ignore_errors=True)
+
+
+def ref_tool_parallel(tool: str, data: bytes, nproc: int, *flags: str):
+    """`nproc` independent runs of one reference tool at the same time, each on its own copy of
+    `data` (the reference is single threaded; independent files are how it uses more cores).
+    Returns (output of the first run, wall seconds until the last one finished)."""
+    import time
+    src, dst = _EXT[tool]
+    base = "/dev/shm" if os.path.isdir("/dev/shm") else None
+    d = tempfile.mkdtemp(prefix="dxrefp_", dir=base)
+    try:
+        for k in range(nproc):
+            with open(os.path.join(d, f"x{k}" + src), "wb") as f:
+                f.write(data)
+        t0 = time.perf_counter()
+        procs = [subprocess.Popen([os.path.join(REF_DIR, tool), "-k", *flags,
+                                   os.path.join(d, f"x{k}" + src)],
+                                  stdout=subprocess.DEVNULL, stderr=subprocess.PIPE)
+                 for k in range(nproc)]
+        for p in procs:
+            _, err = p.communicate()
+            if p.returncode != 0:
+                raise RuntimeError(f"{tool} failed rc={p.returncode}: {err.decode()[:500]}")
+        dt = time.perf_counter() - t0
+        with open(os.path.join(d, "x0" + dst), "rb") as f:
+            return f.read(), dt
+    finally:
+        shutil.rmtree(d, ignore_errors=True)

@@ -1,0 +1,138 @@
+"""The alternative routes through the library must all give the reference's bytes: the general
+(host-planned) decoders behind the device-planned fast paths, the exact two-pass index behind the
+single-pass one, the byte-serial 2-bit kernels behind the vectorised ones, the older decoder
+generations, and inputs built to defeat the fast paths' assumptions (line lattice, candidate
+filter).  Bit-exact against the oracle."""
+import numpy as np
+import pytest
+
+import dextractor_b200 as dx
+from dextractor_b200 import synth
+from tests import cases
+
+pytestmark = pytest.mark.gpu
+
+QUIVA = dict(cases.quiva_cases())
+FASTA = dict(cases.fasta_cases())
+ARROW = dict(cases.arrow_cases())
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = dx.Context(0)
+    yield c
+    c.close()
+
+
+ROUTES = [
+    {},                                                  # the default routes
+    {"DEXB200_NO_FAST": "1"},                            # host-planned decoders
+    {"DEXB200_NO_FAST": "1", "DEXB200_NO_SPEC": "1"},    # ... with a separate walk of all candidates
+    {"DEXB200_EXACT_INDEX": "1"},                        # two-pass position index
+    {"DEXB200_EXACT_PACK": "1"},                         # counted symbol lengths, byte-serial packer
+    {"DEXB200_DECODER": "v1"},                           # sequential decode kernels
+    {"DEXB200_DECODER": "v4"},                           # CTA-per-entry parallel decoder
+]
+
+
+@pytest.mark.parametrize("env", ROUTES, ids=lambda e: "+".join(sorted(e)) or "default")
+def test_every_route_gives_the_same_bytes(ctx, orc, monkeypatch, env):
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    for name in ("lognormal_40", "edge_lengths", "long_runs", "big_well_gaps", "no_n_tags"):
+        text = QUIVA[name]
+        enc = orc.dexqv(text)
+        assert ctx.dexqv(text) == enc, name
+        assert ctx.undexqv(enc) == orc.undexqv(enc), name
+    for name in ("edge_lengths", "ragged", "width_1", "big_well_gaps", "upper_and_n"):
+        text = FASTA[name]
+        enc = orc.dexta(text)
+        assert ctx.dexta(text) == enc, name
+        for width in (80, 16, 15, 7):
+            assert ctx.undexta(enc, width=width) == orc.undexta(enc, width=width), (name, width)
+    for name in ("edge_lengths", "odd_symbols"):
+        text = ARROW[name]
+        enc = orc.dexta(text, arrow=True)
+        assert ctx.dexta(text, kind=dx.ARROW) == enc, name
+        assert ctx.undexta(enc, kind=dx.ARROW) == orc.undexta(enc, arrow=True), name
+
+
+def test_fasta_lines_off_the_lattice(ctx, orc):
+    """Entries whose line layout contradicts the width of their first line: the packer's symbol
+    count check must send the file down the exact path."""
+    rng = np.random.default_rng(5)
+    acgt = np.frombuffer(b"acgt", dtype=np.uint8)
+    parts = []
+    for i in range(40):
+        L = int(rng.integers(200, 3000))
+        seq = acgt[rng.integers(0, 4, size=L)].tobytes()
+        parts.append(f">mv/{i * 3}/0_{L} RQ=0.8{i % 10}1\n".encode())
+        if i % 5 == 2:                                   # first line short, the rest long
+            parts.append(seq[:20] + b"\n" + seq[20:] + b"\n")
+        elif i % 5 == 4:                                 # varying widths, same total as a lattice
+            cut = sorted(rng.integers(1, L, size=6))
+            prev = 0
+            for c in cut:
+                parts.append(seq[prev:c] + b"\n")
+                prev = c
+            parts.append(seq[prev:] + b"\n")
+        else:
+            parts.append(synth._wrap(np.frombuffer(seq, dtype=np.uint8), 70))
+    text = b"".join(parts)
+    want = orc.dexta(text)
+    assert ctx.dexta(text) == want
+
+
+def _zero_rich_quiva(seed, n, L):
+    """ins and mrg lines dominated by one value each: the streams are full of zero bytes, which is
+    what the entry-candidate filter keys on (clusters of false candidates)."""
+    def hook(i, s):
+        rng = np.random.default_rng(seed * 1000 + i)
+        s[2][:] = np.where(rng.random(len(s[2])) < 0.995, 40, s[2])
+        s[3][:] = np.where(rng.random(len(s[3])) < 0.995, 45, s[3])
+    return synth.make_quiva(seed, [L] * n, stream_hook=hook)
+
+
+def test_undexqv_with_many_false_candidates(ctx, orc):
+    text = _zero_rich_quiva(21, 60, 6000)
+    enc = orc.dexqv(text)
+    assert ctx.dexqv(text) == enc
+    assert ctx.undexqv(enc) == orc.undexqv(enc)
+
+
+def test_undexqv_mid_size_and_long_entries(ctx, orc):
+    """~40 MB with entries from 500 to 60000 positions plus a few very long ones (the decoder takes
+    long entries first); decode with discovered entries, with the index, and the size query."""
+    import torch
+    rng = np.random.default_rng(31)
+    lengths = list(synth.lengths_for_bytes(rng, 36_000_000, 5.0)) + [140000, 300, 200000, 70000]
+    text = synth.make_quiva(31, lengths)
+    enc = orc.dexqv(text)
+    assert ctx.dexqv(text) == enc
+    assert ctx.undexqv(enc) == text
+    img = torch.frombuffer(bytearray(enc), dtype=torch.uint8).cuda()
+    back = torch.empty(len(text) + 64, dtype=torch.uint8, device="cuda")
+    offs = orc.dexqv_offsets(enc, len(lengths))
+    m = ctx.undexqv_dev(img.data_ptr(), len(enc), False, back.data_ptr(), back.numel(), entry_off=offs)
+    assert m == len(text) and back[:m].cpu().numpy().tobytes() == text
+    assert ctx.undexqv_size_dev(img.data_ptr(), len(enc)) == len(text)
+
+
+def test_dexta_mid_size_round_trip(ctx, orc):
+    rng = np.random.default_rng(41)
+    lengths = synth.lengths_for_bytes(rng, 30_000_000, 1.0125)
+    for kind, make, arrow in ((dx.FASTA, synth.make_fasta, False), (dx.ARROW, synth.make_arrow, True)):
+        text = make(41, lengths)
+        enc = orc.dexta(text, arrow=arrow)
+        assert ctx.dexta(text, kind=kind) == enc
+        assert ctx.undexta(enc, kind=kind) == orc.undexta(enc, arrow=arrow)
+        assert ctx.undexta(enc, kind=kind, width=60, upper=True) == \
+            orc.undexta(enc, arrow=arrow, width=60, upper=True)
+
+
+def test_output_buffer_too_small_is_an_error(ctx, orc):
+    text = QUIVA["lognormal_40"]
+    enc = orc.dexqv(text)
+    with pytest.raises(dx.DexError) as e:
+        ctx.undexqv(enc, cap=len(text) // 2)
+    assert e.value.code == -2                            # DX_E_CAP
