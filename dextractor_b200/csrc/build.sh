@@ -24,3 +24,8 @@ done
 wait
 $NVCC -shared -gencode arch=compute_100a,code=sm_100a -o $OUT $objs -lcudart_static -lpthread -ldl -lrt
 echo "built $OUT"
+# libdexcompat.so: the reference's QV.h / DB.h symbols over libdexb200.so
+if [ ! -f ../libdexcompat.so ] || [ dx_compat.cu -nt ../libdexcompat.so ] || [ ../../include/dexb200.h -nt ../libdexcompat.so ]; then
+  $NVCC $FLAGS -shared -o ../libdexcompat.so dx_compat.cu -L.. -ldexb200 -Xlinker -rpath -Xlinker '$ORIGIN' -lcudart_static -lpthread -ldl -lrt
+  echo "built ../libdexcompat.so"
+fi

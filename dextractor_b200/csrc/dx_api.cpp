@@ -218,6 +218,7 @@ extern "C" void dx_close(dx_ctx *ctx)
   if (ctx->io_in)    cudaFree(ctx->io_in);
   if (ctx->io_out)   cudaFree(ctx->io_out);
   if (ctx->qv_store) cudaFree(ctx->qv_store);
+  if (ctx->last_index) delete (std::vector<dx_index_row> *) ctx->last_index;
   if (ctx->hpin)     cudaFreeHost(ctx->hpin);
   while (ctx->hpin_extra)
     { DxPinExtra *e = (DxPinExtra *) ctx->hpin_extra; ctx->hpin_extra = e->next; cudaFreeHost(e->p); free(e); }
@@ -232,6 +233,22 @@ extern "C" void dx_close(dx_ctx *ctx)
 extern "C" const char *dx_strerror(const dx_ctx *ctx) { return ctx ? ctx->err : "no context"; }
 extern "C" int64_t     dx_error_line(const dx_ctx *ctx) { return ctx ? ctx->err_line : 0; }
 extern "C" void       *dx_stream(dx_ctx *ctx) { return ctx ? (void *) ctx->stream : NULL; }
+
+extern "C" int dx_keep_index(dx_ctx *ctx, int keep)
+{ if (ctx == NULL) return DX_E_ARG;
+  ctx->keep_index = keep;
+  if (ctx->last_index == NULL) ctx->last_index = new std::vector<dx_index_row>();
+  return DX_OK;
+}
+
+extern "C" int dx_last_index(dx_ctx *ctx, dx_index_row *rows, int64_t max, int64_t *count)
+{ if (ctx == NULL || count == NULL) return DX_E_ARG;
+  std::vector<dx_index_row> *v = (std::vector<dx_index_row> *) ctx->last_index;
+  *count = v ? (int64_t) v->size() : 0;
+  if (v && rows)
+    for (int64_t i = 0; i < *count && i < max; i++) rows[i] = (*v)[(size_t) i];
+  return DX_OK;
+}
 
 extern "C" int dx_sync(dx_ctx *ctx)
 { DX_CUDA(ctx,cudaStreamSynchronize(ctx->stream));
@@ -1204,6 +1221,7 @@ struct QvPlan
   uint8_t     *d_tmp;         // the scratch image (lines only)
   size_t       tmp_n;
   std::vector<int64_t> src;   // per entry: offset of its lines in d_tmp, -1 = not decoded yet
+  std::vector<int64_t> ix_fs, ix_end;   // per entry: first stream byte, first byte after the entry
 };
 
 // ticket order for the one-warp-per-entry decoder: the long entries first (they would otherwise be
@@ -1370,6 +1388,9 @@ static int plan_undexqv(dx_ctx *ctx, const uint8_t *d_in, size_t n, const int64_
           for (size_t i = 0; i < N; i++)
             if (stat[i]) return dx_fail(ctx,DX_E_TRUNC,"Could not read more bits (Decode), entry %zu",i+1);
         }
+      plan.ix_fs = fs;
+      plan.ix_end.resize(N);
+      for (size_t i = 0; i < N; i++) plan.ix_end[i] = (i + 1 < N) ? h_entry_off[i+1] : (int64_t) n;
       int32_t well = well_in;
       hdrs.resize(N);
       for (size_t i = 0; i < N; i++)
@@ -1512,6 +1533,9 @@ static int plan_undexqv(dx_ctx *ctx, const uint8_t *d_in, size_t n, const int64_
           st[i] = c.q + 12;
           rl[i] = hdrs[i].end - hdrs[i].beg;
         }
+      plan.ix_fs = st;
+      plan.ix_end.resize(M);
+      for (size_t i = 0; i < M; i++) plan.ix_end[i] = chain[i].end;
       if (need_streams)
         { plan.d_start = (int64_t *) dx_arena_get(ctx,M*8);
           plan.d_rlen  = (int32_t *) dx_arena_get(ctx,M*4);
@@ -1639,6 +1663,17 @@ static int undexqv_fast(dx_ctx *ctx, const uint8_t *d_in, size_t n, int upper, u
       ph.mark("decode");
       ph.report("undexqv (index known)");
       if (h_tail->flag) return dx_fail(ctx,DX_E_TRUNC,"Could not read more bits (Decode)");
+      if (ctx->keep_index)
+        { std::vector<dx_index_row> &ix = *(std::vector<dx_index_row> *) ctx->last_index;
+          std::vector<QvDecEntry> he; std::vector<int64_t> hfs;
+          if ((rc = download(ctx,d_ent,N,he)) != DX_OK) return rc;
+          if ((rc = download(ctx,pa.fs,N,hfs)) != DX_OK) return rc;
+          ix.resize(N);
+          for (size_t i = 0; i < N; i++)
+            { ix[i].stream_off = hfs[i]; ix[i].end_off = (i + 1 < N) ? h_entry_off[i+1] : (int64_t) n;
+              ix[i].text_off = he[i].text_off; ix[i].rlen = he[i].end - he[i].beg; ix[i].well = he[i].well;
+            }
+        }
       *out_len = (size_t) h_tail->total;
       *handled = true;
       return DX_OK;
@@ -1751,6 +1786,17 @@ static int undexqv_fast(dx_ctx *ctx, const uint8_t *d_in, size_t n, int upper, u
   DX_CUDA(ctx,cudaStreamSynchronize(ctx->stream));
   ph.mark("assemble");
   ph.report("undexqv (entries discovered)");
+  if (ctx->keep_index)
+    { std::vector<dx_index_row> &ix = *(std::vector<dx_index_row> *) ctx->last_index;
+      std::vector<QvDecEntry> he;
+      if ((rc = download(ctx,d_ent,M,he)) != DX_OK) return rc;
+      ix.resize(M);
+      for (size_t m = 0; m < M; m++)
+        { const size_t c = (size_t) h_cand[m];
+          ix[m].stream_off = h_q[c] + 12; ix[m].end_off = h_soff[6*c + 5];
+          ix[m].text_off = he[m].text_off; ix[m].rlen = he[m].end - he[m].beg; ix[m].well = he[m].well;
+        }
+    }
   *out_len = (size_t) h_tail->total;
   *handled = true;
   return DX_OK;
@@ -1771,6 +1817,7 @@ extern "C" int dx_undexqv_dev(dx_ctx *ctx, const uint8_t *d_in, size_t n, int up
     if (handled) return DX_OK;
     dx_arena_reset(ctx);
   }
+  if (ctx->last_index) ((std::vector<dx_index_row> *) ctx->last_index)->clear();
   QvPlan plan;
   if ((rc = plan_undexqv(ctx,d_in,n,h_entry_off,nentries,well_in,true,upper,plan)) != DX_OK) return rc;
   if (plan.text_len > cap)
@@ -1828,6 +1875,15 @@ extern "C" int dx_undexqv_dev(dx_ctx *ctx, const uint8_t *d_in, size_t n, int up
   DX_CUDA(ctx,cudaMemcpyAsync(&stat,d_stat,4,cudaMemcpyDeviceToHost,ctx->stream));
   DX_CUDA(ctx,cudaStreamSynchronize(ctx->stream));
   if (stat) return dx_fail(ctx,DX_E_TRUNC,"Could not read more bits (Decode)");
+  if (ctx->keep_index && ctx->last_index && plan.ix_fs.size() == N)
+    { std::vector<dx_index_row> &ix = *(std::vector<dx_index_row> *) ctx->last_index;
+      ix.resize(N);
+      for (size_t i = 0; i < N; i++)
+        { ix[i].stream_off = plan.ix_fs[i]; ix[i].end_off = plan.ix_end[i];
+          ix[i].text_off = plan.ent[i].text_off; ix[i].rlen = plan.ent[i].end - plan.ent[i].beg;
+          ix[i].well = plan.ent[i].well;
+        }
+    }
   *out_len = plan.text_len;
   return DX_OK;
 }

@@ -1,0 +1,493 @@
+// dx_compat.cu -- libdexcompat.so: the reference's own QV.h / DB.h entry points over libdexb200.so.
+//
+// the reference tools call the codec one read at a time through FILE* streams
+// (QVcoding_Scan, Create_QVcoding, Write_QVcoding, Compress_Next_QVentry, Read_QVcoding,
+// Uncompress_Next_QVentry of QV.h:48-97; Compress_Read, Uncompress_Read, Number_Read, Lower_Read,
+// Upper_Read, Number_Arrow, Letter_Arrow, Change_Read of DB.h:255-267; the Malloc/Fopen/PathTo/Root/
+// Catenate helpers of DB.h:235-247).  This file exports exactly those C symbols, so that the
+// reference's mains (dexqv.c, undexqv.c, dexta.c, ...) compile against their own headers and link
+// here instead of against DB.c + QV.c.  All codec work runs on the GPU through the batch ABI of
+// include/dexb200.h: the per-entry calls are served by "capture at scan, replay at compress" --
+// the reference's call pattern (scan all entries, create the coding, compress the same entries in the
+// same order; read the coding, then decode entries) is what makes that exact.  Nothing here
+// encodes or decodes on the host; line reading and path handling are host I/O, as in the reference.
+//
+// One process-wide context on device 0, not thread safe -- like the statics of QV.c:35-38, 733-736,
+// 860-862 (SURVEY 8b "Threading").
+
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <strings.h>
+#include <stdint.h>
+#include <limits.h>
+#include <vector>
+#include <algorithm>
+#include <cuda_runtime.h>
+#include "dexb200.h"
+
+typedef long long int64;
+
+// QV.h:31-42 (layout is part of the interface: callers read delChar/subChar/flip and own prefix)
+typedef struct
+  { void *delScheme, *insScheme, *mrgScheme, *subScheme, *dRunScheme, *sRunScheme;
+    int   delChar, subChar, flip;
+    char *prefix;
+  } QVcoding;
+
+extern "C" { extern char *Prog_Name; }
+
+namespace {
+
+// ---- tiny kernels for the per-read DB.h calls ---------------------------------------------------------
+__global__ void k_map(uint8_t *s, int n, const uint8_t *table)
+{ const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) s[i] = table[s[i]];
+}
+
+__global__ void k_pack_numeric(const uint8_t *s, int len, uint8_t *out)          // DB.c:319-338
+{ const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (4*j >= len) return;
+  uint32_t v = 0;
+  for (int k = 0; k < 4; k++)
+    v = (v << 2) | ((4*j + k < len) ? (s[4*j + k] & 3u) : 0u);
+  out[j] = (uint8_t) v;
+}
+
+__global__ void k_unpack_numeric(const uint8_t *in, int clen, uint8_t *out)        // DB.c:342-363
+{ const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= clen) return;
+  const uint32_t b = in[j];
+  out[4*j] = (uint8_t) (b >> 6); out[4*j+1] = (uint8_t) ((b >> 4) & 3u);
+  out[4*j+2] = (uint8_t) ((b >> 2) & 3u); out[4*j+3] = (uint8_t) (b & 3u);
+}
+
+struct Shim
+{ dx_ctx *ctx = NULL;
+  uint8_t *d_a = NULL, *d_b = NULL, *d_tab = NULL; size_t cap_a = 0, cap_b = 0;
+  // encoder side
+  std::vector<uint8_t> text;            // captured .quiva text (QVcoding_Scan / QVcoding_Scan1)
+  uint8_t *d_text = NULL; size_t d_text_cap = 0;
+  bool scanned = false, encoded = false;
+  int64_t scan1_entries = 0;
+  dx_qv_stats stats;
+  std::vector<uint8_t> image;           // all entries, encoded
+  std::vector<int64_t> eoff;
+  int64_t next = 0;
+  // decoder side
+  std::vector<uint8_t> dimg;            // key + coding header + entries
+  int64_t dpos0 = 0;                    // file offset of dimg[2]
+  bool decoded = false;
+  std::vector<uint8_t> dtext;
+  std::vector<dx_index_row> index;
+  // line reader (QV.c:733-798)
+  char *line = NULL; int rmax = 0; int nline = 0;
+};
+Shim S;
+
+void fatal(const char *what)
+{ fprintf(stderr,"%s: %s%s%s\n",Prog_Name ? Prog_Name : "dexcompat",what,S.ctx ? ": " : "",
+          S.ctx ? dx_strerror(S.ctx) : "");
+  exit (1);
+}
+
+dx_ctx *gpu()
+{ if (S.ctx == NULL && dx_open(0,&S.ctx) != DX_OK)
+    { S.ctx = NULL; fatal("no usable CUDA device (there is no CPU fallback)"); }
+  return S.ctx;
+}
+
+void need(uint8_t **p, size_t *cap, size_t n)
+{ if (*cap >= n + 64) return;
+  if (*p) dx_device_free(gpu(),*p);
+  *cap = n + n/2 + 4096;
+  *p = (uint8_t *) dx_device_alloc(gpu(),*cap);
+  if (*p == NULL) fatal("device allocation failed");
+}
+
+// in-place byte map of s[0..n) on the GPU
+void map_bytes(char *s, int n, const uint8_t table[256])
+{ if (n <= 0) return;
+  dx_ctx *c = gpu();
+  need(&S.d_a,&S.cap_a,(size_t) n);
+  if (S.d_tab == NULL) S.d_tab = (uint8_t *) dx_device_alloc(c,256);
+  cudaStream_t st = (cudaStream_t) dx_stream(c);
+  dx_h2d(c,S.d_tab,table,256);
+  dx_h2d(c,S.d_a,s,(size_t) n);
+  k_map<<<(n + 255)/256,256,0,st>>>(S.d_a,n,S.d_tab);
+  dx_d2h(c,s,S.d_a,(size_t) n);
+  if (dx_sync(c) != DX_OK) fatal("GPU error");
+}
+
+struct Tables
+{ uint8_t number[256], lower[256], upper[256], narrow[256], larrow[256], change[256];
+  Tables()
+  { for (int i = 0; i < 256; i++)
+      { number[i] = 0; lower[i] = upper[i] = larrow[i] = (uint8_t) i; narrow[i] = 3; change[i] = (uint8_t) i; }
+    number['c'] = number['C'] = 1; number['g'] = number['G'] = 2; number['t'] = number['T'] = 3;   // DB.c:394-411
+    narrow['1'] = 0; narrow['2'] = 1; narrow['3'] = 2; narrow['G'] = 2; narrow['4'] = 3;           // DB.c:419-436
+    for (int i = 0; i < 4; i++)
+      { lower[i] = (uint8_t) "acgt"[i]; upper[i] = (uint8_t) "ACGT"[i]; larrow[i] = (uint8_t) "1234"[i]; }
+    for (int i = 'a'; i <= 'z'; i++) { change[i] = (uint8_t) (i - 32); change[i - 32] = (uint8_t) i; }
+  }
+} T;
+
+dx_qv_coding *dxc(QVcoding *c) { return (dx_qv_coding *) c->delScheme; }
+
+void publish(QVcoding *out, const dx_qv_coding *cd)
+{ dx_qv_coding *copy = (dx_qv_coding *) malloc(sizeof(dx_qv_coding));
+  if (copy == NULL) fatal("Out of memory (coding)");
+  *copy = *cd;
+  out->delScheme = copy;                                  // the other five only signal "present"
+  out->insScheme = out->mrgScheme = out->subScheme = copy;
+  out->dRunScheme = (cd->delchar >= 0) ? copy : NULL;
+  out->sRunScheme = (cd->subchar >= 0) ? copy : NULL;
+  out->delChar = cd->delchar; out->subChar = cd->subchar; out->flip = cd->flip;
+  out->prefix = NULL;
+}
+
+void upload_text()
+{ dx_ctx *c = gpu();
+  need(&S.d_text,&S.d_text_cap,S.text.size());
+  if (!S.text.empty() && dx_h2d(c,S.d_text,S.text.data(),S.text.size()) != DX_OK) fatal("copy to the device failed");
+  dx_sync(c);
+}
+
+void run_scan()
+{ upload_text();
+  if (dx_qv_scan_dev(gpu(),S.d_text,S.text.size(),NULL,&S.stats) != DX_OK) fatal("QVcoding_Scan");
+  S.scanned = true; S.encoded = false; S.next = 0;
+}
+
+void run_encode(QVcoding *coding, int lossy)
+{ dx_ctx *c = gpu();
+  const size_t cap = 3*S.text.size() + 200000;
+  need(&S.d_b,&S.cap_b,cap);
+  size_t m = 0; int32_t lastw = 0;
+  S.eoff.assign((size_t) S.stats.nentries + 1,0);
+  if (dx_qv_encode_dev(c,S.d_text,S.text.size(),dxc(coding),lossy,0,S.d_b,cap,&m,&lastw,S.eoff.data(),
+                       S.stats.nentries) != DX_OK) fatal("Compress_Next_QVentry");
+  S.image.resize(m);
+  if (m && dx_d2h(c,S.image.data(),S.d_b,m) != DX_OK) fatal("copy from the device failed");
+  dx_sync(c);
+  S.encoded = true; S.next = 0;
+}
+
+// write the streams of captured entry k (its well-delta bytes and beg/end/qv are the caller's job)
+void emit_entry(FILE *output)
+{ if (S.next >= (int64_t) S.eoff.size() - 1) fatal("Compress_Next_QVentry called more often than entries were scanned");
+  const uint8_t *p = S.image.data() + S.eoff[(size_t) S.next], *e = S.image.data() + S.eoff[(size_t) S.next + 1];
+  while (p < e && *p == 0xff) p++;
+  p += 13;
+  if (p > e) fatal("internal error: short entry");
+  if (e > p) fwrite(p,1,(size_t) (e - p),output);
+  S.next++;
+}
+
+}  // namespace
+
+extern "C" {
+
+char *Prog_Name = NULL;
+
+// ---- DB.h:235-247 utilities (host, not on the hot path) -------------------------------------------------
+void *Malloc(int64 size, char *mesg)
+{ void *p = malloc((size_t) size);
+  if (p == NULL) fprintf(stderr,mesg ? "%s: Out of memory (%s)\n" : "%s: Out of memory\n",Prog_Name,mesg);
+  return p;
+}
+
+void *Realloc(void *p, int64 size, char *mesg)
+{ p = realloc(p,(size_t) (size > 0 ? size : 1));
+  if (p == NULL) fprintf(stderr,mesg ? "%s: Out of memory (%s)\n" : "%s: Out of memory\n",Prog_Name,mesg);
+  return p;
+}
+
+char *Strdup(char *string, char *mesg)
+{ if (string == NULL) return NULL;
+  char *s = strdup(string);
+  if (s == NULL) fprintf(stderr,mesg ? "%s: Out of memory (%s)\n" : "%s: Out of memory\n",Prog_Name,mesg);
+  return s;
+}
+
+FILE *Fopen(char *path, char *mode)
+{ if (path == NULL || mode == NULL) return NULL;
+  FILE *f = fopen(path,mode);
+  if (f == NULL) fprintf(stderr,"%s: Cannot open %s for '%s'\n",Prog_Name,path,mode);
+  return f;
+}
+
+char *PathTo(char *path)
+{ if (path == NULL) return NULL;
+  const char *sl = strrchr(path,'/');
+  if (sl == NULL) return Strdup((char *) ".",(char *) "Allocating default path");
+  char *out = (char *) Malloc((int64) (sl - path) + 1,(char *) "Extracting path from");
+  if (out != NULL) { memcpy(out,path,(size_t) (sl - path)); out[sl - path] = '\0'; }
+  return out;
+}
+
+char *Root(char *path, char *suffix)
+{ if (path == NULL) return NULL;
+  const char *base = strrchr(path,'/');
+  base = base ? base + 1 : path;
+  size_t keep = strlen(base);
+  if (suffix == NULL)
+    { const char *dot = strchr(base,'.');
+      if (dot) keep = (size_t) (dot - base);
+    }
+  else
+    { const size_t ls = strlen(suffix);
+      if (keep > ls && strcasecmp(base + keep - ls,suffix) == 0) keep -= ls;
+    }
+  char *out = (char *) Malloc((int64) keep + 1,(char *) "Extracting root from");
+  if (out != NULL) { memcpy(out,base,keep); out[keep] = '\0'; }
+  return out;
+}
+
+char *Catenate(char *path, char *sep, char *root, char *suffix)
+{ static std::vector<char> buf;
+  if (path == NULL || sep == NULL || root == NULL || suffix == NULL) return NULL;
+  buf.resize(strlen(path) + strlen(sep) + strlen(root) + strlen(suffix) + 1);
+  sprintf(buf.data(),"%s%s%s%s",path,sep,root,suffix);
+  return buf.data();
+}
+
+char *Numbered_Suffix(char *left, int num, char *right)
+{ static std::vector<char> buf;
+  if (left == NULL || right == NULL) return NULL;
+  buf.resize(strlen(left) + strlen(right) + 48);
+  sprintf(buf.data(),"%s%d%s",left,num,right);
+  return buf.data();
+}
+
+// ---- DB.h:255-267: the 2-bit codec and alphabet maps, one read at a time, on the GPU ---------------------
+void Number_Read(char *s)
+{ const int n = (int) strlen(s);
+  map_bytes(s,n,T.number);
+  s[n] = 4;
+}
+
+void Number_Arrow(char *s)
+{ const int n = (int) strlen(s);
+  map_bytes(s,n,T.narrow);
+  s[n] = 4;
+}
+
+static void letters(char *s, const uint8_t *table)
+{ int n = 0;
+  while (s[n] != 4) n++;
+  map_bytes(s,n,table);
+  s[n] = '\0';
+}
+
+void Lower_Read(char *s)   { letters(s,T.lower); }
+void Upper_Read(char *s)   { letters(s,T.upper); }
+void Letter_Arrow(char *s) { letters(s,T.larrow); }
+void Change_Read(char *s)  { map_bytes(s,(int) strlen(s),T.change); }
+
+void Compress_Read(int len, char *s)
+{ if (len <= 0) { if (len == 0) s[0] = 0; return; }
+  dx_ctx *c = gpu();
+  const int clen = (len + 3) >> 2;
+  need(&S.d_a,&S.cap_a,(size_t) len); need(&S.d_b,&S.cap_b,(size_t) clen);
+  cudaStream_t st = (cudaStream_t) dx_stream(c);
+  dx_h2d(c,S.d_a,s,(size_t) len);
+  k_pack_numeric<<<(clen + 255)/256,256,0,st>>>(S.d_a,len,S.d_b);
+  dx_d2h(c,s,S.d_b,(size_t) clen);
+  if (dx_sync(c) != DX_OK) fatal("GPU error");
+  if (clen < len) s[len] = 0;                     // what DB.c:329-337 leaves behind
+}
+
+void Uncompress_Read(int len, char *s)
+{ const int clen = (len + 3) >> 2;
+  if (clen > 0)
+    { dx_ctx *c = gpu();
+      need(&S.d_a,&S.cap_a,(size_t) clen); need(&S.d_b,&S.cap_b,(size_t) 4*clen);
+      cudaStream_t st = (cudaStream_t) dx_stream(c);
+      dx_h2d(c,S.d_a,s,(size_t) clen);
+      k_unpack_numeric<<<(clen + 255)/256,256,0,st>>>(S.d_a,clen,S.d_b);
+      dx_d2h(c,s,S.d_b,(size_t) 4*clen);          // like DB.c:352-362 this may write up to 3 bytes past len
+      if (dx_sync(c) != DX_OK) fatal("GPU error");
+    }
+  s[len] = 4;
+}
+
+// ---- QV.h: line reader (host I/O, QV.c:733-798) --------------------------------------------------------------
+void Set_QV_Line(int line) { S.nline = line; }
+int  Get_QV_Line()         { return S.nline; }
+char *QVentry()            { return S.line; }
+
+int Read_Lines(FILE *input, int nlines)
+{ if (S.line == NULL)
+    { S.rmax = 50000;
+      S.line = (char *) malloc((size_t) 5*S.rmax);
+      if (S.line == NULL) { fprintf(stderr,"%s: Out of memory (Allocating QV entry read buffer)\n",Prog_Name); exit (1); }
+    }
+  int rlen = 0;
+  for (int i = 0; i < nlines; i++)
+    { char *dst = S.line + (size_t) i*S.rmax;
+      if (fgets(dst,S.rmax,input) == NULL)
+        { if (i == 0) return -1;
+          fprintf(stderr,"Line %d: incomplete last entry of .quiv file\n",S.nline);
+          return -2;
+        }
+      S.nline++;
+      int len = (int) strlen(dst);
+      while (len > 0 && dst[len-1] != '\n')       // longer than the buffer: grow all five slots and go on
+        { const int nmax = S.rmax + S.rmax/2 + 1000;
+          char *nl = (char *) malloc((size_t) 5*nmax);
+          if (nl == NULL) { fprintf(stderr,"%s: Out of memory (Reallocating QV entry read buffer)\n",Prog_Name); exit (1); }
+          for (int k = 0; k <= i; k++) strcpy(nl + (size_t) k*nmax,S.line + (size_t) k*S.rmax);
+          free(S.line); S.line = nl; S.rmax = nmax;
+          dst = S.line + (size_t) i*S.rmax;
+          if (fgets(dst + len,S.rmax - len,input) == NULL) break;
+          len += (int) strlen(dst + len);
+        }
+      if (len == 0 || dst[len-1] != '\n')
+        { fprintf(stderr,"Line %d: Last line does not end with a newline !\n",S.nline);
+          return -2;
+        }
+      len--;
+      if (i == 0) rlen = len;
+      else if (len != rlen)
+        { fprintf(stderr,"Line %d: Lines for an entry are not the same length\n",S.nline);
+          return -2;
+        }
+    }
+  return rlen;
+}
+
+// ---- QV.h: statistics, coding (GPU scan; tables on the host exactly like dx_qv_make_coding) ------------
+int QVcoding_Scan(FILE *input, int num, FILE *temp)
+{ // capture the entries (all that follow, or the next num) and scan them on the GPU
+  S.text.clear(); S.scan1_entries = 0;
+  const off_t at = ftello(input);
+  int64_t got = 0;
+  if (num == INT_MAX)
+    { char buf[1 << 16]; size_t k;
+      while ((k = fread(buf,1,sizeof(buf),input)) > 0) S.text.insert(S.text.end(),buf,buf + k);
+    }
+  else
+    { int c, lines = 0;
+      while (lines < 6*(int64_t) num && (c = fgetc(input)) != EOF)
+        { S.text.push_back((uint8_t) c);
+          if (c == '\n') lines++;
+        }
+    }
+  (void) at;
+  if (temp != NULL && !S.text.empty()) fwrite(S.text.data(),1,S.text.size(),temp);
+  run_scan();
+  got = S.stats.nentries;
+  S.nline += (int) (6*got);
+  return (int) got;
+}
+
+void QVcoding_Scan1(int rlen, char *del, char *tag, char *ins, char *mrg, char *sub)
+{ if (rlen == 0) { S.text.clear(); S.scan1_entries = 0; S.scanned = false; return; }    // QV.c:868-885
+  char hdr[64];
+  const int hl = sprintf(hdr,"@s/%lld/0_%d RQ=0.0\n",(long long) S.scan1_entries++,rlen);
+  S.text.insert(S.text.end(),hdr,hdr + hl);
+  const char *l[5] = { del, tag, ins, mrg, sub };
+  for (int k = 0; k < 5; k++)
+    { S.text.insert(S.text.end(),l[k],l[k] + rlen); S.text.push_back('\n'); }
+  S.scanned = false;
+}
+
+QVcoding *Create_QVcoding(int lossy)
+{ static QVcoding coding;
+  if (!S.scanned) run_scan();
+  dx_qv_coding cd;
+  if (dx_qv_make_coding(&S.stats,lossy,&cd) != DX_OK)
+    { fprintf(stderr,"%s: a QV stream has fewer than two distinct symbols\n",Prog_Name); exit (1); }
+  publish(&coding,&cd);
+  return &coding;
+}
+
+void Write_QVcoding(FILE *output, QVcoding *coding)
+{ std::vector<uint8_t> buf(20000 + (coding->prefix ? strlen(coding->prefix) : 0));
+  size_t n = 0;
+  if (dx_qv_write_coding(dxc(coding),coding->prefix ? coding->prefix : "",
+                         coding->prefix ? (int) strlen(coding->prefix) : 0,buf.data(),buf.size(),&n) != DX_OK)
+    fatal("Write_QVcoding");
+  fwrite(buf.data(),1,n,output);
+}
+
+QVcoding *Read_QVcoding(FILE *input)
+{ static QVcoding coding;
+  S.dpos0 = (int64_t) ftello(input);
+  S.dimg.assign(2,0);
+  S.dimg[0] = 0xaa; S.dimg[1] = 0x55;                      // the key the caller has already read
+  { char buf[1 << 16]; size_t k;
+    while ((k = fread(buf,1,sizeof(buf),input)) > 0) S.dimg.insert(S.dimg.end(),buf,buf + k);
+  }
+  dx_qv_coding cd;
+  std::vector<char> prefix(100001);
+  size_t used = 0;
+  if (dx_qv_read_coding(S.dimg.data() + 2,S.dimg.size() - 2,&cd,prefix.data(),(int) prefix.size(),&used) != DX_OK)
+    { fprintf(stderr,"%s: System error, read failed!\n",Prog_Name); exit (2); }
+  publish(&coding,&cd);
+  coding.prefix = strdup(prefix.data());
+  fseeko(input,(off_t) (S.dpos0 + (int64_t) used),SEEK_SET);
+  S.decoded = false;
+  return &coding;
+}
+
+void Free_QVcoding(QVcoding *coding)
+{ if (coding->delScheme) free(coding->delScheme);
+  coding->delScheme = coding->insScheme = coding->mrgScheme = coding->subScheme = NULL;
+  coding->dRunScheme = coding->sRunScheme = NULL;
+  free(coding->prefix);
+  coding->prefix = NULL;
+}
+
+// ---- QV.h: entries ------------------------------------------------------------------------------------------
+int Compress_Next_QVentry(FILE *input, FILE *output, QVcoding *coding, int lossy)
+{ const int rlen = Read_Lines(input,5);                      // keep the FILE* where the reference would
+  if (rlen < 0) { if (rlen == -1) fprintf(stderr,"Line %d: incomplete last entry of .quiv file\n",S.nline); exit (1); }
+  if (!S.encoded) run_encode(coding,lossy);
+  emit_entry(output);
+  return rlen;
+}
+
+void Compress_Next_QVentry1(int rlen, char *del, char *tag, char *ins, char *mrg, char *sub,
+                            FILE *output, QVcoding *coding, int lossy)
+{ (void) rlen; (void) del; (void) tag; (void) ins; (void) mrg; (void) sub;
+  if (!S.encoded) run_encode(coding,lossy);
+  emit_entry(output);
+}
+
+int Uncompress_Next_QVentry(FILE *input, char **entry, QVcoding *coding, int rlen)
+{ (void) coding;
+  if (!S.decoded)
+    { dx_ctx *c = gpu();
+      need(&S.d_a,&S.cap_a,S.dimg.size());
+      dx_h2d(c,S.d_a,S.dimg.data(),S.dimg.size());
+      size_t want = 0, m = 0;
+      if (dx_undexqv_size_dev(c,S.d_a,S.dimg.size(),&want) != DX_OK) fatal("Uncompress_Next_QVentry");
+      need(&S.d_b,&S.cap_b,want);
+      dx_keep_index(c,1);
+      if (dx_undexqv_dev(c,S.d_a,S.dimg.size(),0,S.d_b,S.cap_b,&m,NULL,0,0) != DX_OK) fatal("Uncompress_Next_QVentry");
+      int64_t cnt = 0;
+      dx_last_index(c,NULL,0,&cnt);
+      S.index.resize((size_t) cnt);
+      dx_last_index(c,S.index.data(),cnt,&cnt);
+      S.dtext.resize(m);
+      if (m) dx_d2h(c,S.dtext.data(),S.d_b,m);
+      dx_sync(c);
+      if (cnt == 0 && m > 0) fatal("no entry index for this file (general decode path)");
+      S.decoded = true;
+    }
+  // which entry starts at the current file position
+  const int64_t img = (int64_t) ftello(input) - S.dpos0 + 2;
+  size_t lo = 0, hi = S.index.size();
+  while (lo < hi) { const size_t mid = (lo + hi)/2; if (S.index[mid].stream_off < img) lo = mid + 1; else hi = mid; }
+  if (lo >= S.index.size() || S.index[lo].stream_off != img || S.index[lo].rlen != rlen)
+    { fprintf(stderr,"%s: System error, read failed!\n",Prog_Name); return 1; }
+  const dx_index_row &r = S.index[lo];
+  for (int e = 0; e < 5; e++)
+    memcpy(entry[e],S.dtext.data() + r.text_off + (int64_t) e*(rlen + 1),(size_t) rlen);
+  fseeko(input,(off_t) (S.dpos0 - 2 + r.end_off),SEEK_SET);
+  return 0;
+}
+
+}  // extern "C"

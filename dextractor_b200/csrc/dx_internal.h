@@ -93,6 +93,10 @@ struct dx_ctx
   uint8_t     *hpin;    size_t hpin_cap, hpin_top, hpin_want;
   void        *hpin_extra;     // one-off blocks handed out when hpin was too small
 
+  // entry index of the last dx_undexqv_dev call, kept on request (dx_keep_index)
+  int          keep_index;
+  void        *last_index;     // std::vector<dx_index_row>*
+
   // framing of the last scanned .quiva buffer (reused by the encode pass)
   const uint8_t *qv_text;
   size_t         qv_n;

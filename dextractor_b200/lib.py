@@ -24,7 +24,7 @@ SYMBOLS = [
     "dx_compress_reads_dev", "dx_uncompress_reads_dev",
     "dx_qv_scan_dev", "dx_qv_make_coding", "dx_qv_write_coding", "dx_qv_read_coding",
     "dx_qv_encode_dev", "dx_dexqv_dev", "dx_dexqv_host", "dx_undexqv_dev", "dx_undexqv_host",
-    "dx_undexqv_size_dev",
+    "dx_undexqv_size_dev", "dx_keep_index", "dx_last_index",
 ]
 
 
@@ -43,6 +43,11 @@ class Stats(C.Structure):
 class Carry(C.Structure):
     _fields_ = [("delchar", C.c_int32), ("subchar", C.c_int32), ("totchar", C.c_uint64),
                 ("sub", C.c_uint64 * 256)]
+
+
+class IndexRow(C.Structure):
+    _fields_ = [("stream_off", C.c_int64), ("end_off", C.c_int64), ("text_off", C.c_int64),
+                ("rlen", C.c_int32), ("well", C.c_int32)]
 
 
 class Scheme(C.Structure):
@@ -113,6 +118,8 @@ def load_library():
         "dx_undexqv_dev": (C.c_int, [vp, vp, sz, C.c_int, vp, sz, szp, vp, i64, i32]),
         "dx_undexqv_host": (C.c_int, [vp, vp, sz, C.c_int, vp, sz, szp]),
         "dx_undexqv_size_dev": (C.c_int, [vp, vp, sz, szp]),
+        "dx_keep_index": (C.c_int, [vp, C.c_int]),
+        "dx_last_index": (C.c_int, [vp, vp, i64, C.POINTER(i64)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -301,6 +308,17 @@ class Context:
             self._check(self.L.dx_undexqv_dev(self.h, d_in, n, int(upper), d_out, cap, C.byref(m),
                                               None, 0, well_in))
         return m.value
+
+    def keep_index(self, keep: bool = True):
+        self._check(self.L.dx_keep_index(self.h, int(keep)))
+
+    def last_index(self):
+        """rows (stream_off, end_off, text_off, rlen, well) of the last undexqv_dev call"""
+        cnt = C.c_int64(0)
+        self._check(self.L.dx_last_index(self.h, None, 0, C.byref(cnt)))
+        rows = (IndexRow * max(cnt.value, 1))()
+        self._check(self.L.dx_last_index(self.h, rows, cnt.value, C.byref(cnt)))
+        return [(r.stream_off, r.end_off, r.text_off, r.rlen, r.well) for r in rows[: cnt.value]]
 
     def undexqv_size_dev(self, d_in, n) -> int:
         m = C.c_size_t(0)

@@ -197,6 +197,19 @@ int dx_undexqv_host(dx_ctx *ctx, const uint8_t *h_in, size_t n, int upper,
 /* size of the .quiva text dx_undexqv_* would produce for this file */
 int dx_undexqv_size_dev(dx_ctx *ctx, const uint8_t *d_in, size_t n, size_t *out_len);
 
+/* Where the entries of the last dx_undexqv_dev call were: for callers that keep the reference's
+ * per-entry view of a file (the QV.h shim, a Dazzler .idx writer: DAZZ_READ.coff, dex2DB.c:617-621).
+ * Off by default; dx_keep_index(ctx,1) makes every following dx_undexqv_dev record one row per
+ * entry, dx_last_index copies up to max rows out and returns the number of entries in *count. */
+typedef struct
+  { int64_t stream_off;      /* first stream byte in the image (just after beg/end/qv)         */
+    int64_t end_off;         /* first byte after the entry                                      */
+    int64_t text_off;        /* first QV line of the entry in the decoded text                  */
+    int32_t rlen, well;
+  } dx_index_row;
+int dx_keep_index(dx_ctx *ctx, int keep);
+int dx_last_index(dx_ctx *ctx, dx_index_row *rows, int64_t max, int64_t *count);
+
 #ifdef __cplusplus
 }
 #endif
