@@ -219,25 +219,26 @@ def main():
     back = torch.empty(U + 4096, dtype=torch.uint8, device=dev)
     state = {}
 
-    def allreduce_stats(st):
-        """the only inter-GPU exchange of the path: 6x256 histograms + a few integers"""
+    def exchange_stats(st):
+        """the only inter-GPU exchange of the path, one NCCL all-gather per step: every rank's
+        6x256 histograms, its position / entry counts and the last well of its shard (the offset
+        hand-off); the sums are formed locally.  -> (summed statistics, last well of rank-1)"""
         if world == 1:
-            return st
-        h = torch.tensor(np.ctypeslib.as_array(st.hist).astype(np.int64).reshape(-1), device=dev)
-        extra = torch.tensor([st.totchar, st.nentries], dtype=torch.int64, device=dev)
-        dist.all_reduce(h); dist.all_reduce(extra)
-        hh = h.cpu().numpy().reshape(6, 256)
+            return st, 0
+        mine = np.empty(6 * 256 + 3, dtype=np.int64)
+        mine[: 6 * 256] = np.ctypeslib.as_array(st.hist).reshape(-1)
+        mine[6 * 256:] = (st.totchar, st.nentries, state["last_well"])
+        t = torch.from_numpy(mine).to(dev)
+        allt = torch.empty(world * mine.size, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(allt, t)
+        hh = allt.view(world, -1).cpu().numpy()
         tot = dx.Stats()
-        for k in range(6):
-            for i in range(256):
-                tot.hist[k][i] = int(hh[k, i])
-        tot.totchar, tot.nentries = int(extra[0]), int(extra[1])
-        # run characters are fixed by the first shard (rank 0 resolves them in its first ~100 k
-        # positions); broadcast them
-        rc = torch.tensor([st.delchar, st.subchar], dtype=torch.int64, device=dev)
-        dist.broadcast(rc, 0)
-        tot.delchar, tot.subchar = int(rc[0]), int(rc[1])
-        return tot
+        np.ctypeslib.as_array(tot.hist)[:] = hh[:, : 6 * 256].sum(axis=0).reshape(6, 256).astype(np.uint64)
+        tot.totchar, tot.nentries = int(hh[:, 6 * 256].sum()), int(hh[:, 6 * 256 + 1].sum())
+        # the run characters were fixed by the first shard (rank 0 resolves them in its first ~100 k
+        # positions) and handed to the other ranks before the loop
+        tot.delchar, tot.subchar = state["rc"]
+        return tot, (int(hh[rank - 1, 6 * 256 + 2]) if rank > 0 else 0)
 
     def carry_for_rank():
         """rank r > 0 counts run lengths with rank 0's run characters from its first entry on"""
@@ -249,16 +250,9 @@ def main():
         """dexqv: scan -> (allreduce) -> code construction -> file header + encode.
         The image is laid out as [header][entries] from enc[0] (16-byte aligned)."""
         st = ctx.qv_scan_dev(text.data_ptr(), U, carry_for_rank())
-        tot = allreduce_stats(st)
+        tot, lwell_in = exchange_stats(st)
         cd = dxl.make_coding(tot, False)
         hdr = b"\xaa\x55" + dxl.write_coding(cd, prefix)
-        if world > 1:
-            lastw = torch.tensor([state["last_well"]], dtype=torch.int64, device=dev)
-            allw = [torch.zeros_like(lastw) for _ in range(world)]
-            dist.all_gather(allw, lastw)                       # offset hand-off between shards
-            lwell_in = int(allw[rank - 1][0]) if rank > 0 else 0
-        else:
-            lwell_in = 0
         hl = len(hdr)
         ctx.h2d(enc.data_ptr(), hdr)
         body, lastw_out, offs = ctx.qv_encode_dev(text.data_ptr(), U, cd, False, lwell_in,
@@ -289,10 +283,11 @@ def main():
         c = dx.Carry()
         c.delchar, c.subchar, c.totchar = int(rc[0]), int(rc[1]), 200000
         state["carry"] = c
+        state["rc"] = (int(rc[0]), int(rc[1]))
         # last well of this shard: parse the last header once
         tail = bytes(text[-400000:].cpu().numpy().tobytes())
-        k = tail.rindex(b"\n@")
-        state["last_well"] = int(tail[k + 2:].split(b"/")[1])
+        k = tail.rindex(b"\n" + prefix + b"/")          # a QV line may start with '@' too
+        state["last_well"] = int(tail[k + 1:].split(b"/")[1])
     else:
         state["last_well"] = 0
 
