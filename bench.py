@@ -357,7 +357,7 @@ def main():
     algo = {"k_qv_hist_plain": 0.4 * lines_bytes, "k_qv_hist_run": 0.4 * lines_bytes,
             "k_qv_size": lines_bytes, "k_qv_emit": lines_bytes + C,
             "k_qv_decode5": C + U, "k_qv_decode5_spec": C + lines_bytes, "k_qv_assemble": 2 * U,
-            "k_pred_single": U}
+            "k_pred_slots": U}
     top = max(prof.items(), key=lambda kv: kv[1][1]) if prof else ("none", (1, 1.0))
     tname, (tcalls, ttot) = top
     tavg = ttot / max(tcalls, 1)
@@ -459,6 +459,58 @@ def main():
                       undexta_frac=(UF + m) / (unpack_ms * 1e-3) / GB / hbm_peak,
                       fasta_bytes=int(UF), dexta_bytes=int(m))
         del fa, pk, un
+        torch.cuda.empty_cache()
+
+        # configs[2]: dexar/undexar on a synthetic 1 GB Sequel-style .arrow
+        ar, nar = synth_torch.make_fasta_device(9, int(1.0 * GB), dev, arrow=True)
+        UA = ar.numel()
+        pk = torch.empty(UA // 3 + (1 << 20), dtype=torch.uint8, device=dev)
+        un = torch.empty(UA + 4096, dtype=torch.uint8, device=dev)
+        m = ctx.dexta_dev(dx.ARROW, ar.data_ptr(), UA, pk.data_ptr(), pk.numel())
+        k = ctx.undexta_dev(dx.ARROW, pk.data_ptr(), m, 80, False, un.data_ptr(), un.numel())
+        # SN=%.2f headers pass through a float and lose up to 0.01 per trip, so the
+        # property at full size is: same length, and only SNR digits of the header lines may differ
+        ndiff = int((un[:UA] != ar).sum()) if k == UA else -1
+        assert k == UA and 0 <= ndiff <= 16 * nar, "dexar/undexar round trip differs outside the SNR digits"
+        par_ms, _ = timed(lambda: ctx.dexta_dev(dx.ARROW, ar.data_ptr(), UA, pk.data_ptr(), pk.numel()))
+        unar_ms, _ = timed(lambda: ctx.undexta_dev(dx.ARROW, pk.data_ptr(), m, 80, False,
+                                                   un.data_ptr(), un.numel()))
+        extras.update(dexar_gbs=UA / (par_ms * 1e-3) / GB, undexar_gbs=UA / (unar_ms * 1e-3) / GB,
+                      arrow_bytes=int(UA), dexar_bytes=int(m))
+        del ar, pk, un
+        torch.cuda.empty_cache()
+
+        # configs[4]: mixed short/long subread lengths (500 bp - 50 kb), 0.5 GB each
+        sweep = {}
+        rs = np.random.default_rng(5)
+        npos_t = int(0.5 * GB / 5.02)
+        dists = {"log_uniform_500_50k": lambda k: np.exp(rs.uniform(np.log(500), np.log(50000), size=k)),
+                 "90pct_500bp_10pct_50kb": lambda k: np.where(rs.random(k) < 0.9, 500, 50000),
+                 "10pct_500bp_90pct_50kb": lambda k: np.where(rs.random(k) < 0.1, 500, 50000)}
+        for name, draw in dists.items():
+            Ls = np.asarray(draw(200000), dtype=np.int64)
+            Ls = Ls[: int(np.searchsorted(np.cumsum(Ls), npos_t)) + 1]
+            tx, ne, npz = synth_torch.make_quiva_device(50, 0, dev, lengths=Ls)
+            Us = tx.numel()
+            e2 = torch.empty(Us // 2 + (1 << 20), dtype=torch.uint8, device=dev)
+            b2 = torch.empty(Us + 4096, dtype=torch.uint8, device=dev)
+            st2 = {}
+
+            def enc2():
+                st2["n"] = ctx.dexqv_dev(tx.data_ptr(), Us, False, e2.data_ptr(), e2.numel())
+
+            def dec2():
+                st2["m"] = ctx.undexqv_dev(e2.data_ptr(), st2["n"], False, b2.data_ptr(), b2.numel())
+
+            enc2(); dec2(); dec2()
+            assert st2["m"] == Us and bool(torch.equal(b2[:Us], tx)), "length sweep round trip differs"
+            t_e, _ = timed(enc2)
+            t_d, _ = timed(dec2)
+            sweep[name] = {"entries": int(ne), "bytes": int(Us), "dexqv_gbs": Us / (t_e * 1e-3) / GB,
+                           "undexqv_discovered_gbs": Us / (t_d * 1e-3) / GB}
+            del tx, e2, b2
+            torch.cuda.empty_cache()
+        extras["length_sweep"] = sweep
 
     # ---- CPU baseline beside it (rank 0, N=1 only) ---------------------------------------------
     cpu = None

@@ -6,8 +6,9 @@
 //   DX_PRED_FASTA_HDR  every '>' that starts a line
 //   DX_PRED_QVCAND     every offset whose next 12 bytes look like the beg/end/qv fields of a
 //                      .dexqv entry header (dexqv.c:137-139) -- candidates only, verified later
-// One launch (decoupled look-back over 16 KB tiles); the exact three-launch form -- per-tile counts,
-// an exclusive scan of the counts, an ordered write -- remains as the fallback for dense inputs.
+// One pass over the text (per-tile slot rows, scan, gather); the exact form -- per-tile counts, an
+// exclusive scan of the counts, an ordered write in a second pass -- remains as the fallback for
+// inputs with more than 16 hits in a 16 KB tile.
 
 #include <stdlib.h>
 #include "dx_internal.h"
@@ -30,9 +31,16 @@ __device__ __forceinline__ uint32_t load_le32(const uint8_t *p)
 
 // 16-bit hit mask of the chunk starting at byte `at` (16-byte aligned, at < n)
 template <int PRED>
+__device__ __forceinline__ uint32_t chunk_hits(const uint8_t *buf, size_t n, size_t first, size_t at, uint4 v);
+
+template <int PRED>
 __device__ __forceinline__ uint32_t chunk_hits(const uint8_t *buf, size_t n, size_t first, size_t at)
-{ uint4 v = dx_ldg16(buf + at);                    // the buffer is padded to a 16-byte multiple
-  uint32_t hits;
+{ return chunk_hits<PRED>(buf,n,first,at,dx_ldg16(buf + at));   // the buffer is padded to a 16-byte multiple
+}
+
+template <int PRED>
+__device__ __forceinline__ uint32_t chunk_hits(const uint8_t *buf, size_t n, size_t first, size_t at, uint4 v)
+{ uint32_t hits;
   if (PRED == DX_PRED_NEWLINE)
     { // newlines are rare: one exact "is any byte a newline" test for the whole chunk first
       const uint32_t k = 0x0a0a0a0au;
@@ -247,106 +255,6 @@ __global__ void k_qv_entries(const uint8_t *text, const int64_t *nl, int64_t nen
   ent.flag[e] = ok ? 0 : 1;
 }
 
-// ---- single pass: count, scan and write in one launch ------------------------------------------
-// Tiles are taken in ticket order; a tile publishes its count in a 64-bit status word (state in the
-// top two bits: 1 = tile aggregate, 2 = inclusive prefix) and finds its own prefix by looking back
-// over its predecessors' words, 32 at a time (decoupled look-back).  The text is read once.
-// Positions beyond `cap` are counted but not written; the host then repeats with the exact
-// two-pass kernels above.
-constexpr int kSThreads = 256;
-constexpr int kSChunks  = 32;                                     // 16-byte chunks per thread
-constexpr int kSBytes   = kSThreads * kSChunks * 16;              // 128 KB: a look-back hop skips 4 MB
-
-template <int PRED>
-__global__ void __launch_bounds__(kSThreads,4)
-k_pred_single(const uint8_t *buf, size_t n, size_t first, int64_t ntiles,
-              unsigned long long *status, unsigned long long *ticket, int64_t *pos, int64_t cap,
-              int64_t *count_out)
-{ __shared__ uint32_t wsum[kSChunks][kSThreads/32];      // per chunk row and warp: hits, then hits before
-  __shared__ uint32_t rowpre[kSChunks];                  // hits of the tile before chunk row j
-  __shared__ unsigned long long s_prefix;
-  __shared__ unsigned int s_tile;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (threadIdx.x == 0) s_tile = (unsigned int) atomicAdd(ticket,1ull);
-  __syncthreads();
-  const int64_t tile = (int64_t) s_tile;
-  const size_t base = (size_t) tile * kSBytes;
-
-  uint32_t hits[kSChunks];
-#pragma unroll
-  for (int j = 0; j < kSChunks; j++)
-    { const size_t at = base + ((size_t) j * kSThreads + threadIdx.x) * 16;
-      hits[j] = (at < n) ? chunk_hits<PRED>(buf,n,first,at) : 0;
-    }
-#pragma unroll
-  for (int j = 0; j < kSChunks; j++)
-    { const uint32_t c = dx_warp_sum(__popc(hits[j]));
-      if (lane == 0) wsum[j][warp] = c;
-    }
-  __syncthreads();
-  { // thread (j, w): hits of row j in the warps before w; the last warp's thread also has the row total
-    const int j = threadIdx.x >> 3, w = threadIdx.x & 7;
-    uint32_t before = 0;
-    for (int k = 0; k < w; k++) before += wsum[j][k];
-    const uint32_t mine = wsum[j][w];
-    __syncthreads();
-    wsum[j][w] = before;
-    if (w == 7) rowpre[j] = before + mine;
-  }
-  __syncthreads();
-  if (warp == 0)
-    { const uint32_t v = rowpre[lane];
-      const uint32_t iv = dx_warp_incl_sum(v,lane);
-      const uint32_t total = __shfl_sync(DX_FULL,iv,31);
-      rowpre[lane] = iv - v;
-      unsigned long long prefix = 0;
-      volatile unsigned long long *st = status;
-      if (tile > 0)
-        { if (lane == 0) st[tile] = (1ull << 62) | total;
-          int64_t j = tile - 1;
-          while (true)
-            { const int64_t idx = j - lane;
-              unsigned long long x = (2ull << 62);                    // before the first tile: inclusive 0
-              if (idx >= 0)
-                { x = st[idx];
-                  while ((x >> 62) == 0) x = st[idx];
-                }
-              const uint32_t incl = __ballot_sync(DX_FULL,(x >> 62) == 2);
-              const int stop = incl ? __ffs(incl) - 1 : 31;           // nearest predecessor with a full prefix
-              unsigned long long part = (lane <= stop) ? (x & ((1ull << 62) - 1)) : 0ull;
-#pragma unroll
-              for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(DX_FULL,part,d);
-              prefix += part;
-              if (incl) break;
-              j -= 32;
-            }
-        }
-      if (lane == 0)
-        { __threadfence();
-          st[tile] = (2ull << 62) | (prefix + total);
-          s_prefix = prefix;
-          if (tile == ntiles - 1) *count_out = (int64_t) (prefix + total);
-        }
-    }
-  __syncthreads();
-  const int64_t mybase = (int64_t) s_prefix;
-#pragma unroll
-  for (int j = 0; j < kSChunks; j++)
-    { uint32_t h = hits[j];
-      if (!__any_sync(DX_FULL,h != 0)) continue;
-      const uint32_t c = __popc(h);
-      const uint32_t inc = dx_warp_incl_sum(c,lane);
-      const size_t at = base + ((size_t) j * kSThreads + threadIdx.x) * 16;
-      int64_t r = mybase + rowpre[j] + wsum[j][warp] + inc - c;
-      while (h)
-        { const int i = __ffs(h) - 1;
-          h &= h - 1;
-          if (r < cap) pos[r] = (int64_t) (at + i);
-          r++;
-        }
-    }
-}
-
 template <int PRED>
 int index_positions_exact(dx_ctx *ctx, const uint8_t *buf, size_t n, size_t first,
                           int64_t **d_pos, int64_t *count)
@@ -373,32 +281,96 @@ int index_positions_exact(dx_ctx *ctx, const uint8_t *buf, size_t n, size_t firs
   return DX_OK;
 }
 
+// ---- one pass over the text: per-tile slots ---------------------------------------------------------
+// Hits are sparse (a newline every ~10 KB of .quiva, a header every ~10 KB of .fasta, an entry every
+// ~17 KB of .dexqv): every 16 KB tile drops its (few) hit positions, unordered, into a fixed row of
+// kSlot slots and reports its count; an exclusive scan of the counts and a gather that sorts each
+// row give the ordered index.  The text is read once, by a kernel as simple as k_pred_count.  A tile
+// with more than kSlot hits (dense input) sends the call to the exact two-pass kernels above.
+constexpr int kSlot = 16;
+
+template <int PRED>
+__global__ void __launch_bounds__(kTileThreads)
+k_pred_slots(const uint8_t *buf, size_t n, size_t first, uint32_t *tile_count, int64_t *slots, int32_t *overflow)
+{ __shared__ uint32_t cnt;
+  if (threadIdx.x == 0) cnt = 0;
+  __syncthreads();
+  const size_t base = (size_t) blockIdx.x * kTileBytes;
+  uint4 v[kTileChunks];
+#pragma unroll
+  for (int j = 0; j < kTileChunks; j++)
+    { const size_t at = base + ((size_t) j * kTileThreads + threadIdx.x) * 16;
+      v[j] = (at < n) ? dx_ldg16(buf + at) : make_uint4(0,0,0,0);
+    }
+#pragma unroll
+  for (int j = 0; j < kTileChunks; j++)
+    { const size_t at = base + ((size_t) j * kTileThreads + threadIdx.x) * 16;
+      uint32_t hits = (at < n) ? chunk_hits<PRED>(buf,n,first,at,v[j]) : 0;
+      if (hits)
+        { uint32_t s = atomicAdd(&cnt,(uint32_t) __popc(hits));
+          while (hits)
+            { const int i = __ffs(hits) - 1;
+              hits &= hits - 1;
+              if (s < (uint32_t) kSlot) slots[(size_t) blockIdx.x * kSlot + s] = (int64_t) (at + i);
+              s++;
+            }
+        }
+    }
+  __syncthreads();
+  if (threadIdx.x == 0)
+    { tile_count[blockIdx.x] = cnt;
+      if (cnt > (uint32_t) kSlot) atomicExch(overflow,1);
+    }
+}
+
+__global__ void k_pred_gather(const uint32_t *tile_count, const int64_t *tile_prefix, const int64_t *slots,
+                              int64_t ntiles, int64_t *pos)
+{ const int64_t t = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= ntiles) return;
+  const uint32_t c = min(tile_count[t],(uint32_t) kSlot);
+  if (c == 0) return;
+  int64_t p[kSlot];
+  for (uint32_t i = 0; i < c; i++)                       // insertion sort of at most kSlot positions
+    { const int64_t x = slots[(size_t) t * kSlot + i];
+      int k = (int) i;
+      while (k > 0 && p[k-1] > x) { p[k] = p[k-1]; k--; }
+      p[k] = x;
+    }
+  int64_t *dst = pos + tile_prefix[t];
+  for (uint32_t i = 0; i < c; i++) dst[i] = p[i];
+}
+
 template <int PRED>
 int index_positions(dx_ctx *ctx, const uint8_t *buf, size_t n, size_t first,
                     int64_t **d_pos, int64_t *count)
-{ const int64_t ntiles = (int64_t) ((n + kSBytes - 1) / kSBytes);
+{ const int64_t ntiles = (int64_t) ((n + kTileBytes - 1) / kTileBytes);
   *d_pos = NULL; *count = 0;
   if (ntiles == 0) return DX_OK;
-  // expected density: 6 newlines per .quiva entry, one header per fasta entry, one candidate per
-  // .dexqv entry; anything denser falls back to the exact two-pass index
-  const int64_t cap = (int64_t) (n / (PRED == DX_PRED_NEWLINE ? 64 : 256)) + 4096;
-  unsigned long long *d_status = (unsigned long long *) dx_arena_get(ctx,(size_t) (ntiles + 2)*8);
-  int64_t *pos = (int64_t *) dx_arena_get(ctx,(size_t) cap*8);
-  if (d_status == NULL || pos == NULL) return DX_E_NOMEM;
-  DX_CUDA(ctx,cudaMemsetAsync(d_status,0,(size_t) (ntiles + 2)*8,ctx->stream));
-  unsigned long long *d_ticket = d_status + ntiles;
-  int64_t *d_count = (int64_t *) (d_status + ntiles + 1);
+  if (getenv("DEXB200_EXACT_INDEX") != NULL) return index_positions_exact<PRED>(ctx,buf,n,first,d_pos,count);
+  uint32_t *d_cnt  = (uint32_t *) dx_arena_get(ctx,(size_t) ntiles*4 + 16);
+  int64_t  *d_pre  = (int64_t *)  dx_arena_get(ctx,(size_t) (ntiles+1)*8);
+  int64_t  *d_slot = (int64_t *)  dx_arena_get(ctx,(size_t) ntiles*kSlot*8);
+  if (d_cnt == NULL || d_pre == NULL || d_slot == NULL) return DX_E_NOMEM;
+  int32_t *d_over = (int32_t *) (d_cnt + ntiles);
+  DX_CUDA(ctx,cudaMemsetAsync(d_over,0,4,ctx->stream));
   DX_PROF_BEGIN(ctx);
-  k_pred_single<PRED><<<(unsigned) ntiles,kSThreads,0,ctx->stream>>>(buf,n,first,ntiles,d_status,d_ticket,
-                                                                       pos,cap,d_count);
-  DX_LAUNCHED(ctx,"k_pred_single");
-  int64_t total = 0;
-  DX_CUDA(ctx,cudaMemcpyAsync(&total,d_count,8,cudaMemcpyDeviceToHost,ctx->stream));
+  k_pred_slots<PRED><<<(unsigned) ntiles,kTileThreads,0,ctx->stream>>>(buf,n,first,d_cnt,d_slot,d_over);
+  DX_LAUNCHED(ctx,"k_pred_slots");
+  DX_PROF_BEGIN(ctx); k_tile_scan<<<1,1024,0,ctx->stream>>>(d_cnt,ntiles,d_pre);
+  DX_LAUNCHED(ctx,"k_tile_scan");
+  struct { int64_t total; int32_t over; int32_t pad; } h;
+  DX_CUDA(ctx,cudaMemcpyAsync(&h.total,d_pre+ntiles,8,cudaMemcpyDeviceToHost,ctx->stream));
+  DX_CUDA(ctx,cudaMemcpyAsync(&h.over,d_over,4,cudaMemcpyDeviceToHost,ctx->stream));
   DX_CUDA(ctx,cudaStreamSynchronize(ctx->stream));
-  if (total > cap || getenv("DEXB200_EXACT_INDEX") != NULL)
-    return index_positions_exact<PRED>(ctx,buf,n,first,d_pos,count);
-  *count = total;
-  *d_pos = (total > 0) ? pos : NULL;
+  if (h.over) return index_positions_exact<PRED>(ctx,buf,n,first,d_pos,count);
+  *count = h.total;
+  if (h.total == 0) return DX_OK;
+  int64_t *pos = (int64_t *) dx_arena_get(ctx,(size_t) h.total*8);
+  if (pos == NULL) return DX_E_NOMEM;
+  DX_PROF_BEGIN(ctx);
+  k_pred_gather<<<(unsigned) ((ntiles + 255)/256),256,0,ctx->stream>>>(d_cnt,d_pre,d_slot,ntiles,pos);
+  DX_LAUNCHED(ctx,"k_pred_gather");
+  *d_pos = pos;
   return DX_OK;
 }
 
