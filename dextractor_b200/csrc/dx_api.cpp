@@ -873,7 +873,10 @@ extern "C" int dx_compress_reads_dev(dx_ctx *ctx, int kind, const uint8_t *d_src
                                      uint8_t *d_dst, const int64_t *d_dst_off)
 { if (ctx == NULL || nreads < 0) return DX_E_ARG;
   cudaSetDevice(ctx->device);
-  return dxk_compress_reads(ctx,kind,d_src,d_src_off,d_len,nreads,d_dst,d_dst_off);
+  dx_arena_reset(ctx);
+  if (getenv("DEXB200_EXACT_PACK") != NULL)
+    return dxk_compress_reads(ctx,kind,d_src,d_src_off,d_len,nreads,d_dst,d_dst_off);
+  return dxk_compress_reads2(ctx,kind,d_src,d_src_off,d_len,nreads,d_dst,d_dst_off);
 }
 
 extern "C" int dx_uncompress_reads_dev(dx_ctx *ctx, int kind, int upper, const uint8_t *d_src,
@@ -881,7 +884,10 @@ extern "C" int dx_uncompress_reads_dev(dx_ctx *ctx, int kind, int upper, const u
                                        int64_t nreads, uint8_t *d_dst, const int64_t *d_dst_off)
 { if (ctx == NULL || nreads < 0) return DX_E_ARG;
   cudaSetDevice(ctx->device);
-  return dxk_uncompress_reads(ctx,kind,upper,d_src,d_src_off,d_len,nreads,d_dst,d_dst_off);
+  dx_arena_reset(ctx);
+  if (getenv("DEXB200_EXACT_PACK") != NULL)
+    return dxk_uncompress_reads(ctx,kind,upper,d_src,d_src_off,d_len,nreads,d_dst,d_dst_off);
+  return dxk_uncompress_reads2(ctx,kind,upper,d_src,d_src_off,d_len,nreads,d_dst,d_dst_off);
 }
 
 // ================================================================================================

@@ -249,6 +249,12 @@ int dxk_fa_measure2(dx_ctx *ctx, int kind, const uint8_t *d_text, size_t n, cons
 int dxk_fa_pack2(dx_ctx *ctx, int kind, const uint8_t *d_text, FaEntries ent, int32_t lwell_in, uint8_t *d_out,
                  int32_t *d_err, unsigned long long *d_ticket);
 
+int dxk_compress_reads2(dx_ctx *ctx, int kind, const uint8_t *d_src, const int64_t *d_src_off,
+                        const int32_t *d_len, int64_t nreads, uint8_t *d_dst, const int64_t *d_dst_off);
+int dxk_uncompress_reads2(dx_ctx *ctx, int kind, int upper, const uint8_t *d_src,
+                          const int64_t *d_src_off, const int32_t *d_len, int64_t nreads,
+                          uint8_t *d_dst, const int64_t *d_dst_off);
+
 struct PkDecEntry               // table for the unpack kernel
 { int64_t bin_off;              // first payload byte in the image
   int64_t out_off;              // header text start in the output

@@ -382,6 +382,112 @@ k_unpack2(Unpack2Args a)
     }
 }
 
+// ---- batched in-memory reads (the Dazzler DB loader / writer form, no line structure) -----------------------
+// read r: ASCII at src + src_off[r], len[r] symbols  <->  2-bit payload at dst + dst_off[r]
+struct Reads2Args
+{ int kind, upper;
+  const uint8_t *src; const uint8_t *src_end4; const int64_t *src_off; const int32_t *len; int64_t nreads;
+  uint8_t *dst; const int64_t *dst_off;
+  unsigned long long *ticket;
+};
+
+template <int KIND>
+__global__ void __launch_bounds__(kP2Threads)
+k_compress_reads2(Reads2Args a)
+{ __shared__ uint32_t stage_all[kP2Warps][kP2Stage + 4];
+  const int lane = threadIdx.x & 31;
+  uint32_t *stage = stage_all[threadIdx.x >> 5];
+  unsigned long long next = 0;
+  if (lane == 0) next = atomicAdd(a.ticket,1ull);
+  while (true)
+    { const int64_t r = (int64_t) __shfl_sync(DX_FULL,next,0);
+      if (r >= a.nreads) break;
+      if (lane == 0) next = atomicAdd(a.ticket,1ull);
+      const int32_t rlen = a.len[r];
+      if (rlen <= 0) continue;
+      const uint32_t clen = ((uint32_t) rlen + 3u) >> 2;
+      uint8_t *pay = a.dst + a.dst_off[r];
+      LineWalk lw; lw.set(a.src + a.src_off[r],rlen);
+      WarpBits wb; wb.init(stage,pay,kP2Stage);
+      uint4 nxt = (lane < lw.nchunk) ? dx_ldg16(lw.base + (int64_t) lane*16) : make_uint4(0,0,0,0);
+#pragma unroll 1
+      for (int32_t c0 = 0; c0 < lw.nchunk; c0 += 32)
+        { const int32_t c = c0 + lane;
+          const uint4 v = nxt;
+          nxt = (c + 32 < lw.nchunk) ? dx_ldg16(lw.base + (int64_t) (c + 32)*16) : make_uint4(0,0,0,0);
+          const uint32_t valid = lw.valid(c);
+          const uint32_t cnt = __popc(valid);
+          uint32_t val = (codes4<KIND>(v.x) << 24) | (codes4<KIND>(v.y) << 16) |
+                         (codes4<KIND>(v.z) << 8) | codes4<KIND>(v.w);
+          if (valid != 0xffffu)
+            val = cnt ? (val << (2*(__ffs(valid) - 1))) >> (32 - 2*cnt) : 0u;
+          const uint32_t inc = dx_warp_incl_sum(cnt,lane);
+          wb.reserve<true>(__shfl_sync(DX_FULL,inc,31)*2u,lane);
+          LaneSink sk;
+          sk.start(wb.bitpos() + (inc - cnt)*2u);
+          sk.put(wb.stage,val,cnt*2u);
+          sk.finish(wb,lane);
+        }
+      __syncwarp();
+      if (lane == 0 && wb.cbits) stage[wb.nst] = wb.carry;
+      __syncwarp();
+      copy_out<true>(pay + (size_t) wb.flushed*4u,stage,clen - wb.flushed*4u,lane);
+      __syncwarp();
+    }
+}
+
+__global__ void __launch_bounds__(kP2Threads)
+k_uncompress_reads2(Reads2Args a)
+{ const int lane = threadIdx.x & 31;
+  const uint32_t alpha = (a.kind == DX_ARROW) ? 0x34333231u : a.upper ? 0x54474341u : 0x74676361u;
+  unsigned long long next = 0;
+  if (lane == 0) next = atomicAdd(a.ticket,1ull);
+  while (true)
+    { const int64_t r = (int64_t) __shfl_sync(DX_FULL,next,0);
+      if (r >= a.nreads) break;
+      if (lane == 0) next = atomicAdd(a.ticket,1ull);
+      const int64_t rlen = a.len[r];
+      if (rlen <= 0) continue;
+      const uint8_t *pay = a.src + a.src_off[r];
+      // whole 32-bit words are loaded: the word holding the last payload byte is the last readable one
+      const uint8_t *end4 = reinterpret_cast<const uint8_t *>(
+                              (reinterpret_cast<uintptr_t>(pay + ((rlen + 3) >> 2)) + 3) & ~(uintptr_t) 3);
+      uint8_t *dst = a.dst + a.dst_off[r];
+      const int skew = (int) (reinterpret_cast<uintptr_t>(dst) & 15);
+      uint8_t *base = dst - skew;                                    // 16-byte aligned
+      const int64_t nchunk = (skew + rlen + 15) >> 4;
+#pragma unroll 1
+      for (int64_t c = lane; c < nchunk; c += 32)
+        { const int64_t t0 = c*16 - skew;                            // symbol index of the chunk's byte 0
+          if (t0 >= 0 && t0 + 16 <= rlen)
+            { const uint8_t *p = pay + (t0 >> 2);
+              const uintptr_t A = reinterpret_cast<uintptr_t>(p);
+              const uint32_t *a4 = reinterpret_cast<const uint32_t *>(A & ~(uintptr_t) 3);
+              const uint32_t w0 = __ldg(a4);
+              const uint32_t w1 = (reinterpret_cast<const uint8_t *>(a4 + 1) < end4) ? __ldg(a4 + 1) : 0u;
+              const uint32_t sh = (uint32_t) (A & 3)*8u + (uint32_t) (t0 & 3)*2u;
+              const uint32_t x = __funnelshift_l(__byte_perm(w1,0,0x0123),__byte_perm(w0,0,0x0123),sh);
+              uint32_t o[4];
+#pragma unroll
+              for (int k = 0; k < 4; k++)
+                { const uint32_t q = x >> (24 - 8*k);
+                  const uint32_t sel = ((q >> 6) & 3u) | (((q >> 4) & 3u) << 4) | (((q >> 2) & 3u) << 8) | ((q & 3u) << 12);
+                  o[k] = __byte_perm(alpha,0,sel);
+                }
+              dx_stg16(base + c*16,make_uint4(o[0],o[1],o[2],o[3]));
+            }
+          else
+            { const int lo = (int) max((int64_t) 0,-t0), hi = (int) min((int64_t) 16,rlen - t0);
+              for (int k = lo; k < hi; k++)
+                { const int64_t b = t0 + k;
+                  const uint32_t byte = pay[b >> 2];
+                  base[c*16 + k] = (uint8_t) ((alpha >> (8*((byte >> (6 - 2*(b & 3))) & 3u))) & 0xffu);
+                }
+            }
+        }
+    }
+}
+
 // ---- planning a decode on the device ----------------------------------------------------------------------------
 
 __device__ __forceinline__ int32_t ld32(const uint8_t *p)
@@ -521,5 +627,40 @@ int dxk_pk_layout(dx_ctx *ctx, int kind, const uint8_t *d_in, const int64_t *d_q
                                                                         d_opre,d_len,d_ent);
       DX_LAUNCHED(ctx,"k_pk_build_ent");
     }
+  return DX_OK;
+}
+
+int dxk_compress_reads2(dx_ctx *ctx, int kind, const uint8_t *d_src, const int64_t *d_src_off,
+                        const int32_t *d_len, int64_t nreads, uint8_t *d_dst, const int64_t *d_dst_off)
+{ if (nreads == 0) return DX_OK;
+  unsigned long long *d_ticket = (unsigned long long *) dx_arena_get(ctx,8);
+  if (d_ticket == NULL) return DX_E_NOMEM;
+  DX_CUDA(ctx,cudaMemsetAsync(d_ticket,0,8,ctx->stream));
+  Reads2Args a;
+  a.kind = kind; a.upper = 0; a.src = d_src; a.src_end4 = NULL; a.src_off = d_src_off; a.len = d_len; a.nreads = nreads;
+  a.dst = d_dst; a.dst_off = d_dst_off; a.ticket = d_ticket;
+  int64_t grid = (nreads + kP2Warps - 1) / kP2Warps;
+  if (grid > (int64_t) ctx->sm_count * 8) grid = (int64_t) ctx->sm_count * 8;
+  DX_PROF_BEGIN(ctx);
+  if (kind == DX_FASTA) k_compress_reads2<DX_FASTA><<<(unsigned) grid,kP2Threads,0,ctx->stream>>>(a);
+  else                  k_compress_reads2<DX_ARROW><<<(unsigned) grid,kP2Threads,0,ctx->stream>>>(a);
+  DX_LAUNCHED(ctx,"k_compress_reads2");
+  return DX_OK;
+}
+
+int dxk_uncompress_reads2(dx_ctx *ctx, int kind, int upper, const uint8_t *d_src,
+                          const int64_t *d_src_off, const int32_t *d_len, int64_t nreads,
+                          uint8_t *d_dst, const int64_t *d_dst_off)
+{ if (nreads == 0) return DX_OK;
+  unsigned long long *d_ticket = (unsigned long long *) dx_arena_get(ctx,8);
+  if (d_ticket == NULL) return DX_E_NOMEM;
+  DX_CUDA(ctx,cudaMemsetAsync(d_ticket,0,8,ctx->stream));
+  Reads2Args a;
+  a.kind = kind; a.upper = upper; a.src = d_src; a.src_end4 = NULL;
+  a.src_off = d_src_off; a.len = d_len; a.nreads = nreads; a.dst = d_dst; a.dst_off = d_dst_off; a.ticket = d_ticket;
+  int64_t grid = (nreads + kP2Warps - 1) / kP2Warps;
+  if (grid > (int64_t) ctx->sm_count * 8) grid = (int64_t) ctx->sm_count * 8;
+  DX_PROF_BEGIN(ctx); k_uncompress_reads2<<<(unsigned) grid,kP2Threads,0,ctx->stream>>>(a);
+  DX_LAUNCHED(ctx,"k_uncompress_reads2");
   return DX_OK;
 }

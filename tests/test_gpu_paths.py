@@ -136,3 +136,56 @@ def test_output_buffer_too_small_is_an_error(ctx, orc):
     with pytest.raises(dx.DexError) as e:
         ctx.undexqv(enc, cap=len(text) // 2)
     assert e.value.code == -2                            # DX_E_CAP
+
+
+@pytest.mark.parametrize("env", [{}, {"DEXB200_EXACT_PACK": "1"}], ids=["vectorised", "byte_serial"])
+@pytest.mark.parametrize("arrow", [False, True])
+def test_batched_reads_many(ctx, orc, monkeypatch, env, arrow):
+    """dx_compress_reads_dev / dx_uncompress_reads_dev (the Dazzler DB loader form, DB.c:1389-1441,
+    1556-1614) on 1500 reads at ragged offsets, against Number_Read/Number_Arrow + Compress_Read and
+    Uncompress_Read + Lower_/Upper_Read/Letter_Arrow of the oracle, read by read."""
+    import ctypes as C
+    import torch
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    rng = np.random.default_rng(77)
+    lens = np.concatenate([np.arange(0, 40), rng.integers(1, 6000, size=1460)]).astype(np.int32)
+    alpha = np.frombuffer(b"1234G0x" if arrow else b"acgtACGTnN-", dtype=np.uint8)
+    reads = [alpha[rng.integers(0, len(alpha), size=int(n))].tobytes() for n in lens]
+    gap = rng.integers(0, 7, size=len(lens))                      # ragged source / destination offsets
+    src_off = np.concatenate([[3], 3 + np.cumsum(lens + gap)[:-1]]).astype(np.int64)
+    clen = (lens + 3) // 4
+    dst_off = np.concatenate([[5], 5 + np.cumsum(clen + gap)[:-1]]).astype(np.int64)
+    src = bytearray(int(src_off[-1] + lens[-1] + 16))
+    for o, r in zip(src_off, reads):
+        src[o:o + len(r)] = r
+    d_src = torch.frombuffer(src, dtype=torch.uint8).cuda()
+    d_so, d_len = torch.from_numpy(src_off).cuda(), torch.from_numpy(lens).cuda()
+    d_do = torch.from_numpy(dst_off).cuda()
+    d_dst = torch.full((int(dst_off[-1] + clen[-1] + 16),), 0xEE, dtype=torch.uint8, device="cuda")
+    kind = dx.ARROW if arrow else dx.FASTA
+    ctx.compress_reads_dev(kind, d_src.data_ptr(), d_so.data_ptr(), d_len.data_ptr(), len(lens),
+                           d_dst.data_ptr(), d_do.data_ptr())
+    ctx.sync()
+    packed = d_dst.cpu().numpy().tobytes()
+    L = orc.lib()
+    expect = bytearray(b"\xEE" * len(packed))
+    for i, r in enumerate(reads):
+        buf = C.create_string_buffer(r, len(r) + 8)
+        (L.orc_number_arrow if arrow else L.orc_number_read)(buf)
+        L.orc_compress_read(len(r), buf)
+        expect[dst_off[i]: dst_off[i] + clen[i]] = buf.raw[: clen[i]]
+    assert packed == bytes(expect)                                # also: nothing outside the payloads touched
+    for upper in ([False] if arrow else [False, True]):
+        d_back = torch.full((len(src),), 0xDD, dtype=torch.uint8, device="cuda")
+        ctx.uncompress_reads_dev(kind, upper, d_dst.data_ptr(), d_do.data_ptr(), d_len.data_ptr(),
+                                 len(lens), d_back.data_ptr(), d_so.data_ptr())
+        ctx.sync()
+        back = d_back.cpu().numpy().tobytes()
+        want = bytearray(b"\xDD" * len(src))
+        for i, r in enumerate(reads):
+            buf = C.create_string_buffer(packed[dst_off[i]: dst_off[i] + clen[i]], len(r) + 8)
+            L.orc_uncompress_read(len(r), buf)
+            (L.orc_letter_arrow if arrow else (L.orc_upper_read if upper else L.orc_lower_read))(buf)
+            want[src_off[i]: src_off[i] + len(r)] = buf.raw[: len(r)]
+        assert back == bytes(want)
