@@ -7,7 +7,7 @@ NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC,-Wall,-Wno-unused-function -I../../include -I."
 mkdir -p build
 objs=""
-for f in dx_frame.cu dx_qv_stats.cu dx_qv_encode.cu dx_qv_decode.cu dx_qv_decode2.cu dx_qv_decode3.cu dx_qv_decode4.cu dx_qv_decode5.cu dx_qv_plan.cu dx_pack.cu dx_pack2.cu; do
+for f in dx_frame.cu dx_qv_stats.cu dx_qv_encode.cu dx_qv_decode.cu dx_qv_decode2.cu dx_qv_decode3.cu dx_qv_decode4.cu dx_qv_decode5.cu dx_qv_plan.cu dx_pack.cu dx_pack2.cu dx_pack3.cu; do
   o=build/${f%.cu}.o
   if [ ! -f $o ] || [ $f -nt $o ] || [ dx_common.cuh -nt $o ] || [ dx_bits.cuh -nt $o ] || [ dx_internal.h -nt $o ] || [ ../../include/dexb200.h -nt $o ]; then
     $NVCC $FLAGS ${PTXAS_V:+-Xptxas -v} -c $f -o $o &

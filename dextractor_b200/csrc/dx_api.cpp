@@ -585,12 +585,24 @@ static int dexta_impl(dx_ctx *ctx, int kind, const uint8_t *d_text, size_t n,
       DX_CUDA(ctx,cudaStreamSynchronize(ctx->stream));
     }
   else
-    { int32_t err = 0;
-      if ((rc = dxk_fa_pack2(ctx,kind,d_text,ent,0,d_out + hbytes,d_flags + 1,
-                             (unsigned long long *) (d_flags + 2))) != DX_OK) return rc;
-      DX_CUDA(ctx,cudaMemcpyAsync(&err,d_flags + 1,4,cudaMemcpyDeviceToHost,ctx->stream));
+    { // d_flags: [1] pack error, [2..3] ticket, [4] entries left to k_fa_pack2, [6..7] its ticket
+      int32_t res[4] = { 0, 0, 0, 0 };
+      if (getenv("DEXB200_PACK2") != NULL)
+        rc = dxk_fa_pack2(ctx,kind,d_text,ent,0,d_out + hbytes,d_flags + 1,(unsigned long long *) (d_flags + 2),0);
+      else
+        rc = dxk_fa_pack3(ctx,kind,d_text,n,ent,0,d_out + hbytes,d_flags + 1,d_flags + 4,
+                          (unsigned long long *) (d_flags + 2));
+      if (rc != DX_OK) return rc;
+      DX_CUDA(ctx,cudaMemcpyAsync(res,d_flags + 1,16,cudaMemcpyDeviceToHost,ctx->stream));
       DX_CUDA(ctx,cudaStreamSynchronize(ctx->stream));
-      if (err) { *redo = true; return DX_OK; }
+      if (res[0]) { *redo = true; return DX_OK; }
+      if (res[3])                                   // entries off the lattice (or narrower than 16)
+        { if ((rc = dxk_fa_pack2(ctx,kind,d_text,ent,0,d_out + hbytes,d_flags + 1,
+                                 (unsigned long long *) (d_flags + 6),1)) != DX_OK) return rc;
+          DX_CUDA(ctx,cudaMemcpyAsync(res,d_flags + 1,4,cudaMemcpyDeviceToHost,ctx->stream));
+          DX_CUDA(ctx,cudaStreamSynchronize(ctx->stream));
+          if (res[0]) { *redo = true; return DX_OK; }
+        }
     }
   *out_len = hbytes + (size_t) body;
   return DX_OK;
@@ -808,8 +820,11 @@ static int undexta_fast(dx_ctx *ctx, int kind, const uint8_t *d_in, size_t n, in
   const size_t total = (size_t) *h_total;
   if (d_out != NULL)
     { if (total > cap) return dx_fail(ctx,DX_E_CAP,"output needs %zu bytes, buffer has %zu",total,cap);
-      if ((rc = dxk_unpack2(ctx,kind,upper,width,d_in,n,d_ent,(int64_t) M,d_prefix,plen,d_out,d_ticket)) != DX_OK)
-        return rc;
+      if (getenv("DEXB200_PACK2") != NULL)
+        rc = dxk_unpack2(ctx,kind,upper,width,d_in,n,d_ent,(int64_t) M,d_prefix,plen,d_out,d_ticket);
+      else
+        rc = dxk_unpack3(ctx,kind,upper,width,d_in,n,d_ent,(int64_t) M,d_prefix,plen,d_out,d_ticket);
+      if (rc != DX_OK) return rc;
       DX_CUDA(ctx,cudaStreamSynchronize(ctx->stream));
     }
   *out_len = total;

@@ -55,9 +55,13 @@ struct WarpBits
   uint8_t  *gptr;           // global address of word 0 of the stream
 
   uint32_t  cap;            // words the stage holds (plus 4 words of slack)
+  uint32_t  limit;          // bytes there is room for at gptr; a flush past it is dropped and sets ovf
+  uint32_t  ovf;            //                                                (warp-uniform)
 
   __device__ __forceinline__ void init(uint32_t *st, uint8_t *g, uint32_t capacity)
-  { stage = st; nst = 0; carry = 0; cbits = 0; flushed = 0; gptr = g; cap = capacity; }
+  { stage = st; nst = 0; carry = 0; cbits = 0; flushed = 0; gptr = g; cap = capacity;
+    limit = 0xffffffffu; ovf = 0;
+  }
   __device__ __forceinline__ uint32_t bitpos() const { return nst*32u + cbits; }       // in the stage
   __device__ __forceinline__ uint32_t total() const { return (flushed + nst)*32u + cbits; }
 
@@ -66,7 +70,8 @@ struct WarpBits
   __device__ __forceinline__ void reserve(uint32_t bits, int lane)
   { if (nst + ((cbits + bits + 31u) >> 5) + 1u > cap)
       { __syncwarp();
-        copy_out<SWAP>(gptr + (size_t) flushed*4u,stage,nst*4u,lane);
+        if ((flushed + nst)*4u <= limit) copy_out<SWAP>(gptr + (size_t) flushed*4u,stage,nst*4u,lane);
+        else                             ovf = 1;
         __syncwarp();
         flushed += nst; nst = 0;
       }

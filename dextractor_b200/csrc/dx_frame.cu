@@ -123,21 +123,38 @@ k_pred_count(const uint8_t *buf, size_t n, size_t first, uint32_t *tile_count)
     }
 }
 
-// exclusive scan of ntiles 32-bit counts into 64-bit offsets; one CTA, 8 consecutive values per
-// thread per round.  total at prefix[ntiles].
+// exclusive scan of ntiles 32-bit counts into 64-bit offsets; one CTA, 32 consecutive values per
+// thread per round (vector loads and stores when the arrays are 16-byte aligned; a round costs a
+// few microseconds of barrier and memory latency whatever it holds).  total at prefix[ntiles].
+constexpr int kScanItems = 32;
+
 __global__ void __launch_bounds__(1024)
 k_tile_scan(const uint32_t *count, int64_t ntiles, int64_t *prefix)
 { __shared__ uint64_t wsum[32];
   __shared__ uint64_t carry;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bool vec = ((reinterpret_cast<uintptr_t>(count) | reinterpret_cast<uintptr_t>(prefix)) & 15) == 0;
   if (threadIdx.x == 0) carry = 0;
   __syncthreads();
-  for (int64_t b = 0; b < ntiles; b += 8192)
-    { const int64_t i0 = b + (int64_t) threadIdx.x * 8;
-      uint32_t c[8];
+  for (int64_t b = 0; b < ntiles; b += 1024*kScanItems)
+    { const int64_t i0 = b + (int64_t) threadIdx.x * kScanItems;
+      uint32_t c[kScanItems];
       uint64_t v = 0;
+      if (vec && i0 + kScanItems <= ntiles)
+        {
 #pragma unroll
-      for (int k = 0; k < 8; k++) { c[k] = (i0 + k < ntiles) ? count[i0 + k] : 0u; v += c[k]; }
+          for (int k = 0; k < kScanItems; k += 4)
+            { const uint4 q = *reinterpret_cast<const uint4 *>(count + i0 + k);
+              c[k] = q.x; c[k+1] = q.y; c[k+2] = q.z; c[k+3] = q.w;
+            }
+        }
+      else
+        {
+#pragma unroll
+          for (int k = 0; k < kScanItems; k++) c[k] = (i0 + k < ntiles) ? count[i0 + k] : 0u;
+        }
+#pragma unroll
+      for (int k = 0; k < kScanItems; k++) v += c[k];
       uint64_t inc = dx_warp_incl_sum64(v,lane);
       if (lane == 31) wsum[warp] = inc;
       __syncthreads();
@@ -148,10 +165,22 @@ k_tile_scan(const uint32_t *count, int64_t ntiles, int64_t *prefix)
         }
       __syncthreads();
       uint64_t excl = carry + wsum[warp] + inc - v;
+      if (vec && i0 + kScanItems <= ntiles)
+        {
 #pragma unroll
-      for (int k = 0; k < 8; k++)
-        { if (i0 + k < ntiles) prefix[i0 + k] = (int64_t) excl;
-          excl += c[k];
+          for (int k = 0; k < kScanItems; k += 2)
+            { const uint64_t x0 = excl, x1 = excl + c[k];
+              *reinterpret_cast<ulonglong2 *>(prefix + i0 + k) = make_ulonglong2(x0,x1);
+              excl = x1 + c[k+1];
+            }
+        }
+      else
+        {
+#pragma unroll
+          for (int k = 0; k < kScanItems; k++)
+            { if (i0 + k < ntiles) prefix[i0 + k] = (int64_t) excl;
+              excl += c[k];
+            }
         }
       __syncthreads();
       if (threadIdx.x == 1023) carry = excl;

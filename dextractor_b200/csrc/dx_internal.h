@@ -247,7 +247,11 @@ int dxk_fa_pack(dx_ctx *ctx, int kind, const uint8_t *d_text, size_t n, FaEntrie
 int dxk_fa_measure2(dx_ctx *ctx, int kind, const uint8_t *d_text, size_t n, const int64_t *d_hdr,
                     FaEntries ent, int32_t *d_anyflag);
 int dxk_fa_pack2(dx_ctx *ctx, int kind, const uint8_t *d_text, FaEntries ent, int32_t lwell_in, uint8_t *d_out,
-                 int32_t *d_err, unsigned long long *d_ticket);
+                 int32_t *d_err, unsigned long long *d_ticket, int only_leftover);
+// dx_pack3.cu : output-centric kernels for entries on the line lattice (width >= 16); entries that
+// are not are flagged in *d_leftover and packed by dxk_fa_pack2(only_leftover = 1)
+int dxk_fa_pack3(dx_ctx *ctx, int kind, const uint8_t *d_text, size_t n, FaEntries ent, int32_t lwell_in,
+                 uint8_t *d_out, int32_t *d_err, int32_t *d_leftover, unsigned long long *d_ticket);
 
 int dxk_compress_reads2(dx_ctx *ctx, int kind, const uint8_t *d_src, const int64_t *d_src_off,
                         const int32_t *d_len, int64_t nreads, uint8_t *d_dst, const int64_t *d_dst_off);
@@ -268,6 +272,8 @@ int dxk_unpack(dx_ctx *ctx, int kind, int upper, int width, const uint8_t *d_in,
                const PkDecEntry *d_ent, int64_t count, const char *d_prefix, int plen,
                uint8_t *d_out);
 int dxk_unpack2(dx_ctx *ctx, int kind, int upper, int width, const uint8_t *d_in, size_t n, const PkDecEntry *d_ent,
+                int64_t count, const char *d_prefix, int plen, uint8_t *d_out, unsigned long long *d_ticket);
+int dxk_unpack3(dx_ctx *ctx, int kind, int upper, int width, const uint8_t *d_in, size_t n, const PkDecEntry *d_ent,
                 int64_t count, const char *d_prefix, int plen, uint8_t *d_out, unsigned long long *d_ticket);
 int dxk_pk_cand_prep(dx_ctx *ctx, const uint8_t *d_in, size_t n, size_t first, int fieldbytes, const int64_t *d_q,
                      int64_t count, int64_t *d_end, int32_t *d_ffrun, uint8_t *d_last);

@@ -165,6 +165,7 @@ struct Pack2Args
   uint8_t *out;
   int32_t *err;                 // set to 1 when an entry's symbol count is not the measured one
   unsigned long long *ticket;
+  int32_t only_leftover;        // 1: only the entries k_fa_pack3 (dx_pack3.cu) left aside
 };
 
 template <int KIND>
@@ -181,6 +182,7 @@ k_fa_pack2(Pack2Args a)
       if (e >= a.ent.n) break;
       if (lane == 0) next = atomicAdd(a.ticket,1ull);
       const int32_t rlen = a.ent.rlen[e];
+      if (a.only_leftover && !(rlen > 0 && (!(a.ent.flag[e] & 8) || a.ent.width[e] < 16))) continue;
       uint8_t *dst = a.out + a.ent.off[e];
       if (lane == 0)
         { // entry header: well-delta bytes, beg, end, qv | 4 x uint16 SNR (dexta.c:187-198)
@@ -574,10 +576,11 @@ int dxk_fa_measure2(dx_ctx *ctx, int kind, const uint8_t *d_text, size_t n, cons
 }
 
 int dxk_fa_pack2(dx_ctx *ctx, int kind, const uint8_t *d_text, FaEntries ent, int32_t lwell_in, uint8_t *d_out,
-                 int32_t *d_err, unsigned long long *d_ticket)
+                 int32_t *d_err, unsigned long long *d_ticket, int only_leftover)
 { if (ent.n == 0) return DX_OK;
   Pack2Args a;
   a.text = d_text; a.ent = ent; a.lwell_in = lwell_in; a.out = d_out; a.err = d_err; a.ticket = d_ticket;
+  a.only_leftover = only_leftover;
   int64_t grid = (ent.n + kP2Warps - 1) / kP2Warps;
   if (grid > (int64_t) ctx->sm_count * 8) grid = (int64_t) ctx->sm_count * 8;
   DX_PROF_BEGIN(ctx);

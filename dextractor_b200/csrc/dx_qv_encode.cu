@@ -20,6 +20,13 @@
 //                 then code 32 items at a time, one item (run code [+ literal] + symbol code) per
 //                 lane.  The stage is flushed with aligned 32-bit stores at whatever byte alignment
 //                 the stream has in the file.
+//
+// Two routes.  The usual one needs no size pass: k_qv_emit codes every stream into a scratch image
+// laid out like the text (a stream of rlen symbols has rlen+9 bytes of room, i.e. more than 8 bits per
+// symbol) and records its length, k_qv_offsets scans the lengths and k_qv_compact moves the streams
+// to their place in the file with 16-byte stores.  A stream that does not fit (possible only when an
+// entry is full of escaped symbols) sends the call to the exact route: k_qv_size, k_qv_offsets,
+// k_qv_emit straight into the file.
 
 #include "dx_internal.h"
 #include "dx_common.cuh"
@@ -41,9 +48,16 @@ struct EncArgs
   int32_t         delchar, subchar, lossy, lwell_in;
   uint32_t       *bytes;          // [n][6]
   int64_t        *off;            // [n+1]
-  uint8_t        *out;
+  uint8_t        *out;            // MODE 1: the file image; MODE 2: the scratch image
+  int32_t        *ovf;            // MODE 2: set when a stream did not fit its room in the scratch image
   unsigned long long *ticket;
 };
+
+// MODE 2: where the stream of line s (0 del 1 tag 2 ins 3 mrg 4 sub) of entry e goes in the scratch
+// image, and how many bytes it may take
+__device__ __forceinline__ int64_t scratch_off(const EncArgs &a, int64_t e, int s, int32_t rlen)
+{ return a.ent.line0[e] + (int64_t) s*((int64_t) rlen + 1) + 8*(5*e + s); }
+__device__ __forceinline__ uint32_t scratch_room(int32_t rlen) { return (uint32_t) rlen + 9u; }
 
 // table entry: bits 0-4 length of the whole item, bit 5 escape, bits 8-31 the item's bits.
 // Symbol tables fold the 8-bit literal of an escaped symbol into the item (length <= 24); run
@@ -210,17 +224,18 @@ template <int MODE>
 __device__ void code_stream(const EncArgs &a, const uint32_t *stab, const uint8_t *line,
                             int32_t rlen, int kind /*0 del 2 ins 3 mrg 4 sub*/, int lane,
                             uint32_t *stage, uint32_t *queue, uint8_t *gptr,
-                            uint32_t &total_bits, uint32_t &plast_out)
-{ total_bits = 0; plast_out = 0;
+                            uint32_t &total_bits, uint32_t &plast_out, uint32_t &ovf)
+{ total_bits = 0; plast_out = 0; ovf = 0;
   if (rlen <= 0) return;
   const int32_t rc = (kind == 0) ? a.delchar : (kind == 4) ? a.subchar : -1;
   const uint32_t lossmask = !a.lossy ? 0xffffffffu : (kind == 2) ? 0xfefefefeu
                                                     : (kind == 3) ? 0xfcfcfcfcu : 0xffffffffu;
   WarpBits wb; wb.init(stage,gptr,kStageWords);
+  if (MODE == 2) wb.limit = scratch_room(rlen);
   if (rc < 0) code_plain<MODE>(a,stab + kind*256,line,rlen,lossmask,lane,wb,total_bits,plast_out);
   else        code_run<MODE>(a,stab + kind*256,stab + (kind == 0 ? 1 : 5)*256,(uint32_t) rc,line,rlen,lane,
                              queue,wb,total_bits,plast_out);
-  if (MODE == 1)
+  if (MODE >= 1)
     { // final flush incl. the look-ahead padding word (QV.c:436-442)
       __syncwarp();
       const uint32_t full_total = (total_bits + 31u) >> 5;
@@ -231,8 +246,10 @@ __device__ void code_stream(const EncArgs &a, const uint32_t *stab, const uint8_
         }
       uint32_t nst = wb.nst + (wb.cbits ? 1u : 0u) + (want_total > full_total ? 1u : 0u);
       __syncwarp();
-      copy_out<false>(gptr + (size_t) wb.flushed*4u,stage,nst*4u,lane);
+      if ((wb.flushed + nst)*4u <= wb.limit) copy_out<false>(gptr + (size_t) wb.flushed*4u,stage,nst*4u,lane);
+      else                                   wb.ovf = 1;
       __syncwarp();
+      ovf = wb.ovf;
     }
 }
 
@@ -325,16 +342,18 @@ k_qv_code(EncArgs a)
           for (int k = 0; k <= s; k++) o += a.bytes[e*6 + k];
           gptr = a.out + o;
         }
+      if (MODE == 2) gptr = a.out + scratch_off(a,e,s,rlen);
       if (s == 1)
-        { uint32_t kept = code_tags<MODE>(a,l0,line,rlen,lane,stage,gptr);
-          if (MODE == 0 && lane == 0) a.bytes[e*6 + 2] = (kept + 3u) >> 2;
+        { uint32_t kept = code_tags<(MODE == 0) ? 0 : 1>(a,l0,line,rlen,lane,stage,gptr);   // (rlen+3)/4 bytes at most
+          if (MODE != 1 && lane == 0) a.bytes[e*6 + 2] = (kept + 3u) >> 2;
         }
       else
-        { uint32_t bits, plast;
-          code_stream<MODE>(a,stab,line,rlen,s,lane,stage,queue,gptr,bits,plast);
-          if (MODE == 0 && lane == 0)
+        { uint32_t bits, plast, ovf;
+          code_stream<MODE>(a,stab,line,rlen,s,lane,stage,queue,gptr,bits,plast,ovf);
+          if (MODE != 1 && lane == 0)
             { a.bytes[e*6 + 1 + s] = stream_words(bits,plast,rlen)*4u;
               if (s == 0) a.bytes[e*6] = well_bytes(a,e) + 12u;
+              if (MODE == 2 && ovf) atomicExch(a.ovf,1);
             }
           if (MODE == 1 && s == 0 && lane == 0)
             { // entry header: well-delta bytes, beg, end, qv (dexqv.c:128-139)
@@ -384,6 +403,62 @@ k_qv_offsets(const uint32_t *bytes, int64_t n, int64_t *off)
   if (threadIdx.x == 0) off[n] = (int64_t) carry;
 }
 
+// ---- scratch image -> file image -----------------------------------------------------------------------
+// one warp per (entry, line): the stream k_qv_code<2> left in the scratch image moves to its place
+// behind the entry's header (16-byte stores, source at any alignment); line 0 also writes the header
+struct CompactArgs
+{ const uint8_t  *scratch;
+  const uint8_t  *scratch_end16;
+  QvEntries       ent;
+  const uint32_t *bytes;          // [n][6]
+  const int64_t  *off;            // [n+1]
+  int32_t         lwell_in;
+  uint8_t        *out;
+  unsigned long long *ticket;
+};
+
+__global__ void __launch_bounds__(256)
+k_qv_compact(CompactArgs a)
+{ const int lane = threadIdx.x & 31;
+  const int64_t nunits = a.ent.n * 5;
+  unsigned long long next = 0;
+  if (lane == 0) next = atomicAdd(a.ticket,1ull);
+  while (true)
+    { const int64_t u = (int64_t) __shfl_sync(DX_FULL,next,0);
+      if (u >= nunits) break;
+      if (lane == 0) next = atomicAdd(a.ticket,1ull);
+      const int64_t e = u / 5;
+      const int     s = (int) (u - e*5);
+      const int32_t rlen = a.ent.rlen[e];
+      int64_t o = a.off[e];
+      for (int k = 0; k <= s; k++) o += a.bytes[e*6 + k];
+      const uint32_t n = a.bytes[e*6 + 1 + s];
+      if (s == 0 && lane == 0)
+        { // entry header: well-delta bytes, beg, end, qv (dexqv.c:128-139)
+          uint8_t *h = a.out + a.off[e];
+          int32_t lwell = (e == 0) ? a.lwell_in : a.ent.well[e-1];
+          const int32_t well = a.ent.well[e];
+          while (well - lwell >= 255) { *h++ = 0xff; lwell += 255; }
+          *h++ = (uint8_t) (well - lwell);
+          const int32_t f3[3] = { a.ent.beg[e], a.ent.end[e], a.ent.qv[e] };
+          for (int k = 0; k < 3; k++)
+            for (int b = 0; b < 4; b++)
+              *h++ = (uint8_t) ((uint32_t) f3[k] >> (8*b));
+        }
+      if (n == 0) continue;
+      const uint8_t *src = a.scratch + (a.ent.line0[e] + (int64_t) s*((int64_t) rlen + 1) + 8*(5*e + s));
+      uint8_t *dst = a.out + o;
+      uint32_t head = (16u - (uint32_t) (reinterpret_cast<uintptr_t>(dst) & 15u)) & 15u;
+      if (head > n) head = n;
+      if ((uint32_t) lane < head) dst[lane] = src[lane];
+      const uint32_t nvec = (n - head) >> 4;
+      for (uint32_t i = lane; i < nvec; i += 32)
+        dx_stg16(dst + head + (size_t) i*16,dx_ld16_any(src + head + (size_t) i*16,a.scratch_end16));
+      const uint32_t done = head + nvec*16u;
+      if ((uint32_t) lane < n - done) dst[done + lane] = src[done + lane];
+    }
+}
+
 }  // namespace
 
 int dxk_qv_encode(dx_ctx *ctx, const uint8_t *d_text, size_t text_n, QvEntries ent,
@@ -410,30 +485,64 @@ int dxk_qv_encode(dx_ctx *ctx, const uint8_t *d_text, size_t text_n, QvEntries e
   a.text_end16 = d_text + ((text_n + 15) & ~(size_t) 15);
   a.ent = ent; a.tab = d_tab;
   a.delchar = delchar; a.subchar = subchar; a.lossy = lossy; a.lwell_in = lwell_in;
-  a.bytes = d_bytes; a.off = d_off; a.out = d_out; a.ticket = d_ticket;
+  a.bytes = d_bytes; a.off = d_off; a.out = d_out; a.ovf = NULL; a.ticket = d_ticket;
 
   const int grid = ctx->sm_count * 2;
   const size_t smem1 = 6*256*4 + (size_t) kEncWarps*kWarpWords*4;
   const size_t smem0 = smem1;
   DX_CUDA(ctx,cudaFuncSetAttribute(k_qv_code<0>,cudaFuncAttributeMaxDynamicSharedMemorySize,(int) smem0));
   DX_CUDA(ctx,cudaFuncSetAttribute(k_qv_code<1>,cudaFuncAttributeMaxDynamicSharedMemorySize,(int) smem1));
-
-  DX_PROF_BEGIN(ctx); k_qv_code<0><<<grid,kEncThreads,smem0,ctx->stream>>>(a);
-  DX_LAUNCHED(ctx,"k_qv_size");
-  DX_PROF_BEGIN(ctx); k_qv_offsets<<<1,1024,0,ctx->stream>>>(d_bytes,n,d_off);
-  DX_LAUNCHED(ctx,"k_qv_offsets");
+  DX_CUDA(ctx,cudaFuncSetAttribute(k_qv_code<2>,cudaFuncAttributeMaxDynamicSharedMemorySize,(int) smem1));
 
   int64_t total = 0;
   int32_t lastw = 0;
-  DX_CUDA(ctx,cudaMemcpyAsync(&total,d_off+n,8,cudaMemcpyDeviceToHost,ctx->stream));
-  DX_CUDA(ctx,cudaMemcpyAsync(&lastw,ent.well+(n-1),4,cudaMemcpyDeviceToHost,ctx->stream));
-  DX_CUDA(ctx,cudaStreamSynchronize(ctx->stream));
-  if ((size_t) total > cap)
-    return dx_fail(ctx,DX_E_CAP,"output needs %lld bytes, buffer has %zu",(long long) total,cap);
-
-  a.ticket = d_ticket + 1;
-  DX_PROF_BEGIN(ctx); k_qv_code<1><<<grid,kEncThreads,smem1,ctx->stream>>>(a);
-  DX_LAUNCHED(ctx,"k_qv_emit");
+  bool done = false;
+  if (getenv("DEXB200_TWO_PASS") == NULL)
+    { // code into a scratch image first, then move the streams to where their lengths put them
+      const size_t sbytes = ((text_n + (size_t) n*40 + 15) & ~(size_t) 15) + 32;
+      uint8_t *d_scratch = (uint8_t *) dx_arena_get(ctx,sbytes);
+      int32_t *d_ovf = (int32_t *) dx_arena_get(ctx,16);
+      unsigned long long *d_ticket2 = (unsigned long long *) dx_arena_get(ctx,16);
+      if (!d_scratch || !d_ovf || !d_ticket2) return DX_E_NOMEM;
+      DX_CUDA(ctx,cudaMemsetAsync(d_ovf,0,16,ctx->stream));
+      DX_CUDA(ctx,cudaMemsetAsync(d_ticket2,0,16,ctx->stream));
+      EncArgs b = a;
+      b.out = d_scratch; b.ovf = d_ovf; b.ticket = d_ticket2;
+      DX_PROF_BEGIN(ctx); k_qv_code<2><<<grid,kEncThreads,smem1,ctx->stream>>>(b);
+      DX_LAUNCHED(ctx,"k_qv_emit");
+      DX_PROF_BEGIN(ctx); k_qv_offsets<<<1,1024,0,ctx->stream>>>(d_bytes,n,d_off);
+      DX_LAUNCHED(ctx,"k_qv_offsets");
+      int32_t ovf = 0;
+      DX_CUDA(ctx,cudaMemcpyAsync(&total,d_off+n,8,cudaMemcpyDeviceToHost,ctx->stream));
+      DX_CUDA(ctx,cudaMemcpyAsync(&lastw,ent.well+(n-1),4,cudaMemcpyDeviceToHost,ctx->stream));
+      DX_CUDA(ctx,cudaMemcpyAsync(&ovf,d_ovf,4,cudaMemcpyDeviceToHost,ctx->stream));
+      DX_CUDA(ctx,cudaStreamSynchronize(ctx->stream));
+      if (!ovf)
+        { if ((size_t) total > cap)
+            return dx_fail(ctx,DX_E_CAP,"output needs %lld bytes, buffer has %zu",(long long) total,cap);
+          CompactArgs c;
+          c.scratch = d_scratch; c.scratch_end16 = d_scratch + sbytes - 16;
+          c.ent = ent; c.bytes = d_bytes; c.off = d_off; c.lwell_in = lwell_in; c.out = d_out;
+          c.ticket = d_ticket2 + 1;
+          DX_PROF_BEGIN(ctx); k_qv_compact<<<ctx->sm_count*8,256,0,ctx->stream>>>(c);
+          DX_LAUNCHED(ctx,"k_qv_compact");
+          done = true;
+        }
+    }
+  if (!done)
+    { DX_PROF_BEGIN(ctx); k_qv_code<0><<<grid,kEncThreads,smem0,ctx->stream>>>(a);
+      DX_LAUNCHED(ctx,"k_qv_size");
+      DX_PROF_BEGIN(ctx); k_qv_offsets<<<1,1024,0,ctx->stream>>>(d_bytes,n,d_off);
+      DX_LAUNCHED(ctx,"k_qv_offsets");
+      DX_CUDA(ctx,cudaMemcpyAsync(&total,d_off+n,8,cudaMemcpyDeviceToHost,ctx->stream));
+      DX_CUDA(ctx,cudaMemcpyAsync(&lastw,ent.well+(n-1),4,cudaMemcpyDeviceToHost,ctx->stream));
+      DX_CUDA(ctx,cudaStreamSynchronize(ctx->stream));
+      if ((size_t) total > cap)
+        return dx_fail(ctx,DX_E_CAP,"output needs %lld bytes, buffer has %zu",(long long) total,cap);
+      a.ticket = d_ticket + 1;
+      DX_PROF_BEGIN(ctx); k_qv_code<1><<<grid,kEncThreads,smem1,ctx->stream>>>(a);
+      DX_LAUNCHED(ctx,"k_qv_emit");
+    }
   if (h_entry_off != NULL)
     { if (max_entries < n)
         return dx_fail(ctx,DX_E_CAP,"entry offset array holds %lld, need %lld",

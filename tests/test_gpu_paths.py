@@ -30,6 +30,8 @@ ROUTES = [
     {"DEXB200_NO_FAST": "1", "DEXB200_NO_SPEC": "1"},    # ... with a separate walk of all candidates
     {"DEXB200_EXACT_INDEX": "1"},                        # two-pass position index
     {"DEXB200_EXACT_PACK": "1"},                         # counted symbol lengths, byte-serial packer
+    {"DEXB200_PACK2": "1"},                              # input-centric vectorised 2-bit kernels (scan + bit writer)
+    {"DEXB200_TWO_PASS": "1"},                           # dexqv with a size pass instead of the scratch image
     {"DEXB200_DECODER": "v1"},                           # sequential decode kernels
     {"DEXB200_DECODER": "v4"},                           # CTA-per-entry parallel decoder
 ]
@@ -189,3 +191,26 @@ def test_batched_reads_many(ctx, orc, monkeypatch, env, arrow):
             (L.orc_letter_arrow if arrow else (L.orc_upper_read if upper else L.orc_lower_read))(buf)
             want[src_off[i]: src_off[i] + len(r)] = buf.raw[: len(r)]
         assert back == bytes(want)
+
+
+def test_stream_that_outgrows_its_scratch_room(ctx, orc):
+    """dexqv codes every stream into a scratch image with room for a little more than 8 bits per
+    symbol.  One entry made only of symbols that are rare in the file (escaped: 24 bits each) does
+    not fit and must send the call down the exact route (size pass first)."""
+    rng = np.random.default_rng(11)
+    lengths = [int(x) for x in rng.integers(800, 1500, size=60)]
+    text = synth.make_quiva(11, lengths)
+    lines = text.split(b"\n")
+    # entry 30: insertion and merge QVs drawn uniformly from 60 values that occur nowhere else
+    k = 30 * 6
+    L = len(lines[k + 3])
+    rare = (rng.integers(0, 60, size=L) + 66).astype(np.uint8).tobytes()
+    lines[k + 3] = rare
+    lines[k + 4] = rare[::-1]
+    text = b"\n".join(lines)
+    enc = orc.dexqv(text)
+    ctx.profile(True); ctx.profile_report()
+    assert ctx.dexqv(text) == enc
+    prof = ctx.profile_report(); ctx.profile(False)
+    assert "k_qv_size" in prof and "k_qv_compact" not in prof, sorted(prof)
+    assert ctx.undexqv(enc) == text
