@@ -45,6 +45,7 @@ constexpr int kSW       = kS / 32;              // words per subsequence
 constexpr int kRegion   = kSW + 1;              // 64-bit pairs per lane (one look-ahead pair)
 constexpr int kStage    = 2560;                 // bytes of a warp's output stage
 constexpr int kTail     = 24;                   // longest single step (16-bit code + 8-bit literal)
+constexpr int kFingerBudget = 24;               // two-finger steps per lane beyond which the stream's code counts as slow to synchronise
 
 struct Dec5Args
 { const uint8_t *in;
@@ -181,6 +182,7 @@ __device__ __noinline__ StreamOut decode_stream(const Dec5Args &a, int slot, int
   uint32_t carry = 0;                                 // start state of lane 0 (window relative)
   uint32_t wword = 0;                                 // first stream word of the window
   uint32_t bd = 0, sp = 0, ksum = 0;     // bd: malformed stream seen by the final pass; sp: speculation only
+  bool redecode = false;                 // plain streams: re-synchronise by decoding again (set by the first slow window)
   if (RUN && dst != NULL) fill_line(dst,rc,(uint32_t) rlen,lane);
 
   while (true)
@@ -245,7 +247,7 @@ __device__ __noinline__ StreamOut decode_stream(const Dec5Args &a, int slot, int
         }
 
       // ---- rounds: adopt the predecessor's exit; two fingers until the old path is met ----------
-      uint32_t rounds = 0, restarts = 0;
+      uint32_t rounds = 0, restarts = 0, slow = 0;
       bool giveup = false;
       while (true)
         { int changed = 0;
@@ -284,8 +286,31 @@ __device__ __noinline__ StreamOut decode_stream(const Dec5Args &a, int slot, int
                   if (pa == pb && qa == qb) { n += cb - ca; nk += kb - ka; }
                   else { n = cb; nk = kb; myexit = (pb << 1) | qb; changed = 1; }
                 }
+              else if (redecode)
+                { // a code that synchronises slowly: two fingers would keep the whole warp waiting for
+                  // its unluckiest lane, so decode the subsequence again at full speed instead
+                  uint32_t pos = want >> 1, cnt = 0;
+                  const uint32_t limf = lim - kTail;
+                  while (pos < limf)
+                    { const uint32_t w = win32(D,pos);
+                      uint32_t e = mt[w >> 20];
+                      if (e == 0u) e = long_entry(t2,symtab,w,&sp);
+                      pos += DX_E_LEN(e);
+                      cnt += DX_E_N(e);
+                    }
+                  while (pos < lim)
+                    { const uint32_t w = win32(D,pos);
+                      uint32_t e = mt[w >> 20];
+                      if (e == 0u) e = long_entry(t2,symtab,w,&sp);
+                      pos += DX_E_LEN1(e);
+                      cnt += 1;
+                    }
+                  n = cnt;
+                  if ((pos << 1) != myexit) { myexit = pos << 1; changed = 1; }
+                }
               else
-                { while (pa != pb && min(pa,pb) < lim)
+                { uint32_t steps = 0;
+                  while (pa != pb && min(pa,pb) < lim)
                     { const bool fa = (pa < pb);
                       const uint32_t pos = fa ? pa : pb;
                       const uint32_t w = win32(D,pos);
@@ -293,7 +318,9 @@ __device__ __noinline__ StreamOut decode_stream(const Dec5Args &a, int slot, int
                       if (e == 0u) e = long_entry(t2,symtab,w,&sp);
                       const uint32_t np = pos + DX_E_LEN1(e);
                       if (fa) { pa = np; ca++; } else { pb = np; cb++; }
+                      steps++;
                     }
+                  if (steps > kFingerBudget) slow = 1;
                   if (pa == pb) n += cb - ca;
                   else { n = cb; myexit = pb << 1; changed = 1; }
                 }
@@ -303,6 +330,7 @@ __device__ __noinline__ StreamOut decode_stream(const Dec5Args &a, int slot, int
           if (!__any_sync(DX_FULL,changed)) break;
           if (a.limit != NULL && rounds >= 12u) { giveup = true; break; }
         }
+      if (!RUN && !redecode && __any_sync(DX_FULL,slow != 0)) redecode = true;
       if (giveup)                     // speculative modes: this does not look like a code stream (a false
         { bd = 1;                     // candidate); a true entry given up here is found by the slow path
           res.bytes = wword*4u;
@@ -363,25 +391,35 @@ __device__ __noinline__ StreamOut decode_stream(const Dec5Args &a, int slot, int
                 }
             }
           else
-            { uint32_t ppos = pos, pe = 0;
-              while (cnt < need)
+            { // all lookups but the last ones: up to two symbols each, nothing to check
+              while (cnt + 2u < need)
                 { const uint32_t w = win32(D,pos);
                   uint32_t e = mt[w >> 20];
                   if (e == 0u) e = long_entry(t2,symtab,w,&bd);
                   uint32_t c0 = (e >> 16) & 0xffu;
                   if (e & 0x80u) c0 = (w << DX_E_LEN0(e)) >> 24;      // the literal after the escape
-                  if (DX_E_N(e) > need - cnt) e = (e & ~0x7fu) | (1u << 5) | DX_E_LEN0(e);
                   if (wr)
                     { p[0] = (uint8_t) c0;
                       if (e & 0x40u) p[1] = (uint8_t) (e >> 24);
                     }
-                  ppos = pos; pe = e;
                   pos += DX_E_LEN(e);
                   p   += DX_E_N(e);
                   cnt += DX_E_N(e);
                 }
-              // position of the last item: the second symbol, or the literal of an escape
-              last = ppos + ((pe & 0xc0u) ? DX_E_LEN0(pe) : 0u);
+              // the last one or two symbols, one at a time: `last` is the position of the last item
+              // (the literal of an escape)
+              while (cnt < need)
+                { const uint32_t w = win32(D,pos);
+                  uint32_t e = mt[w >> 20];
+                  if (e == 0u) e = long_entry(t2,symtab,w,&bd);
+                  uint32_t c0 = (e >> 16) & 0xffu;
+                  const uint32_t l0 = DX_E_LEN0(e);
+                  last = pos;
+                  if (e & 0x80u) { c0 = (w << l0) >> 24; last = pos + l0; }
+                  if (wr) p[0] = (uint8_t) c0;
+                  pos += (e & 0x80u) ? l0 + 8u : l0;
+                  p++; cnt++;
+                }
             }
         }
       if (RUN && symtab == 0)
