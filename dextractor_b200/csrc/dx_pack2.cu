@@ -182,7 +182,7 @@ k_fa_pack2(Pack2Args a)
       if (e >= a.ent.n) break;
       if (lane == 0) next = atomicAdd(a.ticket,1ull);
       const int32_t rlen = a.ent.rlen[e];
-      if (a.only_leftover && !(rlen > 0 && (!(a.ent.flag[e] & 8) || a.ent.width[e] < 16))) continue;
+      if (a.only_leftover && !(rlen > 0 && (!(a.ent.flag[e] & 8) || a.ent.width[e] < 32))) continue;
       uint8_t *dst = a.out + a.ent.off[e];
       if (lane == 0)
         { // entry header: well-delta bytes, beg, end, qv | 4 x uint16 SNR (dexta.c:187-198)

@@ -71,10 +71,34 @@ struct Pack3Args
   int32_t lwell_in;
   uint8_t *out;
   int32_t *err;                 // set to 1 when an entry's text is not the lattice it was measured as
-  int32_t *leftover;            // set to 1 when an entry was left to k_fa_pack2 (no lattice / W < 16)
+  int32_t *leftover;            // set to 1 when an entry was left to k_fa_pack2 (no lattice / W < 32)
   unsigned long long *ticket;
 };
 
+// the top `k` bits set, k clamped to 0..32
+__device__ __forceinline__ uint32_t top_mask(int k)
+{ return __funnelshift_rc(0u,0xffffffffu,(uint32_t) max(k,0)); }
+
+// aligned payload word g of an entry <- x (its first byte in the top bits); the first and the last
+// word may be shared with the neighbouring header fields / the next entry, so only their payload
+// bytes are written
+__device__ __forceinline__ void store_word(uint32_t *abase, uint32_t g, uint32_t x, uint32_t skew, uint32_t pend)
+{ const uint32_t v = __byte_perm(x,0u,0x0123);
+  const int lo = (g == 0) ? (int) skew : 0;
+  const int hi = min(4,(int) pend - 4*(int) g);                  // pend = skew + payload bytes
+  if (lo == 0 && hi == 4) abase[g] = v;
+  else
+    { uint8_t *p = reinterpret_cast<uint8_t *>(abase + g);
+      for (int k = lo; k < hi; k++) p[k] = (uint8_t) (v >> (8*k));
+    }
+}
+
+// One warp per entry, one ALIGNED 32-byte block of text per lane per round (two 16-byte loads, no
+// realignment).  On the lattice the block's first symbol index and the place of its (at most one)
+// newline follow from the block's offset; the 32 codes form a 64-bit string from which the newline's
+// slot is cut, and the string is shifted to its bit position in the payload.  A lane stores the words
+// it completes; the partial word at its end goes to the next lane by shuffle (to lane 0 of the next
+// round in a register).
 template <int KIND>
 __global__ void __launch_bounds__(kP3Threads)
 k_fa_pack3(Pack3Args a)
@@ -88,7 +112,7 @@ k_fa_pack3(Pack3Args a)
       if (lane == 0) next = atomicAdd(a.ticket,1ull);
       const int32_t rlen = a.ent.rlen[e];
       const int32_t Wi   = a.ent.width[e];
-      if (rlen > 0 && (!(a.ent.flag[e] & 8) || Wi < 16))
+      if (rlen > 0 && (!(a.ent.flag[e] & 8) || Wi < 32))
         { if (lane == 0) atomicExch(a.leftover,1);
           continue;
         }
@@ -106,88 +130,95 @@ k_fa_pack3(Pack3Args a)
             *h++ = (uint8_t) (f[k >> 2] >> (8*(k & 3)));
         }
       if (rlen <= 0) continue;
-      const uint32_t W = (uint32_t) Wi;
+      const uint32_t W = (uint32_t) Wi, Wp1 = W + 1u;
       const uint32_t clen = ((uint32_t) rlen + 3u) >> 2;
       uint8_t *pay = dst + (a.ent.bytes[e] - clen);
       const uint32_t skew = (uint32_t) (reinterpret_cast<uintptr_t>(pay) & 3u);
       uint32_t *abase = reinterpret_cast<uint32_t *>(pay - skew);
-      const uint32_t nw = (clen + skew + 3u) >> 2;                  // aligned words the payload touches
+      const uint32_t pend = clen + skew;
       const uint8_t *seq = a.text + a.ent.seq[e];
-      uint32_t b = 16u * (uint32_t) lane;                           // first symbol of my payload word
-      uint32_t line = b / W, col = b - line*W;                      // its line and column
-      const uint32_t dline = 512u / W, dcol = 512u - dline*W;
+      const int32_t rend = (int32_t) a.ent.region[e] - 1;           // the final newline (k_fa_measure2 saw it)
+      const int32_t d0 = (int32_t) (reinterpret_cast<uintptr_t>(seq) & 31);
+      const uint8_t *blk = seq - d0 + 32*lane;                      // my block of the round
+      int32_t t0 = 32*lane - d0;                                    // text offset of its byte 0
+      int32_t line; uint32_t col;                                   // t0 = line*(W+1) + col, 0 <= col <= W
+      if (t0 >= 0) { line = (int32_t) ((uint32_t) t0 / Wp1); col = (uint32_t) t0 - (uint32_t) line*Wp1; }
+      else         { line = -1; col = Wp1 - (uint32_t) (-t0); }
+      const uint32_t dline = 1024u / Wp1, dcol = 1024u - dline*Wp1;
       uint32_t carry = 0, bad = 0;
-      // the three 8-byte words around the window of the NEXT round are already in flight
-      const uint8_t *Pn = seq + b + line;                           // text position of symbol b
-      uint2 n0 = make_uint2(0u,0u), n1 = n0, n2 = n0;
-      if ((int32_t) b < rlen)
-        { const uint2 *A8 = reinterpret_cast<const uint2 *>(reinterpret_cast<uintptr_t>(Pn) & ~(uintptr_t) 7);
-          n0 = ld8_guard(A8,a.text_end); n1 = ld8_guard(A8+1,a.text_end); n2 = ld8_guard(A8+2,a.text_end);
-        }
 #pragma unroll 1
-      for (uint32_t j0 = 0; j0 < nw; j0 += 32)
-        { const uint32_t j = j0 + (uint32_t) lane;
-          const int32_t nv = rlen - (int32_t) b;                    // symbols from b on (16 = a full word)
-          const int32_t jn = (int32_t) (W - col);                   // window index of the line's newline
-          const uint8_t *P = Pn;
-          const uint2 q0 = n0, q1 = n1, q2 = n2;
-          b += 512u; line += dline; col += dcol;
-          if (col >= W) { col -= W; line++; }
-          if ((int32_t) b < rlen)
-            { Pn = seq + b + line;
-              const uint2 *A8 = reinterpret_cast<const uint2 *>(reinterpret_cast<uintptr_t>(Pn) & ~(uintptr_t) 7);
-              n0 = ld8_guard(A8,a.text_end); n1 = ld8_guard(A8+1,a.text_end); n2 = ld8_guard(A8+2,a.text_end);
-            }
-          uint32_t val = 0;
-          if (nv > 0)
-            { const uintptr_t PA = reinterpret_cast<uintptr_t>(P);
-              const bool up = (PA & 4) != 0;
-              const uint32_t x0 = up ? q0.y : q0.x, x1 = up ? q1.x : q0.y, x2 = up ? q1.y : q1.x,
-                             x3 = up ? q2.x : q1.y, x4 = up ? q2.y : q2.x;
-              const uint32_t sh = (uint32_t) (PA & 3) * 8u;
-              // window bytes 0..16: A holds bytes k.., B the same one byte further on
-              const uint32_t A0 = __funnelshift_r(x0,x1,sh), A1 = __funnelshift_r(x1,x2,sh),
-                             A2 = __funnelshift_r(x2,x3,sh), A3 = __funnelshift_r(x3,x4,sh),
-                             A4 = x4 >> sh;
-              const uint32_t B0 = __funnelshift_r(A0,A1,8), B1 = __funnelshift_r(A1,A2,8),
-                             B2 = __funnelshift_r(A2,A3,8), B3 = __funnelshift_r(A3,A4,8);
-              const int32_t jb = (jn > 16) ? 128 : 8*jn;
-              const uint32_t M0 = low_mask(jb), M1 = low_mask(jb - 32), M2 = low_mask(jb - 64),
-                             M3 = low_mask(jb - 96);
-              uint32_t R0 = (A0 & M0) | (B0 & ~M0), R1 = (A1 & M1) | (B1 & ~M1),
-                       R2 = (A2 & M2) | (B2 & ~M2), R3 = (A3 & M3) | (B3 & ~M3);
-              if (jn <= nv && __ldg(P + jn) != '\n') bad = 1;       // the lattice says: a newline here
-              if (nv < 16)                                          // last word of the entry
-                { const int vb = 8*nv;
-                  R0 &= low_mask(vb); R1 &= low_mask(vb - 32); R2 &= low_mask(vb - 64); R3 &= low_mask(vb - 96);
+      for (int32_t r0 = -d0; r0 < rend; r0 += 1024)                 // r0 = t0 of lane 0
+        { uint32_t X0 = 0, X1 = 0, X2 = 0, f = 0, nstore = 0, cout = 0;
+          if (t0 < rend)
+            { uint4 q0 = make_uint4(0,0,0,0), q1 = q0;
+              if (blk >= a.text && blk < a.text_end) q0 = dx_ldg16(blk);
+              if (blk + 16 >= a.text && blk + 16 < a.text_end) q1 = dx_ldg16(blk + 16);
+              uint32_t w[8] = { q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w };
+              const int32_t vlo = max(0,-t0), vhi = min(32,rend - t0);
+              const uint32_t ln = (t0 < 0) ? 0u : (uint32_t) line, cl = (t0 < 0) ? 0u : col;
+              if (vlo > 0 || vhi < 32)                              // first / last block: blank what is not mine
+                {
+#pragma unroll
+                  for (int k = 0; k < 8; k++)
+                    w[k] &= low_mask(8*(vhi - 4*k)) & ~low_mask(8*(vlo - 4*k));
                 }
-              if (newline_flags(R0,R1,R2,R3)) bad = 1;              // ... and none among the symbols
-              const uint32_t c0 = codes4_top<KIND>(R0), c1 = codes4_top<KIND>(R1),
-                             c2 = codes4_top<KIND>(R2), c3 = codes4_top<KIND>(R3);
-              val = __byte_perm(__byte_perm(c0,c1,0x0073),__byte_perm(c2,c3,0x0073),0x5410);
-              if (KIND == DX_ARROW && nv < 16)                      // the padding is 0, not code('\0') = 3
-                { uint32_t keep = 0;
-                  for (int m = 0; m < 4; m++)
-                    { const int cnt = min(4,max(0,nv - 4*m));
-                      keep |= ((0xff00u >> (2*cnt)) & 0xffu) << (8*m);
+              const uint32_t b0 = ln*W + cl;                        // symbols before my first byte
+              const int32_t jn = vlo + (int32_t) (W - cl);          // block index of the line's newline
+              const bool hasnl = (jn < vhi);
+              // every newline must be the lattice's, and the lattice's must be there
+              const uint32_t ebit = hasnl ? (0x80u << (8*(jn & 3))) : 0u;
+              const int32_t  ek   = jn >> 2;
+              uint32_t c[8];
+#pragma unroll
+              for (int k = 0; k < 8; k++)
+                { bad |= dx_eq_mask(w[k],'\n') ^ ((k == ek) ? ebit : 0u);
+                  c[k] = codes4_top<KIND>(w[k]);
+                }
+              // symbol i of the block at bits 63-2i, 62-2i of hi:lo
+              uint32_t hi = __byte_perm(__byte_perm(c[2],c[3],0x0037),__byte_perm(c[0],c[1],0x3700),0x7610);
+              uint32_t lo = __byte_perm(__byte_perm(c[6],c[7],0x0037),__byte_perm(c[4],c[5],0x3700),0x7610);
+              if (hasnl)                                            // cut the newline's slot out
+                { const uint32_t mh = top_mask(2*jn), ml = top_mask(2*jn - 32);
+                  const uint32_t h2 = __funnelshift_l(lo,hi,2), l2 = lo << 2;
+                  hi = (hi & mh) | (h2 & ~mh);
+                  lo = (lo & ml) | (l2 & ~ml);
+                }
+              const int32_t nsym = (vhi - vlo) - (hasnl ? 1 : 0);
+              if (vlo > 0 || vhi < 32)
+                { if (vlo >= 16) { hi = lo << (2*vlo - 32); lo = 0; }
+                  else if (vlo > 0) { hi = __funnelshift_l(lo,hi,2*vlo); lo <<= 2*vlo; }
+                  hi &= top_mask(2*nsym); lo &= top_mask(2*nsym - 32);
+                }
+              const uint32_t nbits = 2u * (uint32_t) nsym;
+              const uint32_t s = 2u*b0 + 8u*skew;                   // my bit position in the payload words
+              const uint32_t o = s & 31u;
+              f = s >> 5;
+              X0 = hi >> o; X1 = __funnelshift_r(lo,hi,o); X2 = __funnelshift_r(0u,lo,o);
+              const uint32_t endb = s + nbits;                      // one past my last bit
+              nstore = (endb >> 5) - f;                             // words I complete (0..2)
+              if (endb & 31u)                                       // ... and a partial one at the end
+                { const uint32_t part = (nstore == 0) ? X0 : (nstore == 1) ? X1 : X2;
+                  if (t0 + 32 >= rend) nstore++;                    // the entry ends here: the rest is padding
+                  else
+                    { // a block in the middle holds >= 62 bits, so only the entry's first block (lane 0,
+                      // whose predecessor is the carry register) can end inside the word it starts in
+                      cout = part;
+                      if (nstore == 0 && lane == 0) cout |= carry;
                     }
-                  val &= keep;
                 }
             }
-          // payload word j-1 | j -> aligned word j
-          const uint32_t up1 = __shfl_up_sync(DX_FULL,val,1);
-          const uint32_t prev = (lane == 0) ? carry : up1;
-          carry = __shfl_sync(DX_FULL,val,31);
-          const uint32_t word = __funnelshift_l(prev,val,8u*skew);
-          if (j < nw)
-            { const int lo = (j == 0) ? (int) skew : 0;
-              const int hi = min(4,(int) (clen + skew) - 4*(int) j);
-              if (lo == 0 && hi == 4) abase[j] = word;
-              else
-                { uint8_t *p = reinterpret_cast<uint8_t *>(abase + j);
-                  for (int k = lo; k < hi; k++) p[k] = (uint8_t) (word >> (8*k));
-                }
+          // the partial word my predecessor ended with is the start of my first word
+          uint32_t cin = __shfl_up_sync(DX_FULL,cout,1);
+          if (lane == 0) cin = carry;
+          carry = __shfl_sync(DX_FULL,cout,31);
+          if (t0 < rend)
+            { X0 |= cin;
+              if (nstore > 0) store_word(abase,f,X0,skew,pend);
+              if (nstore > 1) store_word(abase,f+1,X1,skew,pend);
+              if (nstore > 2) store_word(abase,f+2,X2,skew,pend);
             }
+          blk += 1024; t0 += 1024; line += (int32_t) dline; col += dcol;
+          if (col >= Wp1) { col -= Wp1; line++; }
         }
       if (__any_sync(DX_FULL,bad != 0) && lane == 0) atomicExch(a.err,1);
     }
