@@ -1,23 +1,23 @@
 // dx_pack3.cu -- the 2-bit codec for entries whose lines form the usual lattice (every line but the
-// last W characters + '\n', W >= 16): the kernels dx_dexta_* / dx_undexta_* use first.
+// last W characters + '\n'; W >= 32 to pack, >= 16 to unpack): the kernels dx_dexta_* / dx_undexta_* use first.
 //
 // Replaces Number_Read / Number_Arrow + Compress_Read (reference DB.c:393-441, 319-338) behind
 // dexta.c:139-205 / dexar.c:138-211, and Uncompress_Read + Lower_/Upper_Read / Letter_Arrow
 // (DB.c:342-389) with the line wrapping of undexta.c:263-270 / undexar.c:221-228.
 //
-// Both kernels are OUTPUT-centric: on the lattice the text position of symbol b is b + b/W, so a
-// lane can address the 16 symbols of one 32-bit payload word (pack) or the 32 payload bits behind an
-// aligned 16-byte piece of text (unpack) directly.  No warp scans, no bit writer, no staging:
+// On the lattice the text position of symbol b is b + b/W, so both directions can be addressed
+// arithmetically.  No warp scans, no bit writer, no staging in shared memory:
 //
-//   k_fa_pack3    one warp per entry, one payload word per lane per round.  The 17-byte text window
-//                 of the word (16 symbols + at most one newline) comes from three cached 8-byte
-//                 loads and funnel shifts, the newline is squeezed out with byte masks, SWAR
-//                 compares give the codes, and the word leaves through an aligned 32-bit store (the
-//                 payload's byte alignment is absorbed by a shuffle + funnel shift).  Every byte of
-//                 the entry's text is checked on the way: symbols must not be '\n' and every lattice
-//                 position must hold one, so the symbol count k_fa_measure2 derived from the size of
-//                 the entry is PROVEN before the result is used (a mismatch sends the file to the
-//                 exact path).
+//   k_fa_pack3    one warp per entry, one ALIGNED 32-byte block of text per lane per round (two
+//                 16-byte loads, nothing to realign).  The block's first symbol index and the place
+//                 of its (at most one) newline follow from the block's offset; SWAR compares give
+//                 the 32 codes as a 64-bit string, the newline's slot is cut out with two masks, the
+//                 string is shifted to its bit position in the payload, and the lane stores the
+//                 words it completes -- the partial word at its end travels to the next lane by
+//                 shuffle.  Every byte of the entry's text is checked on the way: a newline must sit
+//                 at every lattice position and nowhere else, so the symbol count k_fa_measure2
+//                 derived from the size of the entry is PROVEN before the result is used (a
+//                 mismatch sends the file to the exact path).
 //   k_unpack3     one warp per entry, one aligned 16-byte store per lane per round: 32 payload bits
 //                 from two word loads, the gap for a newline opened with two masks, bit reversal +
 //                 three mask-shift steps spread the sixteen 2-bit codes over the nibbles of two
@@ -51,16 +51,9 @@ __device__ __forceinline__ uint32_t codes4_top(uint32_t w)
   return v * 0x40100401u;                      // byte k's code lands at bits 31-2k..30-2k
 }
 
-// 0x80 flags of the bytes that are '\n', OR-ed over four words (exact per byte)
-__device__ __forceinline__ uint32_t newline_flags(uint32_t a, uint32_t b, uint32_t c, uint32_t d)
-{ return dx_eq_mask(a,'\n') | dx_eq_mask(b,'\n') | dx_eq_mask(c,'\n') | dx_eq_mask(d,'\n'); }
-
 // the low `bits` bits set, bits clamped to 0..32
 __device__ __forceinline__ uint32_t low_mask(int bits)
 { return __funnelshift_lc(0xffffffffu,0u,(uint32_t) max(bits,0)); }
-
-__device__ __forceinline__ uint2 ld8_guard(const uint2 *p, const uint8_t *end)
-{ return (reinterpret_cast<const uint8_t *>(p + 1) <= end) ? __ldg(p) : make_uint2(0u,0u); }
 
 // ---- pack ----------------------------------------------------------------------------------------------------
 

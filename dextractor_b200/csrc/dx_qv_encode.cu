@@ -87,14 +87,21 @@ __device__ void code_plain(const EncArgs &a, const uint32_t *sym, const uint8_t 
       const uint4 v = nxt;
       nxt = (c + 32 < lw.nchunk) ? dx_ldg16(lw.base + (int64_t) (c + 32)*16) : make_uint4(0,0,0,0);
       const uint32_t valid = lw.valid(c);
-      const uint32_t w[4] = { v.x & lossmask, v.y & lossmask, v.z & lossmask, v.w & lossmask };
+      uint32_t w[4] = { v.x & lossmask, v.y & lossmask, v.z & lossmask, v.w & lossmask };
+      if (valid != 0xffffu)                                // first / last chunk of the line (or none of it):
+        {                                                  // byte 0 has no code (see dxk_qv_encode), so blank
+#pragma unroll
+          for (int q = 0; q < 4; q++)
+            { const uint32_t n4 = (valid >> (4*q)) & 15u;
+              w[q] &= ((n4 & 1u) ? 0xffu : 0u) | ((n4 & 2u) ? 0xff00u : 0u) |
+                      ((n4 & 4u) ? 0xff0000u : 0u) | ((n4 & 8u) ? 0xff000000u : 0u);
+            }
+        }
       uint32_t e[16];
       uint32_t bits = 0, esc = 0;
 #pragma unroll
       for (int i = 0; i < 16; i++)
-        { const uint32_t x = (w[i >> 2] >> ((i & 3)*8)) & 0xffu;
-          uint32_t t = sym[x];
-          if (!((valid >> i) & 1u)) t = 0;
+        { const uint32_t t = sym[__byte_perm(w[i >> 2],0u,0x4440 + (i & 3))];
           e[i] = t;
           bits += E_LEN(t);
           esc  |= t;
@@ -477,6 +484,12 @@ int dxk_qv_encode(dx_ctx *ctx, const uint8_t *d_text, size_t text_n, QvEntries e
   int64_t  *d_off   = (int64_t *)  dx_arena_get(ctx,(size_t) (n+1)*8);
   unsigned long long *d_ticket = (unsigned long long *) dx_arena_get(ctx,16);
   if (!d_tab || !d_bytes || !d_off || !d_ticket) return DX_E_NOMEM;
+  // k_qv_code blanks the bytes of a chunk that lie outside the line and relies on byte 0 having no
+  // code; a NUL inside a line would end the reference's fgets string (QV.c:751-798), so no valid
+  // coding gives it one
+  for (int k = 0; k < 6; k++)
+    if (k != 1 && k != 5 && h_tab->t[k][0] != 0)
+      return dx_fail(ctx,DX_E_CODING,"the coding scheme assigns a code to the NUL byte");
   DX_CUDA(ctx,cudaMemcpyAsync(d_tab,h_tab,sizeof(QvEncTables),cudaMemcpyHostToDevice,ctx->stream));
   DX_CUDA(ctx,cudaMemsetAsync(d_ticket,0,16,ctx->stream));
 
