@@ -91,6 +91,8 @@ def make_quiva_device(seed: int, target_bytes: int, device, well_base: int = 0,
         nl0 = torch.from_numpy(ent_start[a:b] + hlen[a:b]).to(device) + Lc
         for k in range(5):
             text[nl0 + k * (Lc + 1)] = 10
+    # the library runs on its own non-blocking stream: the text must be complete before it is handed over
+    torch.cuda.synchronize(device)
     return text, n, int(L.sum())
 
 
@@ -145,4 +147,5 @@ def make_fasta_device(seed: int, target_bytes: int, device, arrow: bool = False,
             sym = alpha[torch.randint(0, 4, (P,), device=device, generator=gen)]
         text[dst] = sym
         del ent, col, dst, sym
+    torch.cuda.synchronize(device)                   # see make_quiva_device
     return text, n
