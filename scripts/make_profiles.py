@@ -4,7 +4,7 @@ import collections, csv, io, json, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
 G = os.path.join(ROOT, "gpurun_out"); P = os.path.join(ROOT, "profiles")
-alias = {"k_qv_code<1>": "k_qv_emit", "k_qv_code<0>": "k_qv_size", "k_qv_hist<0>": "k_qv_hist_plain",
+alias = {"k_qv_code<1>": "k_qv_emit(file)", "k_qv_code<2>": "k_qv_emit", "k_qv_code<0>": "k_qv_size", "k_qv_hist<0>": "k_qv_hist_plain",
          "k_pred_slots<0>": "k_pred_slots", "k_pred_slots<2>": "k_pred_slots(candidates)"}
 
 def rows_of(path):
@@ -53,5 +53,10 @@ for k in ("k_qv_decode5", "k_qv_code", "k_qv_hist", "k_pred_slots"):
 open(os.path.join(P, f"{tag}_ncu_full_2GB.txt"), "w").write(
     "# ncu --set full --clock-control none --import-source on, same command; key metrics per captured launch\n" + out +
     "\n# warp-stall sample shares (source page)\n" + "\n".join("\n".join(x) for x in stall) + "\n")
+if os.path.exists(os.path.join(G, "prof_pack.ncu-rep")):
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "ncu_metrics.py"), os.path.join(G, "prof_pack.ncu-rep")],
+                         capture_output=True, text=True).stdout
+    open(os.path.join(P, f"{tag}_ncu_full_pack_1GB.txt"), "w").write(
+        "# ncu --set full --clock-control none on: python scripts/ncu_once.py 0.05 1.0 (1 GB .fasta: dexta then undexta)\n" + out)
 print(open(os.path.join(P, f"{tag}_launches_2GB.txt")).read()[:1500])
 print({k: (v["dram_bytes_per_text_byte"], v["avg_us"]) for k, v in tr["kernels"].items()})
