@@ -1669,6 +1669,11 @@ static int undexqv_fast(dx_ctx *ctx, const uint8_t *d_in, size_t n, int upper, u
       if ((rc = dxk_qv_text_len(ctx,(int64_t) N,NULL,pa,d_wpre,NULL,well_in,plen,d_len,d_well,d_flag)) != DX_OK) return rc;
       if ((rc = dxk_scan_u32(ctx,d_len,(int64_t) N,d_opre)) != DX_OK) return rc;
       if ((rc = dxk_qv_build_ent(ctx,(int64_t) N,NULL,pa,d_well,d_opre,d_len,NULL,d_ent,NULL,NULL,NULL)) != DX_OK) return rc;
+      int32_t *h_rlen  = (int32_t *) dx_hpin_get(ctx,N*4);
+      int32_t *h_order = (int32_t *) dx_hpin_get(ctx,N*4);
+      int32_t *d_order = (int32_t *) dx_arena_get(ctx,N*4);
+      if (!h_rlen || !h_order || !d_order) return DX_E_NOMEM;
+      DX_CUDA(ctx,cudaMemcpyAsync(h_rlen,pa.rlen,N*4,cudaMemcpyDeviceToHost,ctx->stream));
       DX_CUDA(ctx,cudaMemcpyAsync(&h_tail->total,d_opre+N,8,cudaMemcpyDeviceToHost,ctx->stream));
       DX_CUDA(ctx,cudaMemcpyAsync(&h_tail->flag,d_flag,4,cudaMemcpyDeviceToHost,ctx->stream));
       DX_CUDA(ctx,cudaStreamSynchronize(ctx->stream));
@@ -1677,8 +1682,16 @@ static int undexqv_fast(dx_ctx *ctx, const uint8_t *d_in, size_t n, int upper, u
       if (h_tail->flag == 2) return dx_fail(ctx,DX_E_FORMAT,"unusable read length in an entry header");
       if ((size_t) h_tail->total > cap)
         return dx_fail(ctx,DX_E_CAP,"output needs %lld bytes, buffer has %zu",(long long) h_tail->total,cap);
-      if ((rc = dxk_qv_decode5(ctx,d_in,n,d_tab4,coding.delchar,coding.subchar,upper,1,(int64_t) N,pa.fs,pa.rlen,
-                               d_ent,d_prefix,plen,d_out,NULL,d_stat1)) != DX_OK) return rc;
+      { size_t k = 0;                                    // tickets: long entries first (they would be the
+        std::vector<std::pair<int32_t,int32_t> > big;    // tail of the launch), the rest in file order
+        for (size_t i = 0; i < N; i++) if (h_rlen[i] >= 32768) big.push_back(std::make_pair(-h_rlen[i],(int32_t) i));
+        std::sort(big.begin(),big.end());
+        for (size_t b = 0; b < big.size(); b++) h_order[k++] = big[b].second;
+        for (size_t i = 0; i < N; i++) if (h_rlen[i] < 32768) h_order[k++] = (int32_t) i;
+      }
+      DX_CUDA(ctx,cudaMemcpyAsync(d_order,h_order,N*4,cudaMemcpyHostToDevice,ctx->stream));
+      if ((rc = dxk_qv_decode5x(ctx,d_in,n,d_tab4,coding.delchar,coding.subchar,upper,1,(int64_t) N,pa.fs,pa.rlen,
+                                d_ent,d_prefix,plen,d_out,NULL,d_stat1,NULL,d_order,NULL)) != DX_OK) return rc;
       DX_CUDA(ctx,cudaMemcpyAsync(&h_tail->flag,d_stat1,4,cudaMemcpyDeviceToHost,ctx->stream));
       DX_CUDA(ctx,cudaStreamSynchronize(ctx->stream));
       ph.mark("decode");
