@@ -134,12 +134,20 @@ int dx_arena_reserve(dx_ctx *ctx, size_t bytes)
 // ---- per-kernel event timing -------------------------------------------------------------------
 
 struct DxProfRec { const char *name; cudaEvent_t a, b; };
-typedef std::vector<DxProfRec> DxProf;
+struct DxProf : std::vector<DxProfRec>
+{ std::vector<cudaEvent_t> pool;                    // events of earlier reports, reused
+  cudaEvent_t get()
+  { cudaEvent_t e;
+    if (!pool.empty()) { e = pool.back(); pool.pop_back(); }
+    else cudaEventCreate(&e);
+    return e;
+  }
+};
 
 void dx_prof_begin(dx_ctx *ctx)
 { DxProf *pv = (DxProf *) ctx->prof;
   DxProfRec r; r.name = NULL;
-  cudaEventCreate(&r.a); cudaEventCreate(&r.b);
+  r.a = pv->get(); r.b = pv->get();
   cudaEventRecord(r.a,ctx->stream);
   pv->push_back(r);
 }
@@ -174,7 +182,7 @@ extern "C" int dx_profile_report(dx_ctx *ctx, char *buf, size_t cap)
           if (k == acc.size()) acc.push_back(Acc{r.name,0,0.0});
           acc[k].calls += 1; acc[k].ms += ms;
         }
-      cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+      pv->pool.push_back(r.a); pv->pool.push_back(r.b);
     }
   pv->clear();
   size_t at = 0;
@@ -224,6 +232,7 @@ extern "C" void dx_close(dx_ctx *ctx)
     { DxPinExtra *e = (DxPinExtra *) ctx->hpin_extra; ctx->hpin_extra = e->next; cudaFreeHost(e->p); free(e); }
   if (ctx->prof)
     { char tmp[16]; ctx->prof_on = 0; dx_profile_report(ctx,tmp,sizeof(tmp));
+      for (cudaEvent_t e : ((DxProf *) ctx->prof)->pool) cudaEventDestroy(e);
       delete (DxProf *) ctx->prof;
     }
   cudaStreamDestroy(ctx->stream);
@@ -917,18 +926,18 @@ static int qv_frame(dx_ctx *ctx, const uint8_t *d_text, size_t n, uint64_t *totc
 
   int64_t *d_nl = NULL, nlines = 0;
   if ((rc = dxk_index_positions(ctx,DX_PRED_NEWLINE,d_text,n,0,&d_nl,&nlines)) != DX_OK) return rc;
-  int64_t last = -1;
-  if (nlines > 0)
-    { DX_CUDA(ctx,cudaMemcpyAsync(&last,d_nl+nlines-1,8,cudaMemcpyDeviceToHost,ctx->stream));
-      DX_CUDA(ctx,cudaStreamSynchronize(ctx->stream));
-    }
-  if (last != (int64_t) n - 1)
-    { ctx->err_line = nlines + 1;
-      return dx_fail(ctx,DX_E_FORMAT,"Line %lld: Last line does not end with a newline !",
-                     (long long) nlines + 1);
-    }
-  if (nlines % 6 != 0)
-    { ctx->err_line = nlines + 1;
+  // the text must end with a newline; in the usual case (complete entries) k_qv_entries reports the
+  // last newline together with its other results, so there is no extra round trip for it
+  if (nlines % 6 != 0 || nlines == 0)
+    { int64_t last = -1;
+      if (nlines > 0)
+        { DX_CUDA(ctx,cudaMemcpyAsync(&last,d_nl+nlines-1,8,cudaMemcpyDeviceToHost,ctx->stream));
+          DX_CUDA(ctx,cudaStreamSynchronize(ctx->stream));
+        }
+      ctx->err_line = nlines + 1;
+      if (last != (int64_t) n - 1)
+        return dx_fail(ctx,DX_E_FORMAT,"Line %lld: Last line does not end with a newline !",
+                       (long long) nlines + 1);
       return dx_fail(ctx,DX_E_FORMAT,"Line %lld: incomplete last entry of .quiv file",
                      (long long) nlines + 1);
     }
@@ -953,7 +962,13 @@ static int qv_frame(dx_ctx *ctx, const uint8_t *d_text, size_t n, uint64_t *totc
   ent.flag  = (int32_t *) p;
 
   int32_t err[2];
-  if ((rc = dxk_qv_entries(ctx,d_text,n,d_nl,nlines,ent,err,totchar)) != DX_OK) return rc;
+  int64_t noncanon = 0, last = -1;
+  if ((rc = dxk_qv_entries(ctx,d_text,n,d_nl,nlines,ent,err,totchar,&noncanon,&last)) != DX_OK) return rc;
+  if (last != (int64_t) n - 1)
+    { ctx->err_line = nlines + 1;
+      return dx_fail(ctx,DX_E_FORMAT,"Line %lld: Last line does not end with a newline !",
+                     (long long) nlines + 1);
+    }
   if (err[0] != 0)
     { ctx->err_line = err[1];
       if (err[0] == 5)
@@ -965,8 +980,8 @@ static int qv_frame(dx_ctx *ctx, const uint8_t *d_text, size_t n, uint64_t *totc
 
   // headers the device parser did not recognise as canonical: the host's sscanf decides
   std::vector<int32_t> flag;
-  if ((rc = download(ctx,ent.flag,(size_t) nent,flag)) != DX_OK) return rc;
-  for (int64_t e = 0; e < nent; e++)
+  if (noncanon > 0 && (rc = download(ctx,ent.flag,(size_t) nent,flag)) != DX_OK) return rc;
+  for (int64_t e = 0; e < nent && noncanon > 0; e++)
     { if (!flag[e]) continue;
       int64_t h0 = 0;
       DX_CUDA(ctx,cudaMemcpyAsync(&h0,ent.hdr+e,8,cudaMemcpyDeviceToHost,ctx->stream));

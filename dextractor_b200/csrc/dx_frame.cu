@@ -252,7 +252,8 @@ __device__ bool parse_quiva_header(const uint8_t *t, int64_t p, int64_t end,
 }
 
 __global__ void k_qv_entries(const uint8_t *text, const int64_t *nl, int64_t nent, QvEntries ent,
-                             unsigned long long *err /*[0] first error, [1] total positions*/)
+                             unsigned long long *err /*[0] first error, [1] total positions, [2] headers
+                                                       the host has to parse, [3] offset of the last newline*/)
 { int64_t e = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
   { // total positions of the shard (totChar, QV.c:1005): one atomic per warp
     uint32_t mylen = 0;
@@ -264,6 +265,7 @@ __global__ void k_qv_entries(const uint8_t *text, const int64_t *nl, int64_t nen
     if ((threadIdx.x & 31) == 31 && s) atomicAdd(err+1,s);
   }
   if (e >= nent) return;
+  if (e == nent-1) err[3] = (unsigned long long) nl[6*e+5];
   const int64_t h0 = (e == 0) ? 0 : nl[6*e-1] + 1;
   const int64_t h1 = nl[6*e];
   int64_t len = nl[6*e+1] - h1 - 1;
@@ -282,6 +284,7 @@ __global__ void k_qv_entries(const uint8_t *text, const int64_t *nl, int64_t nen
   bool ok = parse_quiva_header(text,h0,h1,well,beg,en,qv);
   ent.well[e] = well; ent.beg[e] = beg; ent.end[e] = en; ent.qv[e] = qv;
   ent.flag[e] = ok ? 0 : 1;
+  if (!ok) atomicAdd(err+2,1ull);
 }
 
 template <int PRED>
@@ -488,22 +491,26 @@ int dxk_index_positions(dx_ctx *ctx, int pred, const uint8_t *d_buf, size_t n, s
 }
 
 int dxk_qv_entries(dx_ctx *ctx, const uint8_t *d_text, size_t n, const int64_t *d_nl,
-                   int64_t nlines, QvEntries ent, int32_t *h_err, uint64_t *h_totchar)
+                   int64_t nlines, QvEntries ent, int32_t *h_err, uint64_t *h_totchar,
+                   int64_t *h_noncanon, int64_t *h_last_nl)
 { (void) n;
   const int64_t nent = nlines / 6;
-  h_err[0] = 0; h_err[1] = 0; *h_totchar = 0;
+  h_err[0] = 0; h_err[1] = 0; *h_totchar = 0; *h_noncanon = 0; *h_last_nl = -1;
   if (nent == 0) return DX_OK;
-  unsigned long long *d_err = (unsigned long long *) dx_arena_get(ctx,16);
-  if (d_err == NULL) return DX_E_NOMEM;
+  unsigned long long *d_err = (unsigned long long *) dx_arena_get(ctx,32);
+  unsigned long long *res = (unsigned long long *) dx_hpin_get(ctx,32);
+  if (d_err == NULL || res == NULL) return DX_E_NOMEM;
   DX_CUDA(ctx,cudaMemsetAsync(d_err,0xff,8,ctx->stream));
-  DX_CUDA(ctx,cudaMemsetAsync(d_err+1,0,8,ctx->stream));
+  DX_CUDA(ctx,cudaMemsetAsync(d_err+1,0,16,ctx->stream));
+  DX_CUDA(ctx,cudaMemsetAsync(d_err+3,0xff,8,ctx->stream));
   DX_PROF_BEGIN(ctx); k_qv_entries<<<(unsigned) ((nent+255)/256),256,0,ctx->stream>>>(d_text,d_nl,nent,ent,d_err);
   DX_LAUNCHED(ctx,"k_qv_entries");
-  unsigned long long res[2] = { 0, 0 };
-  DX_CUDA(ctx,cudaMemcpyAsync(res,d_err,16,cudaMemcpyDeviceToHost,ctx->stream));
+  DX_CUDA(ctx,cudaMemcpyAsync(res,d_err,32,cudaMemcpyDeviceToHost,ctx->stream));
   DX_CUDA(ctx,cudaStreamSynchronize(ctx->stream));
   const unsigned long long e = res[0];
   *h_totchar = res[1];
+  *h_noncanon = (int64_t) res[2];
+  *h_last_nl = (int64_t) res[3];
   if (e != ~0ull)
     { h_err[0] = (int32_t) (e & 0xff);
       h_err[1] = (int32_t) (e >> 8);        // 1-based line number

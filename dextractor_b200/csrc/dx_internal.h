@@ -128,8 +128,8 @@ enum { DX_PRED_NEWLINE = 0, DX_PRED_FASTA_HDR = 1, DX_PRED_QVCAND = 2, DX_PRED_A
 int dxk_index_positions(dx_ctx *ctx, int pred, const uint8_t *d_buf, size_t n, size_t first,
                         int64_t **d_pos, int64_t *count);
 int dxk_qv_entries(dx_ctx *ctx, const uint8_t *d_text, size_t n, const int64_t *d_nl,
-                   int64_t nlines, QvEntries ent, int32_t *h_err /*[2]: code, line*/,
-                   uint64_t *h_totchar);
+                   int64_t nlines, QvEntries ent, int32_t *h_err, uint64_t *h_totchar,
+                   int64_t *h_noncanon, int64_t *h_last_nl);
 
 // dx_qv_stats.cu
 struct QvProbe                  // device-resident result of the order-dependent prefix rules
