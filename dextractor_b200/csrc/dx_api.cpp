@@ -942,7 +942,7 @@ static int qv_frame(dx_ctx *ctx, const uint8_t *d_text, size_t n, uint64_t *totc
                      (long long) nlines + 1);
     }
   const int64_t nent = nlines / 6;
-  const size_t need = round_up((size_t) nent*8,256)*2 + round_up((size_t) nent*4,256)*6 + 256;
+  const size_t need = round_up((size_t) nent*8,256)*2 + round_up((size_t) nent*4,256)*7 + 256;
   if (ctx->qv_store_cap < need)
     { if (ctx->qv_store) cudaFree(ctx->qv_store);
       ctx->qv_store = NULL; ctx->qv_store_cap = 0;
@@ -959,7 +959,8 @@ static int qv_frame(dx_ctx *ctx, const uint8_t *d_text, size_t n, uint64_t *totc
   ent.beg   = (int32_t *) p; p += round_up((size_t) nent*4,256);
   ent.end   = (int32_t *) p; p += round_up((size_t) nent*4,256);
   ent.qv    = (int32_t *) p; p += round_up((size_t) nent*4,256);
-  ent.flag  = (int32_t *) p;
+  ent.flag  = (int32_t *) p; p += round_up((size_t) nent*4,256);
+  ent.order = (int32_t *) p;
 
   int32_t err[2];
   int64_t noncanon = 0, last = -1;
@@ -1004,6 +1005,7 @@ static int qv_frame(dx_ctx *ctx, const uint8_t *d_text, size_t n, uint64_t *totc
       if ((rc = upload(ctx,ent.end+e,&en,1)) != DX_OK) return rc;
       if ((rc = upload(ctx,ent.qv+e,&qv,1)) != DX_OK) return rc;
     }
+  if ((rc = dxk_ticket_order(ctx,ent.rlen,nent,ent.order)) != DX_OK) return rc;
   ctx->qv_text = d_text; ctx->qv_n = n; ctx->qv_ent = ent;
   return DX_OK;
 }
@@ -1260,22 +1262,28 @@ struct QvPlan
   std::vector<int64_t> ix_fs, ix_end;   // per entry: first stream byte, first byte after the entry
 };
 
-// ticket order for the one-warp-per-entry decoder: the long entries first (they would otherwise be
-// the tail of the launch), the rest in file order
+// Ticket order for the one-warp-per-entry decoder: longest entries first (a warp decodes ~8 entries
+// of a 2 GB file, so whatever is handed out last is the tail of the launch -- it should be short).
+// Counting sort on rlen / 512, file order within a bucket.
+static void ticket_order(const int32_t *rlen, size_t N, int32_t *order)
+{ enum { kBuckets = 512 };
+  size_t count[kBuckets + 1];
+  memset(count,0,sizeof(count));
+  auto bucket = [](int32_t rl) -> int
+    { const int b = (rl <= 0) ? 0 : (int) (rl >> 9);
+      return kBuckets - 1 - (b >= kBuckets ? kBuckets - 1 : b);           // descending length
+    };
+  for (size_t i = 0; i < N; i++) count[bucket(rlen[i]) + 1]++;
+  for (int b = 0; b < kBuckets; b++) count[b+1] += count[b];
+  for (size_t i = 0; i < N; i++) order[count[bucket(rlen[i])]++] = (int32_t) i;
+}
+
 static void lpt_order(const std::vector<CandInfo> &info, std::vector<int32_t> &order)
 { const size_t N = info.size();
-  std::vector<std::pair<int32_t,int32_t> > big;
-  order.clear(); order.reserve(N);
-  for (size_t i = 0; i < N; i++)
-    { const int32_t rl = le32(info[i].field+4) - le32(info[i].field);
-      if (rl >= 32768) big.push_back(std::make_pair(-rl,(int32_t) i));
-    }
-  std::sort(big.begin(),big.end());
-  for (size_t k = 0; k < big.size(); k++) order.push_back(big[k].second);
-  for (size_t i = 0; i < N; i++)
-    { const int32_t rl = le32(info[i].field+4) - le32(info[i].field);
-      if (rl < 32768) order.push_back((int32_t) i);
-    }
+  std::vector<int32_t> rl(N);
+  for (size_t i = 0; i < N; i++) rl[i] = le32(info[i].field+4) - le32(info[i].field);
+  order.resize(N);
+  ticket_order(rl.data(),N,order.data());
 }
 
 struct QvWalkUser
@@ -1697,13 +1705,7 @@ static int undexqv_fast(dx_ctx *ctx, const uint8_t *d_in, size_t n, int upper, u
       if (h_tail->flag == 2) return dx_fail(ctx,DX_E_FORMAT,"unusable read length in an entry header");
       if ((size_t) h_tail->total > cap)
         return dx_fail(ctx,DX_E_CAP,"output needs %lld bytes, buffer has %zu",(long long) h_tail->total,cap);
-      { size_t k = 0;                                    // tickets: long entries first (they would be the
-        std::vector<std::pair<int32_t,int32_t> > big;    // tail of the launch), the rest in file order
-        for (size_t i = 0; i < N; i++) if (h_rlen[i] >= 32768) big.push_back(std::make_pair(-h_rlen[i],(int32_t) i));
-        std::sort(big.begin(),big.end());
-        for (size_t b = 0; b < big.size(); b++) h_order[k++] = big[b].second;
-        for (size_t i = 0; i < N; i++) if (h_rlen[i] < 32768) h_order[k++] = (int32_t) i;
-      }
+      ticket_order(h_rlen,N,h_order);
       DX_CUDA(ctx,cudaMemcpyAsync(d_order,h_order,N*4,cudaMemcpyHostToDevice,ctx->stream));
       if ((rc = dxk_qv_decode5x(ctx,d_in,n,d_tab4,coding.delchar,coding.subchar,upper,1,(int64_t) N,pa.fs,pa.rlen,
                                 d_ent,d_prefix,plen,d_out,NULL,d_stat1,NULL,d_order,NULL)) != DX_OK) return rc;
@@ -1771,13 +1773,7 @@ static int undexqv_fast(dx_ctx *ctx, const uint8_t *d_in, size_t n, int upper, u
   DX_CUDA(ctx,cudaMemcpyAsync(&h_tail->total,d_toff+N,8,cudaMemcpyDeviceToHost,ctx->stream));
   DX_CUDA(ctx,cudaStreamSynchronize(ctx->stream));
   ph.mark("prep");
-  { size_t k = 0;                                        // long entries first, the rest in file order
-    std::vector<std::pair<int32_t,int32_t> > big;
-    for (size_t i = 0; i < N; i++) if (h_rlen[i] >= 32768) big.push_back(std::make_pair(-h_rlen[i],(int32_t) i));
-    std::sort(big.begin(),big.end());
-    for (size_t b = 0; b < big.size(); b++) h_order[k++] = big[b].second;
-    for (size_t i = 0; i < N; i++) if (h_rlen[i] < 32768) h_order[k++] = (int32_t) i;
-  }
+  ticket_order(h_rlen,N,h_order);
   DX_CUDA(ctx,cudaMemcpyAsync(d_order,h_order,N*4,cudaMemcpyHostToDevice,ctx->stream));
   const size_t tmp_n = (size_t) h_tail->total;
   uint8_t *d_tmp = (uint8_t *) dx_arena_get(ctx,tmp_n + 64);

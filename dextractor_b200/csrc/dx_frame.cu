@@ -446,7 +446,45 @@ __global__ void k_field_rlen(const uint8_t *buf, const int64_t *q, int64_t count
   rlen[i] = (int32_t) (load_le32(p+4) - load_le32(p));
 }
 
+
+// ---- ticket order ---------------------------------------------------------------------------------
+// The per-entry kernels hand out work through a ticket counter; whatever is handed out last is the
+// tail of the launch, so tickets go to the longest entries first: a counting sort on rlen / 512
+// (any order inside a bucket).  One CTA; N is tens of thousands.
+constexpr int kOrderBuckets = 512;
+
+__global__ void __launch_bounds__(1024)
+k_ticket_order(const int32_t *rlen, int64_t n, int32_t *order)
+{ __shared__ uint32_t cnt[kOrderBuckets];
+  __shared__ uint32_t start[kOrderBuckets];
+  for (int b = threadIdx.x; b < kOrderBuckets; b += blockDim.x) cnt[b] = 0;
+  __syncthreads();
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x)
+    { const int32_t rl = rlen[i];
+      const int q = (rl <= 0) ? 0 : min(kOrderBuckets - 1,rl >> 9);
+      atomicAdd(&cnt[kOrderBuckets - 1 - q],1u);
+    }
+  __syncthreads();
+  if (threadIdx.x == 0)
+    { uint32_t s = 0;
+      for (int b = 0; b < kOrderBuckets; b++) { start[b] = s; s += cnt[b]; }
+    }
+  __syncthreads();
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x)
+    { const int32_t rl = rlen[i];
+      const int q = (rl <= 0) ? 0 : min(kOrderBuckets - 1,rl >> 9);
+      order[atomicAdd(&start[kOrderBuckets - 1 - q],1u)] = (int32_t) i;
+    }
+}
+
 }  // namespace
+
+int dxk_ticket_order(dx_ctx *ctx, const int32_t *d_rlen, int64_t n, int32_t *d_order)
+{ if (n == 0) return DX_OK;
+  DX_PROF_BEGIN(ctx); k_ticket_order<<<1,1024,0,ctx->stream>>>(d_rlen,n,d_order);
+  DX_LAUNCHED(ctx,"k_ticket_order");
+  return DX_OK;
+}
 
 int dxk_scan_u32(dx_ctx *ctx, const uint32_t *d_in, int64_t n, int64_t *d_prefix)
 { DX_PROF_BEGIN(ctx); k_tile_scan<<<1,1024,0,ctx->stream>>>(d_in,n,d_prefix);

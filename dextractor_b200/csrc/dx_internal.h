@@ -18,6 +18,7 @@ struct QvEntries
   int32_t *rlen;
   int32_t *well, *beg, *end, *qv;
   int32_t *flag;         // 0 ok, 1 header needs the host sscanf path
+  int32_t *order;        // ticket -> entry, longest entries first (NULL: file order)
 };
 
 // Per-entry encode bookkeeping
@@ -127,6 +128,8 @@ void dx_prof_end(dx_ctx *ctx, const char *what);
 enum { DX_PRED_NEWLINE = 0, DX_PRED_FASTA_HDR = 1, DX_PRED_QVCAND = 2, DX_PRED_ARCAND = 3 };
 int dxk_index_positions(dx_ctx *ctx, int pred, const uint8_t *d_buf, size_t n, size_t first,
                         int64_t **d_pos, int64_t *count);
+// order[t] = entry of ticket t, longest first (counting sort on rlen / 512, one CTA)
+int dxk_ticket_order(dx_ctx *ctx, const int32_t *d_rlen, int64_t n, int32_t *d_order);
 int dxk_qv_entries(dx_ctx *ctx, const uint8_t *d_text, size_t n, const int64_t *d_nl,
                    int64_t nlines, QvEntries ent, int32_t *h_err, uint64_t *h_totchar,
                    int64_t *h_noncanon, int64_t *h_last_nl);

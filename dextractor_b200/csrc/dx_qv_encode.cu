@@ -338,8 +338,9 @@ k_qv_code(EncArgs a)
     { const int64_t u = (int64_t) __shfl_sync(DX_FULL,next,0);
       if (u >= nunits) break;
       if (lane == 0) next = atomicAdd(a.ticket,1ull);              // in flight while this unit is coded
-      const int64_t e = u / 5;
-      const int     s = (int) (u - e*5);                           // 0 del 1 tag 2 ins 3 mrg 4 sub
+      const int64_t t = u / 5;
+      const int     s = (int) (u - t*5);                           // 0 del 1 tag 2 ins 3 mrg 4 sub
+      const int64_t e = (a.ent.order != NULL) ? (int64_t) a.ent.order[t] : t;
       const int32_t rlen = a.ent.rlen[e];
       const uint8_t *l0  = a.text + a.ent.line0[e];
       const uint8_t *line = l0 + (int64_t) s*((int64_t) rlen + 1);
@@ -434,8 +435,9 @@ k_qv_compact(CompactArgs a)
     { const int64_t u = (int64_t) __shfl_sync(DX_FULL,next,0);
       if (u >= nunits) break;
       if (lane == 0) next = atomicAdd(a.ticket,1ull);
-      const int64_t e = u / 5;
-      const int     s = (int) (u - e*5);
+      const int64_t t = u / 5;
+      const int     s = (int) (u - t*5);
+      const int64_t e = (a.ent.order != NULL) ? (int64_t) a.ent.order[t] : t;
       const int32_t rlen = a.ent.rlen[e];
       int64_t o = a.off[e];
       for (int k = 0; k <= s; k++) o += a.bytes[e*6 + k];

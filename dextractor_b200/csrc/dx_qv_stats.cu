@@ -220,7 +220,8 @@ k_qv_hist(HistArgs a)
       if (lane == 0) next = atomicAdd(a.ticket,1ull);
       unsigned long long *wd = wide + (size_t) si*C::kBins;
       const int s = a.sidx[si];
-      const int64_t e = u - (int64_t) si*nlines;
+      const int64_t tk = u - (int64_t) si*nlines;
+      const int64_t e = (a.ent.order != NULL) ? (int64_t) a.ent.order[tk] : tk;
       const int32_t rlen = a.ent.rlen[e];
       if (rlen == 0) continue;
       const int lineidx = (s == 0) ? 0 : s + 1;                   // del | tag | ins | mrg | sub
@@ -320,7 +321,8 @@ k_qv_hist_run(HistArgs a)
       if (si >= a.ns) break;
       if (lane == 0) next = atomicAdd(a.ticket,1ull);
       const int s = a.sidx[si];
-      const int64_t e = u - (int64_t) si*nlines;
+      const int64_t tk = u - (int64_t) si*nlines;
+      const int64_t e = (a.ent.order != NULL) ? (int64_t) a.ent.order[tk] : tk;
       const int32_t rlen = a.ent.rlen[e];
       if (rlen == 0) continue;
       const int lineidx = (s == 0) ? 0 : s + 1;                   // del | tag | ins | mrg | sub
