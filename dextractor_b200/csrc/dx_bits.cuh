@@ -92,6 +92,18 @@ struct LaneSink
         stage[widx++] = (uint32_t) (acc >> nacc);
       }
   }
+  // warp-collective, for rounds in which EVERY lane contributed at least 32 bits: each lane then
+  // completes the word it starts in, so the partial word at its end is completed by its upper
+  // neighbour and by nobody else -- one shuffle instead of the segmented scan of finish()
+  __device__ __forceinline__ void finish_wide(WarpBits &wb, int lane)
+  { const uint32_t t = nacc ? (uint32_t) (acc << (32u - nacc)) : 0u;    // my trailing partial word
+    uint32_t before = __shfl_up_sync(DX_FULL,t,1);                       // what is already in my first word
+    if (lane == 0) before = wb.carry;
+    if (before) wb.stage[fw] |= before;
+    wb.carry = __shfl_sync(DX_FULL,t,31);
+    wb.nst = __shfl_sync(DX_FULL,widx,31); wb.cbits = __shfl_sync(DX_FULL,nacc,31);
+  }
+
   // warp-collective: merge the partial words, update the warp state
   __device__ __forceinline__ void finish(WarpBits &wb, int lane)
   { uint32_t t = nacc ? (uint32_t) (acc << (32u - nacc)) : 0u;          // my trailing partial word

@@ -451,29 +451,50 @@ __global__ void k_field_rlen(const uint8_t *buf, const int64_t *q, int64_t count
 // The per-entry kernels hand out work through a ticket counter; whatever is handed out last is the
 // tail of the launch, so tickets go to the longest entries first: a counting sort on rlen / 512
 // (any order inside a bucket).  One CTA; N is tens of thousands.
-constexpr int kOrderBuckets = 512;
+constexpr int kOrderBuckets = 2048;              // rlen / 256, clamped: popular lengths spread over many counters
+
+__device__ __forceinline__ int order_bucket(int32_t rl)
+{ const int q = (rl <= 0) ? 0 : min(kOrderBuckets - 1,rl >> 8);
+  return kOrderBuckets - 1 - q;                    // descending length
+}
 
 __global__ void __launch_bounds__(1024)
 k_ticket_order(const int32_t *rlen, int64_t n, int32_t *order)
 { __shared__ uint32_t cnt[kOrderBuckets];
-  __shared__ uint32_t start[kOrderBuckets];
-  for (int b = threadIdx.x; b < kOrderBuckets; b += blockDim.x) cnt[b] = 0;
+  __shared__ uint32_t wsum[32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int b = threadIdx.x; b < kOrderBuckets; b += 1024) cnt[b] = 0;
   __syncthreads();
-  for (int64_t i = threadIdx.x; i < n; i += blockDim.x)
-    { const int32_t rl = rlen[i];
-      const int q = (rl <= 0) ? 0 : min(kOrderBuckets - 1,rl >> 9);
-      atomicAdd(&cnt[kOrderBuckets - 1 - q],1u);
+  // (eight independent loads in flight per thread: the kernel is one CTA and bound by their latency)
+  for (int64_t i0 = threadIdx.x; i0 < n; i0 += 8*1024)
+    { int32_t r[8];
+#pragma unroll
+      for (int k = 0; k < 8; k++) r[k] = (i0 + k*1024 < n) ? rlen[i0 + k*1024] : -1;
+#pragma unroll
+      for (int k = 0; k < 8; k++) if (i0 + k*1024 < n) atomicAdd(&cnt[order_bucket(r[k])],1u);
     }
   __syncthreads();
-  if (threadIdx.x == 0)
-    { uint32_t s = 0;
-      for (int b = 0; b < kOrderBuckets; b++) { start[b] = s; s += cnt[b]; }
+  // exclusive scan of the counters: two per thread
+  const uint32_t c0 = cnt[2*threadIdx.x], c1 = cnt[2*threadIdx.x + 1];
+  const uint32_t inc = dx_warp_incl_sum(c0 + c1,lane);
+  if (lane == 31) wsum[warp] = inc;
+  __syncthreads();
+  if (warp == 0)
+    { const uint32_t w = wsum[lane];
+      const uint32_t wi = dx_warp_incl_sum(w,lane);
+      wsum[lane] = wi - w;
     }
   __syncthreads();
-  for (int64_t i = threadIdx.x; i < n; i += blockDim.x)
-    { const int32_t rl = rlen[i];
-      const int q = (rl <= 0) ? 0 : min(kOrderBuckets - 1,rl >> 9);
-      order[atomicAdd(&start[kOrderBuckets - 1 - q],1u)] = (int32_t) i;
+  const uint32_t excl = wsum[warp] + inc - (c0 + c1);
+  cnt[2*threadIdx.x] = excl; cnt[2*threadIdx.x + 1] = excl + c0;
+  __syncthreads();
+  for (int64_t i0 = threadIdx.x; i0 < n; i0 += 8*1024)
+    { int32_t r[8];
+#pragma unroll
+      for (int k = 0; k < 8; k++) r[k] = (i0 + k*1024 < n) ? rlen[i0 + k*1024] : -1;
+#pragma unroll
+      for (int k = 0; k < 8; k++)
+        if (i0 + k*1024 < n) order[atomicAdd(&cnt[order_bucket(r[k])],1u)] = (int32_t) (i0 + k*1024);
     }
 }
 

@@ -129,7 +129,8 @@ __device__ void code_plain(const EncArgs &a, const uint32_t *sym, const uint8_t 
               sk.put(wb.stage,E_BITS(t),E_LEN(t));
             }
         }
-      sk.finish(wb,lane);
+      if (__all_sync(DX_FULL,bits >= 32u)) sk.finish_wide(wb,lane);
+      else                                 sk.finish(wb,lane);
     }
   if (MODE == 0) total_bits = dx_warp_sum(mybits);
   else           total_bits = wb.total();
@@ -461,7 +462,16 @@ k_qv_compact(CompactArgs a)
       if (head > n) head = n;
       if ((uint32_t) lane < head) dst[lane] = src[lane];
       const uint32_t nvec = (n - head) >> 4;
-      for (uint32_t i = lane; i < nvec; i += 32)
+      uint32_t i = lane;
+      for ( ; i + 96 < nvec; i += 128)                      // four independent 16-byte moves in flight
+        { const uint4 v0 = dx_ld16_any(src + head + (size_t) i*16,a.scratch_end16),
+                      v1 = dx_ld16_any(src + head + (size_t) (i+32)*16,a.scratch_end16),
+                      v2 = dx_ld16_any(src + head + (size_t) (i+64)*16,a.scratch_end16),
+                      v3 = dx_ld16_any(src + head + (size_t) (i+96)*16,a.scratch_end16);
+          dx_stg16(dst + head + (size_t) i*16,v0);      dx_stg16(dst + head + (size_t) (i+32)*16,v1);
+          dx_stg16(dst + head + (size_t) (i+64)*16,v2); dx_stg16(dst + head + (size_t) (i+96)*16,v3);
+        }
+      for ( ; i < nvec; i += 32)
         dx_stg16(dst + head + (size_t) i*16,dx_ld16_any(src + head + (size_t) i*16,a.scratch_end16));
       const uint32_t done = head + nvec*16u;
       if ((uint32_t) lane < n - done) dst[done + lane] = src[done + lane];
