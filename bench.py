@@ -225,13 +225,21 @@ def main():
         hand-off); the sums are formed locally.  -> (summed statistics, last well of rank-1)"""
         if world == 1:
             return st, 0
-        mine = np.empty(6 * 256 + 3, dtype=np.int64)
+        if "xbuf" not in state:                      # pinned staging + device buffers, allocated once
+            k = 6 * 256 + 3
+            state["xbuf"] = (torch.empty(k, dtype=torch.int64).pin_memory(),
+                             torch.empty(k, dtype=torch.int64, device=dev),
+                             torch.empty(world * k, dtype=torch.int64, device=dev),
+                             torch.empty(world * k, dtype=torch.int64).pin_memory())
+        mine_h, mine_d, allt, all_h = state["xbuf"]
+        mine = mine_h.numpy()
         mine[: 6 * 256] = np.ctypeslib.as_array(st.hist).reshape(-1)
         mine[6 * 256:] = (st.totchar, st.nentries, state["last_well"])
-        t = torch.from_numpy(mine).to(dev)
-        allt = torch.empty(world * mine.size, dtype=torch.int64, device=dev)
-        dist.all_gather_into_tensor(allt, t)
-        hh = allt.view(world, -1).cpu().numpy()
+        mine_d.copy_(mine_h, non_blocking=True)
+        dist.all_gather_into_tensor(allt, mine_d)
+        all_h.copy_(allt, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        hh = all_h.numpy().reshape(world, -1)
         tot = dx.Stats()
         np.ctypeslib.as_array(tot.hist)[:] = hh[:, : 6 * 256].sum(axis=0).reshape(6, 256).astype(np.uint64)
         tot.totchar, tot.nentries = int(hh[:, 6 * 256].sum()), int(hh[:, 6 * 256 + 1].sum())
