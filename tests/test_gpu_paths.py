@@ -214,3 +214,27 @@ def test_stream_that_outgrows_its_scratch_room(ctx, orc):
     prof = ctx.profile_report(); ctx.profile(False)
     assert "k_qv_size" in prof and "k_qv_compact" not in prof, sorted(prof)
     assert ctx.undexqv(enc) == text
+
+
+@pytest.mark.parametrize("width", [16, 17, 31, 32, 33, 47, 63, 64, 65, 80, 127, 128, 129, 1000])
+def test_lattice_kernels_at_every_width(ctx, orc, width):
+    """k_fa_pack3 works on aligned 32-byte blocks with at most one newline each and k_unpack3 on
+    aligned 16-byte pieces of text: line widths around the block sizes, entry lengths around the
+    widths and the 4 / 16 / 32-symbol boundaries, every payload and text alignment (the headers
+    shift them), upper case and non-acgt letters, .fasta and .arrow."""
+    rng = np.random.default_rng(1000 + width)
+    lengths = sorted(set([1, 2, 3, 4, 5, 15, 16, 17, 31, 32, 33, 63, 64, 65, width - 1, width, width + 1,
+                          2 * width - 1, 2 * width, 2 * width + 1, 3 * width + 7, 10 * width, 10 * width + 1]
+                         + [int(x) for x in rng.integers(1, 40 * width + 5, size=40)]))
+    lengths = [x for x in lengths if x > 0]
+    rng.shuffle(lengths)
+    fasta = synth.make_fasta(width, lengths, width=width, alphabet=b"acgtACGTnN")
+    enc = orc.dexta(fasta)
+    assert ctx.dexta(fasta) == enc
+    for w in (width, 80):
+        assert ctx.undexta(enc, width=w) == orc.undexta(enc, width=w), w
+    assert ctx.undexta(enc, width=width, upper=True) == orc.undexta(enc, width=width, upper=True)
+    arrow = synth.make_arrow(width, lengths, width=width)
+    enc = orc.dexta(arrow, arrow=True)
+    assert ctx.dexta(arrow, kind=dx.ARROW) == enc
+    assert ctx.undexta(enc, kind=dx.ARROW, width=width) == orc.undexta(enc, arrow=True, width=width)
