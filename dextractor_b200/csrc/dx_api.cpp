@@ -1183,27 +1183,33 @@ static bool build_dec_tables2(const dx_qv_coding *c, QvDecTables2 *t)
   return true;
 }
 
-// 12-bit shared-memory tables for dx_qv_decode4.cu, derived from the reference's 16-bit LUT
-// (build_dec_tables) so that ties resolve exactly as in QV.c:365-372.
+// 12-bit shared-memory tables for the parallel decoders.  A code of at most 12 bits owns the range
+// of 12-bit windows it is a prefix of; filling the ranges in ascending symbol order resolves the
+// ties of a type-2 scheme (symbols folded onto the escape share its code) exactly as the
+// reference's 16-bit LUT does: 255 wins (QV.c:365-372).
 static bool build_dec_tables4(const dx_qv_coding *c, QvDecTables4 *t)
 { memset(t,0,sizeof(*t));
   if (!build_dec_tables2(c,&t->t2)) return false;
-  QvDecTables *full = (QvDecTables *) malloc(sizeof(QvDecTables));
-  if (full == NULL) return false;
-  build_dec_tables(c,full);
   double ab[6], erun[6];
   for (int k = 0; k < 6; k++)
     { const dx_scheme &s = c->tab[k];
       const bool isrun = (k == 1 || k == 5);
+      uint16_t *one = t->single[k];                        // sym | len << 8, 0 = no code of <= 12 bits
+      for (int i = 0; i < 256; i++)
+        { const int len = s.lens[i];
+          if (len <= 0 || len > 12) continue;
+          const uint32_t base = (s.bits[i] << (12 - len)) & 0xfffu;
+          const uint16_t val = (uint16_t) (i | (len << 8));
+          for (uint32_t j = 0; j < (1u << (12 - len)); j++) one[base + j] = val;
+        }
       auto first = [&](uint32_t w16, int &sym, int &len) -> bool
-        { sym = full->look[k][w16]; len = s.lens[sym];
-          if (len <= 0 || len > 16) return false;
-          return (w16 >> (16 - len)) == (s.bits[sym] & ((1u << len) - 1u));
+        { const uint16_t e = one[w16 >> 4];
+          sym = e & 0xff; len = e >> 8;
+          return e != 0;
         };
       for (uint32_t p = 0; p < 4096; p++)
         { int s0, l0;
-          if (!first(p << 4,s0,l0) || l0 > 12) continue;
-          t->single[k][p] = (uint16_t) (s0 | (l0 << 8));
+          if (!first(p << 4,s0,l0)) continue;
           if (isrun) continue;
           if (s.type == 2 && s0 == 255)
             { t->multi[k][p] = (uint32_t) (l0 + 8) | (1u << 5) | 0x80u | ((uint32_t) l0 << 8) | (255u << 16);
@@ -1232,7 +1238,6 @@ static bool build_dec_tables4(const dx_qv_coding *c, QvDecTables4 *t)
           erun[k] += q * (escape ? 400.0 : (double) i);
         }
     }
-  free(full);
   t->abits[0] = (float) (c->delchar >= 0 ? (ab[0] + ab[1]) / (erun[1] + 1.0) : ab[0]);
   t->abits[2] = (float) ab[2];
   t->abits[3] = (float) ab[3];
@@ -1647,12 +1652,23 @@ static int undexqv_fast(dx_ctx *ctx, const uint8_t *d_in, size_t n, int upper, u
   const int plen = (int) strlen(prefix.data());
   QvDecTables4 *h4 = (QvDecTables4 *) dx_hpin_get(ctx,sizeof(QvDecTables4));
   if (h4 == NULL) return DX_E_NOMEM;
-  if (!build_dec_tables4(&coding,h4)) return DX_OK;
   QvDecTables4 *d_tab4 = (QvDecTables4 *) dx_arena_get(ctx,sizeof(QvDecTables4));
   char *d_prefix = (char *) dx_arena_get(ctx,(size_t) plen + 1);
   int32_t *d_flag = (int32_t *) dx_arena_get(ctx,16);
   if (!d_tab4 || !d_prefix || !d_flag) return DX_E_NOMEM;
-  DX_CUDA(ctx,cudaMemcpyAsync(d_tab4,h4,sizeof(QvDecTables4),cudaMemcpyHostToDevice,ctx->stream));
+  // the decode tables are host work (~0.1 ms): with a known entry index they are built while the
+  // planning kernels run
+  bool tables_ok = true;
+  auto make_tables = [&]() -> int
+    { tables_ok = build_dec_tables4(&coding,h4);
+      if (tables_ok)
+        DX_CUDA(ctx,cudaMemcpyAsync(d_tab4,h4,sizeof(QvDecTables4),cudaMemcpyHostToDevice,ctx->stream));
+      return DX_OK;
+    };
+  if (h_entry_off == NULL)
+    { if ((rc = make_tables()) != DX_OK) return rc;
+      if (!tables_ok) return DX_OK;
+    }
   char *h_prefix = (char *) dx_hpin_get(ctx,(size_t) plen + 1);
   if (h_prefix == NULL) return DX_E_NOMEM;
   memcpy(h_prefix,prefix.data(),(size_t) plen + 1);
@@ -1692,6 +1708,7 @@ static int undexqv_fast(dx_ctx *ctx, const uint8_t *d_in, size_t n, int upper, u
       if ((rc = dxk_qv_text_len(ctx,(int64_t) N,NULL,pa,d_wpre,NULL,well_in,plen,d_len,d_well,d_flag)) != DX_OK) return rc;
       if ((rc = dxk_scan_u32(ctx,d_len,(int64_t) N,d_opre)) != DX_OK) return rc;
       if ((rc = dxk_qv_build_ent(ctx,(int64_t) N,NULL,pa,d_well,d_opre,d_len,NULL,d_ent,NULL,NULL,NULL)) != DX_OK) return rc;
+      if ((rc = make_tables()) != DX_OK) return rc;
       int32_t *h_rlen  = (int32_t *) dx_hpin_get(ctx,N*4);
       int32_t *h_order = (int32_t *) dx_hpin_get(ctx,N*4);
       int32_t *d_order = (int32_t *) dx_arena_get(ctx,N*4);
@@ -1701,6 +1718,7 @@ static int undexqv_fast(dx_ctx *ctx, const uint8_t *d_in, size_t n, int upper, u
       DX_CUDA(ctx,cudaMemcpyAsync(&h_tail->flag,d_flag,4,cudaMemcpyDeviceToHost,ctx->stream));
       DX_CUDA(ctx,cudaStreamSynchronize(ctx->stream));
       ph.mark("plan");
+      if (!tables_ok) return DX_OK;                          // tables that need the general path
       if (h_tail->flag == 1) return dx_fail(ctx,DX_E_TRUNC,"compressed image ends inside an entry header");
       if (h_tail->flag == 2) return dx_fail(ctx,DX_E_FORMAT,"unusable read length in an entry header");
       if ((size_t) h_tail->total > cap)
