@@ -191,7 +191,7 @@ def main():
 
     import dextractor_b200 as dx
     from dextractor_b200 import lib as dxl
-    from dextractor_b200 import synth_torch
+    from dextractor_b200 import shards, synth_torch
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -232,21 +232,14 @@ def main():
                              torch.empty(world * k, dtype=torch.int64, device=dev),
                              torch.empty(world * k, dtype=torch.int64).pin_memory())
         mine_h, mine_d, allt, all_h = state["xbuf"]
-        mine = mine_h.numpy()
-        mine[: 6 * 256] = np.ctypeslib.as_array(st.hist).reshape(-1)
-        mine[6 * 256:] = (st.totchar, st.nentries, state["last_well"])
+        mine_h.numpy()[:] = shards.pack_stats(st, state["last_well"])
         mine_d.copy_(mine_h, non_blocking=True)
         dist.all_gather_into_tensor(allt, mine_d)
         all_h.copy_(allt, non_blocking=True)
         torch.cuda.current_stream().synchronize()
-        hh = all_h.numpy().reshape(world, -1)
-        tot = dx.Stats()
-        np.ctypeslib.as_array(tot.hist)[:] = hh[:, : 6 * 256].sum(axis=0).reshape(6, 256).astype(np.uint64)
-        tot.totchar, tot.nentries = int(hh[:, 6 * 256].sum()), int(hh[:, 6 * 256 + 1].sum())
         # the run characters were fixed by the first shard (rank 0 resolves them in its first ~100 k
         # positions) and handed to the other ranks before the loop
-        tot.delchar, tot.subchar = state["rc"]
-        return tot, (int(hh[rank - 1, 6 * 256 + 2]) if rank > 0 else 0)
+        return shards.merge_stats(all_h.numpy(), rank, state["rc"])
 
     def carry_for_rank():
         """rank r > 0 counts run lengths with rank 0's run characters from its first entry on"""
