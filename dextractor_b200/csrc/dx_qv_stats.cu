@@ -454,14 +454,11 @@ int dxk_qv_hist(dx_ctx *ctx, const uint8_t *d_text, QvEntries ent, const QvProbe
       h.efirst[h.ns] = (s == 0) ? h_probe->e_del : h_probe->e_sub;
       h.ns++;
     }
-  static bool attr_done = false;
-  if (!attr_done)
-    { DX_CUDA(ctx,cudaFuncSetAttribute(k_qv_hist<false>,cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int) HistCfg<false>::kSmem));
-      DX_CUDA(ctx,cudaFuncSetAttribute(k_qv_hist_run,cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int) (kRunWarps*kRunWarpWords*4)));
-      attr_done = true;
-    }
+  // (function attributes are per device: set them on every call, a process may hold several contexts)
+  DX_CUDA(ctx,cudaFuncSetAttribute(k_qv_hist<false>,cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int) HistCfg<false>::kSmem));
+  DX_CUDA(ctx,cudaFuncSetAttribute(k_qv_hist_run,cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int) (kRunWarps*kRunWarpWords*4)));
   if (plain.ns > 0)
     { DX_PROF_BEGIN(ctx);
       k_qv_hist<false><<<ctx->sm_count,HistCfg<false>::kThreads,HistCfg<false>::kSmem,ctx->stream>>>(plain);
