@@ -189,6 +189,86 @@ k_tile_scan(const uint32_t *count, int64_t ntiles, int64_t *prefix)
   if (threadIdx.x == 0) prefix[ntiles] = (int64_t) carry;
 }
 
+// ... the same scan over several CTAs, for more than a few thousand values: a tile of 8192 values per
+// CTA (tiles handed out by a ticket, so a tile's predecessors are always running or done), every
+// tile publishes its total as soon as it has it, and a tile's base is the sum of its predecessors'
+// totals, gathered 32 at a time by its first warp.  No tile waits for anything but that first phase
+// of earlier tiles.  state: [0] ticket, [1 + t] total of tile t | 1 << 63 once published (zeroed).
+constexpr int kChainItems = 8;
+constexpr int kChainTile  = 1024 * kChainItems;    // with the usual 1024 threads (tests run it with 32)
+
+__global__ void __launch_bounds__(1024)
+k_chain_scan(const uint32_t *count, int64_t n, int64_t *prefix, unsigned long long *state)
+{ __shared__ uint64_t wsum[32];
+  __shared__ uint64_t s_base, s_total;
+  __shared__ unsigned long long s_tile;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned long long kReady = 1ull << 63;
+  if (threadIdx.x == 0) s_tile = atomicAdd(&state[0],1ull);
+  __syncthreads();
+  const int64_t t = (int64_t) s_tile;
+  const int64_t tile = (int64_t) blockDim.x * kChainItems;
+  const int nwarp = (int) (blockDim.x >> 5);
+  const int64_t i0 = t * tile + (int64_t) threadIdx.x * kChainItems;
+  uint32_t c[kChainItems];
+  uint64_t v = 0;
+#pragma unroll
+  for (int k = 0; k < kChainItems; k++) { c[k] = (i0 + k < n) ? count[i0 + k] : 0u; v += c[k]; }
+  const uint64_t inc = dx_warp_incl_sum64(v,lane);
+  if (lane == 31) wsum[warp] = inc;
+  __syncthreads();
+  if (warp == 0)
+    { const uint64_t w = (lane < nwarp) ? wsum[lane] : 0ull;
+      const uint64_t wi = dx_warp_incl_sum64(w,lane);
+      wsum[lane] = wi - w;                          // exclusive over warps
+      if (lane == 31)
+        { s_total = wi;
+          *reinterpret_cast<volatile unsigned long long *>(&state[1 + t]) = (unsigned long long) wi | kReady;
+        }
+    }
+  __syncthreads();
+  if (warp == 0)                                    // base = totals of tiles 0 .. t-1
+    { uint64_t base = 0;
+      for (int64_t p0 = 0; p0 < t; p0 += 32)
+        { const int64_t p = p0 + lane;
+          unsigned long long f = kReady;
+          if (p < t)
+            do f = *reinterpret_cast<volatile unsigned long long *>(&state[1 + p]); while (!(f & kReady));
+          base += (p < t) ? (uint64_t) (f & ~kReady) : 0ull;
+        }
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) base += __shfl_xor_sync(DX_FULL,base,d);
+      if (lane == 0) s_base = base;
+    }
+  __syncthreads();
+  uint64_t excl = s_base + wsum[warp] + inc - v;
+#pragma unroll
+  for (int k = 0; k < kChainItems; k++)
+    { if (i0 + k < n) prefix[i0 + k] = (int64_t) excl;
+      excl += c[k];
+    }
+  if ((t + 1) * tile >= n && threadIdx.x == 0) prefix[n] = (int64_t) (s_base + s_total);
+}
+
+// exclusive scan of n 32-bit values into 64-bit offsets, total at prefix[n]
+static int launch_scan(dx_ctx *ctx, const uint32_t *d_in, int64_t n, int64_t *d_prefix, const char *what)
+{ const bool small_tiles = (getenv("DEXB200_CHAIN_SCAN") != NULL);       // tests: tiles of 256 values
+  if (n == 0 || (n <= 2*kChainTile && !small_tiles))
+    { DX_PROF_BEGIN(ctx); k_tile_scan<<<1,1024,0,ctx->stream>>>(d_in,n,d_prefix);
+      DX_LAUNCHED(ctx,what);
+      return DX_OK;
+    }
+  const int threads = small_tiles ? 32 : 1024;
+  const int64_t tile = (int64_t) threads * kChainItems;
+  const int64_t ntile = (n + tile - 1) / tile;
+  unsigned long long *d_state = (unsigned long long *) dx_arena_get(ctx,(size_t) (ntile + 1)*8);
+  if (d_state == NULL) return DX_E_NOMEM;
+  DX_CUDA(ctx,cudaMemsetAsync(d_state,0,(size_t) (ntile + 1)*8,ctx->stream));
+  DX_PROF_BEGIN(ctx); k_chain_scan<<<(unsigned) ntile,threads,0,ctx->stream>>>(d_in,n,d_prefix,d_state);
+  DX_LAUNCHED(ctx,what);
+  return DX_OK;
+}
+
 template <int PRED>
 __global__ void __launch_bounds__(kTileThreads)
 k_pred_write(const uint8_t *buf, size_t n, size_t first, const int64_t *tile_prefix, int64_t *pos)
@@ -298,8 +378,9 @@ int index_positions_exact(dx_ctx *ctx, const uint8_t *buf, size_t n, size_t firs
   if (d_cnt == NULL || d_pre == NULL) return DX_E_NOMEM;
   DX_PROF_BEGIN(ctx); k_pred_count<PRED><<<(unsigned) ntiles,kTileThreads,0,ctx->stream>>>(buf,n,first,d_cnt);
   DX_LAUNCHED(ctx,"k_pred_count");
-  DX_PROF_BEGIN(ctx); k_tile_scan<<<1,1024,0,ctx->stream>>>(d_cnt,ntiles,d_pre);
-  DX_LAUNCHED(ctx,"k_tile_scan");
+  { const int rc = launch_scan(ctx,d_cnt,ntiles,d_pre,"k_tile_scan");
+    if (rc != DX_OK) return rc;
+  }
   int64_t total = 0;
   DX_CUDA(ctx,cudaMemcpyAsync(&total,d_pre+ntiles,8,cudaMemcpyDeviceToHost,ctx->stream));
   DX_CUDA(ctx,cudaStreamSynchronize(ctx->stream));
@@ -388,8 +469,9 @@ int index_positions(dx_ctx *ctx, const uint8_t *buf, size_t n, size_t first,
   DX_PROF_BEGIN(ctx);
   k_pred_slots<PRED><<<(unsigned) ntiles,kTileThreads,0,ctx->stream>>>(buf,n,first,d_cnt,d_slot,d_over);
   DX_LAUNCHED(ctx,"k_pred_slots");
-  DX_PROF_BEGIN(ctx); k_tile_scan<<<1,1024,0,ctx->stream>>>(d_cnt,ntiles,d_pre);
-  DX_LAUNCHED(ctx,"k_tile_scan");
+  { const int rc = launch_scan(ctx,d_cnt,ntiles,d_pre,"k_tile_scan");
+    if (rc != DX_OK) return rc;
+  }
   struct { int64_t total; int32_t over; int32_t pad; } h;
   DX_CUDA(ctx,cudaMemcpyAsync(&h.total,d_pre+ntiles,8,cudaMemcpyDeviceToHost,ctx->stream));
   DX_CUDA(ctx,cudaMemcpyAsync(&h.over,d_over,4,cudaMemcpyDeviceToHost,ctx->stream));
@@ -508,9 +590,7 @@ int dxk_ticket_order(dx_ctx *ctx, const int32_t *d_rlen, int64_t n, int32_t *d_o
 }
 
 int dxk_scan_u32(dx_ctx *ctx, const uint32_t *d_in, int64_t n, int64_t *d_prefix)
-{ DX_PROF_BEGIN(ctx); k_tile_scan<<<1,1024,0,ctx->stream>>>(d_in,n,d_prefix);
-  DX_LAUNCHED(ctx,"k_scan_u32");
-  return DX_OK;
+{ return launch_scan(ctx,d_in,n,d_prefix,"k_scan_u32");
 }
 
 int dxk_cand_context(dx_ctx *ctx, const uint8_t *d_in, size_t n, size_t first, const int64_t *d_q,

@@ -32,6 +32,7 @@ ROUTES = [
     {"DEXB200_EXACT_PACK": "1"},                         # counted symbol lengths, byte-serial packer
     {"DEXB200_PACK2": "1"},                              # input-centric vectorised 2-bit kernels (scan + bit writer)
     {"DEXB200_TWO_PASS": "1"},                           # dexqv with a size pass instead of the scratch image
+    {"DEXB200_CHAIN_SCAN": "1"},                         # the multi-CTA prefix sums also on small arrays
     {"DEXB200_DECODER": "v1"},                           # sequential decode kernels
     {"DEXB200_DECODER": "v4"},                           # CTA-per-entry parallel decoder
 ]
@@ -238,3 +239,18 @@ def test_lattice_kernels_at_every_width(ctx, orc, width):
     enc = orc.dexta(arrow, arrow=True)
     assert ctx.dexta(arrow, kind=dx.ARROW) == enc
     assert ctx.undexta(enc, kind=dx.ARROW, width=width) == orc.undexta(enc, arrow=True, width=width)
+
+
+def test_multi_cta_scan_with_look_back(ctx, orc, monkeypatch):
+    """DEXB200_CHAIN_SCAN runs the multi-CTA prefix sums with tiles of 256 values, so a few hundred
+    entries already span several tiles and exercise the look-back over published tile totals."""
+    monkeypatch.setenv("DEXB200_CHAIN_SCAN", "1")
+    rng = np.random.default_rng(77)
+    fasta = synth.make_fasta(77, [int(x) for x in rng.integers(1, 300, size=1500)])
+    enc = orc.dexta(fasta)
+    assert ctx.dexta(fasta) == enc
+    assert ctx.undexta(enc) == orc.undexta(enc)
+    quiva = synth.make_quiva(78, [int(x) for x in rng.integers(200, 4000, size=700)])
+    enc = orc.dexqv(quiva)
+    assert ctx.dexqv(quiva) == enc
+    assert ctx.undexqv(enc) == quiva
