@@ -412,6 +412,15 @@ k_qv_offsets(const uint32_t *bytes, int64_t n, int64_t *off)
   if (threadIdx.x == 0) off[n] = (int64_t) carry;
 }
 
+// per-entry byte totals (header + 5 streams) for the multi-CTA scan of dx_frame.cu
+__global__ void k_qv_entry_total(const uint32_t *bytes, int64_t n, uint32_t *total)
+{ const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t v = 0;
+  for (int k = 0; k < 6; k++) v += bytes[i*6 + k];
+  total[i] = v;
+}
+
 // ---- scratch image -> file image -----------------------------------------------------------------------
 // one warp per (entry, line): the stream k_qv_code<2> left in the scratch image moves to its place
 // behind the entry's header (16-byte stores, source at any alignment); line 0 also writes the header
@@ -522,6 +531,20 @@ int dxk_qv_encode(dx_ctx *ctx, const uint8_t *d_text, size_t text_n, QvEntries e
   int64_t total = 0;
   int32_t lastw = 0;
   bool done = false;
+  int rc = DX_OK;
+  uint32_t *d_tot = (uint32_t *) dx_arena_get(ctx,(size_t) n*4);
+  if (d_tot == NULL) return DX_E_NOMEM;
+  auto entry_offsets = [&]() -> int                     // exclusive scan of the entries' byte totals
+    { if (n < 16384)                                      // few entries: the one-CTA kernel
+        { DX_PROF_BEGIN(ctx); k_qv_offsets<<<1,1024,0,ctx->stream>>>(d_bytes,n,d_off);
+          DX_LAUNCHED(ctx,"k_qv_offsets");
+          return DX_OK;
+        }
+      DX_PROF_BEGIN(ctx);
+      k_qv_entry_total<<<(unsigned) ((n + 255)/256),256,0,ctx->stream>>>(d_bytes,n,d_tot);
+      DX_LAUNCHED(ctx,"k_qv_offsets");
+      return dxk_scan_u32(ctx,d_tot,n,d_off);
+    };
   if (getenv("DEXB200_TWO_PASS") == NULL)
     { // code into a scratch image first, then move the streams to where their lengths put them
       const size_t sbytes = ((text_n + (size_t) n*40 + 15) & ~(size_t) 15) + 32;
@@ -535,8 +558,7 @@ int dxk_qv_encode(dx_ctx *ctx, const uint8_t *d_text, size_t text_n, QvEntries e
       b.out = d_scratch; b.ovf = d_ovf; b.ticket = d_ticket2;
       DX_PROF_BEGIN(ctx); k_qv_code<2><<<grid,kEncThreads,smem1,ctx->stream>>>(b);
       DX_LAUNCHED(ctx,"k_qv_emit");
-      DX_PROF_BEGIN(ctx); k_qv_offsets<<<1,1024,0,ctx->stream>>>(d_bytes,n,d_off);
-      DX_LAUNCHED(ctx,"k_qv_offsets");
+      if ((rc = entry_offsets()) != DX_OK) return rc;
       int32_t ovf = 0;
       DX_CUDA(ctx,cudaMemcpyAsync(&total,d_off+n,8,cudaMemcpyDeviceToHost,ctx->stream));
       DX_CUDA(ctx,cudaMemcpyAsync(&lastw,ent.well+(n-1),4,cudaMemcpyDeviceToHost,ctx->stream));
@@ -557,8 +579,7 @@ int dxk_qv_encode(dx_ctx *ctx, const uint8_t *d_text, size_t text_n, QvEntries e
   if (!done)
     { DX_PROF_BEGIN(ctx); k_qv_code<0><<<grid,kEncThreads,smem0,ctx->stream>>>(a);
       DX_LAUNCHED(ctx,"k_qv_size");
-      DX_PROF_BEGIN(ctx); k_qv_offsets<<<1,1024,0,ctx->stream>>>(d_bytes,n,d_off);
-      DX_LAUNCHED(ctx,"k_qv_offsets");
+      if ((rc = entry_offsets()) != DX_OK) return rc;
       DX_CUDA(ctx,cudaMemcpyAsync(&total,d_off+n,8,cudaMemcpyDeviceToHost,ctx->stream));
       DX_CUDA(ctx,cudaMemcpyAsync(&lastw,ent.well+(n-1),4,cudaMemcpyDeviceToHost,ctx->stream));
       DX_CUDA(ctx,cudaStreamSynchronize(ctx->stream));
