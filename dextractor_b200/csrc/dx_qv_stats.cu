@@ -68,17 +68,8 @@ k_probe_sub(const uint8_t *text, QvEntries ent, uint64_t tot_in, const uint64_t 
   for ( ; e < ent.n; e++)
     { const int32_t rlen = ent.rlen[e];
       const uint8_t *sub = text + ent.line0[e] + 4*((int64_t) rlen + 1);
-      // most positions hold the same symbol: one shared atomic per distinct symbol of a warp
-      for (int32_t k0 = 0; k0 < rlen; k0 += (int32_t) blockDim.x)
-        { const int32_t k = k0 + (int32_t) threadIdx.x;
-          const bool in = (k < rlen);
-          const uint32_t lanes = __ballot_sync(DX_FULL,in);
-          if (in)
-            { const uint32_t c = sub[k];
-              const uint32_t peers = __match_any_sync(lanes,c);
-              if ((threadIdx.x & 31u) == (uint32_t) (__ffs(peers) - 1)) atomicAdd(&h[c],(uint32_t) __popc(peers));
-            }
-        }
+      for (int32_t k = threadIdx.x; k < rlen; k += blockDim.x)
+        atomicAdd(&h[sub[k]],1u);
       tot += (uint64_t) rlen;
       if (tot >= 100000) { fixed = true; break; }
     }
