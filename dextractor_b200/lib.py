@@ -3,6 +3,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import sys
 import subprocess
 
 import numpy as np
@@ -26,6 +27,15 @@ SYMBOLS = [
     "dx_qv_encode_dev", "dx_dexqv_dev", "dx_dexqv_host", "dx_undexqv_dev", "dx_undexqv_host",
     "dx_undexqv_size_dev", "dx_keep_index", "dx_last_index",
 ]
+
+
+def _wait_for_torch():
+    """The library runs on its own non-blocking stream.  Callers of the *_dev methods here are the
+    tests and bench.py, which make their buffers with torch on torch's current stream: wait for that
+    stream, so that a fill or a copy still in flight cannot race with the library's kernels."""
+    t = sys.modules.get("torch")
+    if t is not None and t.cuda.is_available() and t.cuda.is_initialized():
+        t.cuda.current_stream().synchronize()
 
 
 class DexError(RuntimeError):
@@ -201,6 +211,7 @@ class Context:
 
     def h2d(self, d_dst: int, data: bytes):
         """small synchronous host->device copy on the context's stream"""
+        _wait_for_torch()
         src = np.frombuffer(data, dtype=np.uint8)
         self._check(self.L.dx_h2d(self.h, d_dst, src.ctypes.data, len(data)))
         self.sync()
@@ -256,25 +267,30 @@ class Context:
 
     # ---- device-pointer API ---------------------------------------------------------------------
     def dexta_dev(self, kind, d_text, n, d_out, cap) -> int:
+        _wait_for_torch()
         m = C.c_size_t(0)
         self._check(self.L.dx_dexta_dev(self.h, kind, d_text, n, d_out, cap, C.byref(m)))
         return m.value
 
     def undexta_dev(self, kind, d_in, n, width, upper, d_out, cap) -> int:
+        _wait_for_torch()
         m = C.c_size_t(0)
         self._check(self.L.dx_undexta_dev(self.h, kind, d_in, n, width, int(upper), d_out, cap,
                                           C.byref(m)))
         return m.value
 
     def compress_reads_dev(self, kind, d_src, d_src_off, d_len, nreads, d_dst, d_dst_off):
+        _wait_for_torch()
         self._check(self.L.dx_compress_reads_dev(self.h, kind, d_src, d_src_off, d_len, nreads,
                                                  d_dst, d_dst_off))
 
     def uncompress_reads_dev(self, kind, upper, d_src, d_src_off, d_len, nreads, d_dst, d_dst_off):
+        _wait_for_torch()
         self._check(self.L.dx_uncompress_reads_dev(self.h, kind, int(upper), d_src, d_src_off,
                                                    d_len, nreads, d_dst, d_dst_off))
 
     def qv_scan_dev(self, d_text, n, carry: Carry | None = None) -> Stats:
+        _wait_for_torch()
         st = Stats()
         self._check(self.L.dx_qv_scan_dev(self.h, d_text, n,
                                           C.byref(carry) if carry is not None else None,
@@ -283,6 +299,7 @@ class Context:
 
     def qv_encode_dev(self, d_text, n, coding: Coding, lossy, lwell_in, d_out, cap,
                       want_offsets: int = 0):
+        _wait_for_torch()
         m = C.c_size_t(0)
         lastw = C.c_int32(0)
         offs = np.empty(want_offsets + 1, dtype=np.int64) if want_offsets else None
@@ -293,12 +310,14 @@ class Context:
         return m.value, lastw.value, offs
 
     def dexqv_dev(self, d_text, n, lossy, d_out, cap) -> int:
+        _wait_for_torch()
         m = C.c_size_t(0)
         self._check(self.L.dx_dexqv_dev(self.h, d_text, n, int(lossy), d_out, cap, C.byref(m)))
         return m.value
 
     def undexqv_dev(self, d_in, n, upper, d_out, cap, entry_off: np.ndarray | None = None,
                     well_in: int = 0) -> int:
+        _wait_for_torch()
         m = C.c_size_t(0)
         if entry_off is not None:
             entry_off = np.ascontiguousarray(entry_off, dtype=np.int64)
@@ -321,6 +340,7 @@ class Context:
         return [(r.stream_off, r.end_off, r.text_off, r.rlen, r.well) for r in rows[: cnt.value]]
 
     def undexqv_size_dev(self, d_in, n) -> int:
+        _wait_for_torch()
         m = C.c_size_t(0)
         self._check(self.L.dx_undexqv_size_dev(self.h, d_in, n, C.byref(m)))
         return m.value
