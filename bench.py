@@ -201,10 +201,10 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        # stdout carries ONE JSON line: keep NCCL's own banner ("NCCL version ...", printed to stdout
-        # at NCCL_DEBUG=VERSION, which this image sets) out of it
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # stdout carries ONE JSON line: keep NCCL's own banner out of it ("NCCL version ..." goes to
+        # stdout at NCCL_DEBUG=VERSION and =WARN; this image sets one of them)
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
+            os.environ.pop("NCCL_DEBUG")
         dist.init_process_group("nccl", device_id=dev)
 
     ctx = dx.Context(local)
