@@ -155,3 +155,29 @@ def test_split_entries_balances_bytes_and_handles_more_shards_than_entries():
     assert shards.merge_stats(rows, 2, (50, 63))[1] == 77          # skips the empty shard
     assert shards.merge_stats(rows, 0, (50, 63))[1] == 0
     assert list(shards.shard_offsets([10, 0, 5])) == [0, 10, 10]
+
+
+def test_split_entries_properties():
+    """For any entry layout and shard count: the shards are contiguous, in order, cover every entry
+    and every byte exactly once, and a cut never falls inside an entry."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=200, deadline=None)
+    @given(st.lists(st.integers(min_value=1, max_value=5000), min_size=0, max_size=60),
+           st.integers(min_value=1, max_value=9))
+    def check(sizes, nshards):
+        starts = np.concatenate([[0], np.cumsum(sizes)[:-1]]).astype(np.int64) if sizes else np.zeros(0, np.int64)
+        total = int(sum(sizes))
+        cuts = shards.split_entries(starts, total, nshards)
+        assert len(cuts) == nshards
+        assert cuts[0][0] == 0 and cuts[-1][1] == len(sizes) and cuts[-1][3] == total
+        assert cuts[0][2] == (0 if sizes else total)
+        for (a, b, lo, hi), nxt in zip(cuts, cuts[1:] + [None]):
+            assert a <= b and lo <= hi
+            assert lo == (int(starts[a]) if a < len(sizes) else total)      # cuts sit on entry starts
+            assert hi - lo == int(sum(sizes[a:b]))
+            if nxt is not None:
+                assert nxt[0] == b and nxt[2] == hi
+        assert list(shards.shard_offsets([c[3] - c[2] for c in cuts])) == [c[2] for c in cuts]
+
+    check()
