@@ -170,7 +170,11 @@ int dx_qv_read_coding (const uint8_t *in, size_t n, dx_qv_coding *coding,
  * per entry the well-delta bytes, beg/end/qv, then del | tags | ins | mrg | sub.
  * lwell_in is the well of the entry preceding this shard (0 for the first); last_well returns
  * this shard's last well.  h_entry_off, if not NULL, receives nentries+1 byte offsets of the
- * entries inside d_out (an index the decoder can use; it is not part of the file). */
+ * entries inside d_out (an index the decoder can use; it is not part of the file).
+ * Memory: the streams are first coded into a scratch image of n + 40 bytes per entry taken from the
+ * context's arena, then moved to their offsets (no size pass); a stream that does not fit its room
+ * there takes the exact two-pass route.  A coding that assigns a code to the NUL byte is refused
+ * (DX_E_CODING): NUL cannot occur inside a line the reference reads with fgets (QV.c:751-798). */
 int dx_qv_encode_dev(dx_ctx *ctx, const uint8_t *d_text, size_t n, const dx_qv_coding *coding,
                      int lossy, int32_t lwell_in, uint8_t *d_out, size_t cap, size_t *out_len,
                      int32_t *last_well, int64_t *h_entry_off, int64_t max_entries);
