@@ -541,8 +541,18 @@ def main():
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
                 "roofline": roofline, "path_roofline": path, "cpu_baseline": cpu,
                 "extra": extras}
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
+    # Teardown order matters: the pinned staging buffers of exchange_stats were used on the
+    # library's stream (`ext`), and torch's pinned-memory allocator records an event on every
+    # stream that used a block when the block is freed.  Freed after ctx.close() had destroyed
+    # that stream, the record threw "CUDA error: context is destroyed" from a tensor destructor
+    # and every rank of an N>1 run ended in SIGABRT after printing its line.  So: drop them first.
+    state.clear()
+    import gc
+    gc.collect()
+    torch.cuda.synchronize()
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
     ctx.close()
 
