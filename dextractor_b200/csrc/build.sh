@@ -29,3 +29,9 @@ if [ ! -f ../libdexcompat.so ] || [ dx_compat.cu -nt ../libdexcompat.so ] || [ .
   $NVCC $FLAGS -shared -o ../libdexcompat.so dx_compat.cu -L.. -ldexb200 -Xlinker -rpath -Xlinker '$ORIGIN' -lcudart_static -lpthread -ldl -lrt
   echo "built ../libdexcompat.so"
 fi
+# libdexcompat_i.so: the same symbols under the reference's -DINTERACTIVE error convention (DB.h:28-47):
+# messages into the exported Ebuffer, error values returned instead of exit()
+if [ ! -f ../libdexcompat_i.so ] || [ dx_compat.cu -nt ../libdexcompat_i.so ] || [ ../../include/dexb200.h -nt ../libdexcompat_i.so ]; then
+  $NVCC $FLAGS -DINTERACTIVE -shared -o ../libdexcompat_i.so dx_compat.cu -L.. -ldexb200 -Xlinker -rpath -Xlinker '$ORIGIN' -lcudart_static -lpthread -ldl -lrt
+  echo "built ../libdexcompat_i.so"
+fi

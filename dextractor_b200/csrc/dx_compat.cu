@@ -37,7 +37,30 @@ typedef struct
 
 extern "C" { extern char *Prog_Name; }
 
+// Error convention (DB.h:28-47, QV.h:20-27; SURVEY 8b "Errors").  Batch build (libdexcompat.so):
+// message to stderr, exit(1) (exit(2) for a failed read).  -DINTERACTIVE build (libdexcompat_i.so):
+// the message goes to the exported Ebuffer[1000] (DB.c:42) and the routine returns its documented
+// error value -- NULL for pointers, -1 / -2 / 1 for the integer routines.  Helpers below the entry
+// points report through fatal(); in the interactive build that unwinds to the entry point by a C++
+// exception, which never crosses the C boundary.
+#ifdef INTERACTIVE
+extern "C" { char Ebuffer[1000]; }
+#define DXC_MSG(...)        snprintf(Ebuffer,sizeof(Ebuffer),__VA_ARGS__)
+#define DXC_EXIT(code,ret)  return ret
+#define DXC_TRY             try
+#define DXC_CATCH(ret)      catch (const ShimError &) { return ret; }
+#define DXC_CATCH_VOID      catch (const ShimError &) { return; }
+#else
+#define DXC_MSG(...)        fprintf(stderr,__VA_ARGS__)
+#define DXC_EXIT(code,ret)  exit (code)
+#define DXC_TRY
+#define DXC_CATCH(ret)
+#define DXC_CATCH_VOID
+#endif
+
 namespace {
+
+struct ShimError {};
 
 // ---- tiny kernels for the per-read DB.h calls ---------------------------------------------------------
 __global__ void k_map(uint8_t *s, int n, const uint8_t *table)
@@ -86,9 +109,13 @@ struct Shim
 Shim S;
 
 void fatal(const char *what)
-{ fprintf(stderr,"%s: %s%s%s\n",Prog_Name ? Prog_Name : "dexcompat",what,S.ctx ? ": " : "",
+{ DXC_MSG("%s: %s%s%s\n",Prog_Name ? Prog_Name : "dexcompat",what,S.ctx ? ": " : "",
           S.ctx ? dx_strerror(S.ctx) : "");
+#ifdef INTERACTIVE
+  throw ShimError();
+#else
   exit (1);
+#endif
 }
 
 dx_ctx *gpu()
@@ -193,27 +220,27 @@ char *Prog_Name = NULL;
 // ---- DB.h:235-247 utilities (host, not on the hot path) -------------------------------------------------
 void *Malloc(int64 size, char *mesg)
 { void *p = malloc((size_t) size);
-  if (p == NULL) fprintf(stderr,mesg ? "%s: Out of memory (%s)\n" : "%s: Out of memory\n",Prog_Name,mesg);
+  if (p == NULL) DXC_MSG(mesg ? "%s: Out of memory (%s)\n" : "%s: Out of memory\n",Prog_Name,mesg);
   return p;
 }
 
 void *Realloc(void *p, int64 size, char *mesg)
 { p = realloc(p,(size_t) (size > 0 ? size : 1));
-  if (p == NULL) fprintf(stderr,mesg ? "%s: Out of memory (%s)\n" : "%s: Out of memory\n",Prog_Name,mesg);
+  if (p == NULL) DXC_MSG(mesg ? "%s: Out of memory (%s)\n" : "%s: Out of memory\n",Prog_Name,mesg);
   return p;
 }
 
 char *Strdup(char *string, char *mesg)
 { if (string == NULL) return NULL;
   char *s = strdup(string);
-  if (s == NULL) fprintf(stderr,mesg ? "%s: Out of memory (%s)\n" : "%s: Out of memory\n",Prog_Name,mesg);
+  if (s == NULL) DXC_MSG(mesg ? "%s: Out of memory (%s)\n" : "%s: Out of memory\n",Prog_Name,mesg);
   return s;
 }
 
 FILE *Fopen(char *path, char *mode)
 { if (path == NULL || mode == NULL) return NULL;
   FILE *f = fopen(path,mode);
-  if (f == NULL) fprintf(stderr,"%s: Cannot open %s for '%s'\n",Prog_Name,path,mode);
+  if (f == NULL) DXC_MSG("%s: Cannot open %s for '%s'\n",Prog_Name,path,mode);
   return f;
 }
 
@@ -263,30 +290,31 @@ char *Numbered_Suffix(char *left, int num, char *right)
 // ---- DB.h:255-267: the 2-bit codec and alphabet maps, one read at a time, on the GPU ---------------------
 void Number_Read(char *s)
 { const int n = (int) strlen(s);
-  map_bytes(s,n,T.number);
+  DXC_TRY { map_bytes(s,n,T.number); } DXC_CATCH_VOID
   s[n] = 4;
 }
 
 void Number_Arrow(char *s)
 { const int n = (int) strlen(s);
-  map_bytes(s,n,T.narrow);
+  DXC_TRY { map_bytes(s,n,T.narrow); } DXC_CATCH_VOID
   s[n] = 4;
 }
 
 static void letters(char *s, const uint8_t *table)
 { int n = 0;
   while (s[n] != 4) n++;
-  map_bytes(s,n,table);
+  DXC_TRY { map_bytes(s,n,table); } DXC_CATCH_VOID
   s[n] = '\0';
 }
 
 void Lower_Read(char *s)   { letters(s,T.lower); }
 void Upper_Read(char *s)   { letters(s,T.upper); }
 void Letter_Arrow(char *s) { letters(s,T.larrow); }
-void Change_Read(char *s)  { map_bytes(s,(int) strlen(s),T.change); }
+void Change_Read(char *s)  { DXC_TRY { map_bytes(s,(int) strlen(s),T.change); } DXC_CATCH_VOID }
 
 void Compress_Read(int len, char *s)
 { if (len <= 0) { if (len == 0) s[0] = 0; return; }
+  DXC_TRY {
   dx_ctx *c = gpu();
   const int clen = (len + 3) >> 2;
   need(&S.d_a,&S.cap_a,(size_t) len); need(&S.d_b,&S.cap_b,(size_t) clen);
@@ -296,11 +324,13 @@ void Compress_Read(int len, char *s)
   dx_d2h(c,s,S.d_b,(size_t) clen);
   if (dx_sync(c) != DX_OK) fatal("GPU error");
   if (clen < len) s[len] = 0;                     // what DB.c:329-337 leaves behind
+  } DXC_CATCH_VOID
 }
 
 void Uncompress_Read(int len, char *s)
 { const int clen = (len + 3) >> 2;
   if (clen > 0)
+    DXC_TRY
     { dx_ctx *c = gpu();
       need(&S.d_a,&S.cap_a,(size_t) clen); need(&S.d_b,&S.cap_b,(size_t) 4*clen);
       cudaStream_t st = (cudaStream_t) dx_stream(c);
@@ -309,6 +339,7 @@ void Uncompress_Read(int len, char *s)
       dx_d2h(c,s,S.d_b,(size_t) 4*clen);          // like DB.c:352-362 this may write up to 3 bytes past len
       if (dx_sync(c) != DX_OK) fatal("GPU error");
     }
+    DXC_CATCH_VOID
   s[len] = 4;
 }
 
@@ -321,14 +352,14 @@ int Read_Lines(FILE *input, int nlines)
 { if (S.line == NULL)
     { S.rmax = 50000;
       S.line = (char *) malloc((size_t) 5*S.rmax);
-      if (S.line == NULL) { fprintf(stderr,"%s: Out of memory (Allocating QV entry read buffer)\n",Prog_Name); exit (1); }
+      if (S.line == NULL) { DXC_MSG("%s: Out of memory (Allocating QV entry read buffer)\n",Prog_Name); DXC_EXIT(1,-2); }
     }
   int rlen = 0;
   for (int i = 0; i < nlines; i++)
     { char *dst = S.line + (size_t) i*S.rmax;
       if (fgets(dst,S.rmax,input) == NULL)
         { if (i == 0) return -1;
-          fprintf(stderr,"Line %d: incomplete last entry of .quiv file\n",S.nline);
+          DXC_MSG("Line %d: incomplete last entry of .quiv file\n",S.nline);
           return -2;
         }
       S.nline++;
@@ -336,7 +367,7 @@ int Read_Lines(FILE *input, int nlines)
       while (len > 0 && dst[len-1] != '\n')       // longer than the buffer: grow all five slots and go on
         { const int nmax = S.rmax + S.rmax/2 + 1000;
           char *nl = (char *) malloc((size_t) 5*nmax);
-          if (nl == NULL) { fprintf(stderr,"%s: Out of memory (Reallocating QV entry read buffer)\n",Prog_Name); exit (1); }
+          if (nl == NULL) { DXC_MSG("%s: Out of memory (Reallocating QV entry read buffer)\n",Prog_Name); DXC_EXIT(1,-2); }
           for (int k = 0; k <= i; k++) strcpy(nl + (size_t) k*nmax,S.line + (size_t) k*S.rmax);
           free(S.line); S.line = nl; S.rmax = nmax;
           dst = S.line + (size_t) i*S.rmax;
@@ -344,13 +375,13 @@ int Read_Lines(FILE *input, int nlines)
           len += (int) strlen(dst + len);
         }
       if (len == 0 || dst[len-1] != '\n')
-        { fprintf(stderr,"Line %d: Last line does not end with a newline !\n",S.nline);
+        { DXC_MSG("Line %d: Last line does not end with a newline !\n",S.nline);
           return -2;
         }
       len--;
       if (i == 0) rlen = len;
       else if (len != rlen)
-        { fprintf(stderr,"Line %d: Lines for an entry are not the same length\n",S.nline);
+        { DXC_MSG("Line %d: Lines for an entry are not the same length\n",S.nline);
           return -2;
         }
     }
@@ -376,7 +407,7 @@ int QVcoding_Scan(FILE *input, int num, FILE *temp)
     }
   (void) at;
   if (temp != NULL && !S.text.empty()) fwrite(S.text.data(),1,S.text.size(),temp);
-  run_scan();
+  DXC_TRY { run_scan(); } DXC_CATCH(-1)
   got = S.stats.nentries;
   S.nline += (int) (6*got);
   return (int) got;
@@ -395,11 +426,13 @@ void QVcoding_Scan1(int rlen, char *del, char *tag, char *ins, char *mrg, char *
 
 QVcoding *Create_QVcoding(int lossy)
 { static QVcoding coding;
+  DXC_TRY {
   if (!S.scanned) run_scan();
   dx_qv_coding cd;
   if (dx_qv_make_coding(&S.stats,lossy,&cd) != DX_OK)
-    { fprintf(stderr,"%s: a QV stream has fewer than two distinct symbols\n",Prog_Name); exit (1); }
+    { DXC_MSG("%s: a QV stream has fewer than two distinct symbols\n",Prog_Name); DXC_EXIT(1,NULL); }
   publish(&coding,&cd);
+  } DXC_CATCH(NULL)
   return &coding;
 }
 
@@ -408,7 +441,7 @@ void Write_QVcoding(FILE *output, QVcoding *coding)
   size_t n = 0;
   if (dx_qv_write_coding(dxc(coding),coding->prefix ? coding->prefix : "",
                          coding->prefix ? (int) strlen(coding->prefix) : 0,buf.data(),buf.size(),&n) != DX_OK)
-    fatal("Write_QVcoding");
+    DXC_TRY { fatal("Write_QVcoding"); } DXC_CATCH_VOID
   fwrite(buf.data(),1,n,output);
 }
 
@@ -424,8 +457,8 @@ QVcoding *Read_QVcoding(FILE *input)
   std::vector<char> prefix(100001);
   size_t used = 0;
   if (dx_qv_read_coding(S.dimg.data() + 2,S.dimg.size() - 2,&cd,prefix.data(),(int) prefix.size(),&used) != DX_OK)
-    { fprintf(stderr,"%s: System error, read failed!\n",Prog_Name); exit (2); }
-  publish(&coding,&cd);
+    { DXC_MSG("%s: Could not read the coding scheme (Read_QVcoding)\n",Prog_Name); DXC_EXIT(2,NULL); }
+  DXC_TRY { publish(&coding,&cd); } DXC_CATCH(NULL)
   coding.prefix = strdup(prefix.data());
   fseeko(input,(off_t) (S.dpos0 + (int64_t) used),SEEK_SET);
   S.decoded = false;
@@ -443,22 +476,29 @@ void Free_QVcoding(QVcoding *coding)
 // ---- QV.h: entries ------------------------------------------------------------------------------------------
 int Compress_Next_QVentry(FILE *input, FILE *output, QVcoding *coding, int lossy)
 { const int rlen = Read_Lines(input,5);                      // keep the FILE* where the reference would
-  if (rlen < 0) { if (rlen == -1) fprintf(stderr,"Line %d: incomplete last entry of .quiv file\n",S.nline); exit (1); }
-  if (!S.encoded) run_encode(coding,lossy);
-  emit_entry(output);
+  if (rlen < 0) { if (rlen == -1) DXC_MSG("Line %d: incomplete last entry of .quiv file\n",S.nline); DXC_EXIT(1,-1); }
+  DXC_TRY
+  { if (!S.encoded) run_encode(coding,lossy);
+    emit_entry(output);
+  }
+  DXC_CATCH(-1)
   return rlen;
 }
 
 void Compress_Next_QVentry1(int rlen, char *del, char *tag, char *ins, char *mrg, char *sub,
                             FILE *output, QVcoding *coding, int lossy)
 { (void) rlen; (void) del; (void) tag; (void) ins; (void) mrg; (void) sub;
-  if (!S.encoded) run_encode(coding,lossy);
-  emit_entry(output);
+  DXC_TRY
+  { if (!S.encoded) run_encode(coding,lossy);
+    emit_entry(output);
+  }
+  DXC_CATCH_VOID
 }
 
 int Uncompress_Next_QVentry(FILE *input, char **entry, QVcoding *coding, int rlen)
 { (void) coding;
   if (!S.decoded)
+    DXC_TRY
     { dx_ctx *c = gpu();
       need(&S.d_a,&S.cap_a,S.dimg.size());
       dx_h2d(c,S.d_a,S.dimg.data(),S.dimg.size());
@@ -477,12 +517,13 @@ int Uncompress_Next_QVentry(FILE *input, char **entry, QVcoding *coding, int rle
       if (cnt == 0 && m > 0) fatal("no entry index for this file (general decode path)");
       S.decoded = true;
     }
+    DXC_CATCH(1)
   // which entry starts at the current file position
   const int64_t img = (int64_t) ftello(input) - S.dpos0 + 2;
   size_t lo = 0, hi = S.index.size();
   while (lo < hi) { const size_t mid = (lo + hi)/2; if (S.index[mid].stream_off < img) lo = mid + 1; else hi = mid; }
   if (lo >= S.index.size() || S.index[lo].stream_off != img || S.index[lo].rlen != rlen)
-    { fprintf(stderr,"%s: System error, read failed!\n",Prog_Name); return 1; }
+    { DXC_MSG("%s: Could not read entry (Uncompress_Next_QVentry)\n",Prog_Name); return 1; }
   const dx_index_row &r = S.index[lo];
   for (int e = 0; e < 5; e++)
     memcpy(entry[e],S.dtext.data() + r.text_off + (int64_t) e*(rlen + 1),(size_t) rlen);
