@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 from dextractor_b200 import lib as dxl
-from tests import cases
+from tests import cases, fuzz
 
 QUIVA = dict(cases.quiva_cases())
 
@@ -47,6 +47,18 @@ def test_coding_header_matches_reference_file(orc, name, lossy):
         assert list(cd2.tab[k].lens) == list(cd.tab[k].lens)
         assert list(cd2.tab[k].bits) == list(cd.tab[k].bits)
         assert cd2.tab[k].type == cd.tab[k].type
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_coding_header_of_random_shapes(orc, seed):
+    """the same header check on the randomly shaped files of tests/fuzz.py, lossless and lossy"""
+    text, _ = fuzz.fuzz_quiva(seed)
+    st = stats_from_oracle(orc.qv_scan(text))
+    prefix = text[: text.index(b"/", 1)]
+    for lossy in (False, True):
+        want = orc.dexqv(text, lossy=lossy)
+        hdr = b"\xaa\x55" + dxl.write_coding(dxl.make_coding(st, lossy), prefix)
+        assert want[: len(hdr)] == hdr
 
 
 def test_huffman_tie_breaks_random_histograms(orc):
