@@ -52,12 +52,16 @@ static uint8_t *slurp(dx_ctx *ctx, FILE *f, size_t *n)
    the extension is stripped only if present (compared without case) */
 static char *file_name(const char *arg, const char *strip, const char *ext)
 { size_t la = strlen(arg), ls = strlen(strip);
-  char *out = (char *) malloc(la + strlen(ext) + 8);
+  char *out = (char *) malloc(la + strlen(ext) + 16);
   const char *base = strrchr(arg,'/');
-  base = (base == NULL) ? arg : base+1;
-  strcpy(out,arg);
+  size_t pre = 0;
+  if (base == NULL)                      /* PathTo gives "." for a bare name: "./<root><ext>" */
+    { strcpy(out,"./"); pre = 2; base = arg; }
+  else
+    base = base+1;
+  strcpy(out+pre,arg);
   if (strlen(base) > ls && strcasecmp(arg+la-ls,strip) == 0)
-    out[la-ls] = '\0';
+    out[pre+la-ls] = '\0';
   strcat(out,ext);
   return out;
 }
@@ -124,15 +128,9 @@ int dx_cli_main(const dx_tool *tool, int argc, char *argv[])
   if (o.pipe)
     { o.keep = 1; argc = 2; }
 
-  { int dev = 0;
-    const char *e = getenv("DEXB200_DEVICE");
-    if (e != NULL) dev = atoi(e);
-    if (dx_open(dev,&ctx) != DX_OK) die(NULL,DX_E_NOGPU);
-  }
-
   for (i = 1; i < argc; i++)
     { char *src = NULL, *dst = NULL, *root;
-      FILE *in, *out;
+      FILE *in, *out = NULL;
       uint8_t *h_in, *h_out, *d_in, *d_out = NULL;
       size_t n, m = 0;
       int rc;
@@ -147,9 +145,17 @@ int dx_cli_main(const dx_tool *tool, int argc, char *argv[])
           root = root_name(argv[i],tool->src_ext);
           if ((in = fopen(src,"r")) == NULL)
             { fprintf(stderr,"%s: Cannot open %s for 'r'\n",Prog,src); exit (1); }
-          if ((out = fopen(dst,"w")) == NULL)
-            { fprintf(stderr,"%s: Cannot open %s for 'w'\n",Prog,dst); exit (1); }
         }
+      /* the device is opened once a source is: a missing file is reported the way the reference
+         reports it, and no output file is created when there is no GPU to fill it */
+      if (ctx == NULL)
+        { int dev = 0;
+          const char *e = getenv("DEXB200_DEVICE");
+          if (e != NULL) dev = atoi(e);
+          if (dx_open(dev,&ctx) != DX_OK) die(NULL,DX_E_NOGPU);
+        }
+      if (!o.pipe && (out = fopen(dst,"w")) == NULL)
+        { fprintf(stderr,"%s: Cannot open %s for 'w'\n",Prog,dst); exit (1); }
       if (o.verbose)
         { fprintf(stderr,"Processing '%s' ...\n",root); fflush(stderr); }
 
