@@ -354,38 +354,40 @@ int Read_Lines(FILE *input, int nlines)
       S.line = (char *) malloc((size_t) 5*S.rmax);
       if (S.line == NULL) { DXC_MSG("%s: Out of memory (Allocating QV entry read buffer)\n",Prog_Name); DXC_EXIT(1,-2); }
     }
-  int rlen = 0;
-  for (int i = 0; i < nlines; i++)
-    { char *dst = S.line + (size_t) i*S.rmax;
-      if (fgets(dst,S.rmax,input) == NULL)
-        { if (i == 0) return -1;
-          DXC_MSG("Line %d: incomplete last entry of .quiv file\n",S.nline);
-          return -2;
-        }
-      S.nline++;
-      int len = (int) strlen(dst);
-      while (len > 0 && dst[len-1] != '\n')       // longer than the buffer: grow all five slots and go on
-        { const int nmax = S.rmax + S.rmax/2 + 1000;
-          char *nl = (char *) malloc((size_t) 5*nmax);
-          if (nl == NULL) { DXC_MSG("%s: Out of memory (Reallocating QV entry read buffer)\n",Prog_Name); DXC_EXIT(1,-2); }
-          for (int k = 0; k <= i; k++) strcpy(nl + (size_t) k*nmax,S.line + (size_t) k*S.rmax);
-          free(S.line); S.line = nl; S.rmax = nmax;
-          dst = S.line + (size_t) i*S.rmax;
-          if (fgets(dst + len,S.rmax - len,input) == NULL) break;
-          len += (int) strlen(dst + len);
-        }
-      if (len == 0 || dst[len-1] != '\n')
+  // Observable behaviour of QV.c:751-798, kept to the letter: the line counter moves BEFORE every read
+  // (so it has moved when end of input is met); only the first line may outgrow the buffer, and a
+  // first line cut short by end of input is the "no newline" error; any later line whose length
+  // (newline included) differs from the first -- also a last line without its newline -- is the
+  // "not the same length" error; lines are compared with their newline and the length returned
+  // without it.
+  S.nline++;
+  if (fgets(S.line,S.rmax,input) == NULL) return -1;
+  int len = (int) strlen(S.line);
+  while (S.line[len-1] != '\n')
+    { const int nmax = S.rmax + S.rmax/2 + 1000;               // only slot 0 is live here
+      char *nl = (char *) malloc((size_t) 5*nmax);
+      if (nl == NULL) { DXC_MSG("%s: Out of memory (Reallocating QV entry read buffer)\n",Prog_Name); DXC_EXIT(1,-2); }
+      memcpy(nl,S.line,(size_t) len + 1);
+      free(S.line); S.line = nl; S.rmax = nmax;
+      if (fgets(S.line + len,S.rmax - len,input) == NULL)
         { DXC_MSG("Line %d: Last line does not end with a newline !\n",S.nline);
-          return -2;
+          DXC_EXIT(1,-2);
         }
-      len--;
-      if (i == 0) rlen = len;
-      else if (len != rlen)
+      len += (int) strlen(S.line + len);
+    }
+  for (int i = 1; i < nlines; i++)
+    { char *dst = S.line + (size_t) i*S.rmax;
+      S.nline++;
+      if (fgets(dst,S.rmax,input) == NULL)
+        { DXC_MSG("Line %d: incomplete last entry of .quiv file\n",S.nline);
+          DXC_EXIT(1,-2);
+        }
+      if ((int) strlen(dst) != len)
         { DXC_MSG("Line %d: Lines for an entry are not the same length\n",S.nline);
-          return -2;
+          DXC_EXIT(1,-2);
         }
     }
-  return rlen;
+  return len - 1;
 }
 
 // ---- QV.h: statistics, coding (GPU scan; tables on the host exactly like dx_qv_make_coding) ------------

@@ -82,9 +82,15 @@ def test_read_lines_follows_the_reference(shim, tmp_path):
 
     p.write_bytes(b"abcd\nefgh")
     f = shim.open(p)
-    assert shim.L.Read_Lines(f, 2) == -2                      # QV.c:778-781
-    assert "Last line does not end with a newline" in shim.message()
+    assert shim.L.Read_Lines(f, 2) == -2                      # a LATER line without its newline is
+    assert "not the same length" in shim.message()            # a length error (QV.c:792-795)
     assert shim.L.Read_Lines(f, 1) == -1                      # end of input before any line
+    shim.libc.fclose(f)
+
+    p.write_bytes(b"abcd")
+    f = shim.open(p)
+    assert shim.L.Read_Lines(f, 1) == -2                      # QV.c:778-781: the FIRST line cut short
+    assert "Last line does not end with a newline" in shim.message()
     shim.libc.fclose(f)
 
     p.write_bytes(b"abcd\nefgh\n")
@@ -139,3 +145,135 @@ def test_batch_codec_calls_exit_without_a_gpu(tmp_path):
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
     assert r.returncode == 1 and "survived" not in r.stdout
     assert "no usable CUDA device" in r.stderr
+
+
+def test_path_helpers_match_the_reference(ref):
+    """PathTo / Root / Catenate / Numbered_Suffix (DB.c:112-202) of libdexcompat.so against the
+    reference's own, compiled from DB.c into oracle/_ref/libdbqv_ref.so."""
+    path = os.path.join(ROOT, "oracle", "_ref", "libdbqv_ref.so")
+    if not os.path.exists(path):
+        pytest.skip("oracle/_ref/libdbqv_ref.so not built")
+    R, L = ctypes.CDLL(path), _load("libdexcompat.so")
+    libc = ctypes.CDLL(None)
+    libc.free.argtypes = [ctypes.c_void_p]
+    for lib in (R, L):
+        lib.PathTo.restype = lib.Root.restype = ctypes.c_void_p
+        lib.PathTo.argtypes = [ctypes.c_char_p]
+        lib.Root.argtypes = [ctypes.c_char_p, ctypes.c_char_p]
+        lib.Catenate.restype = lib.Numbered_Suffix.restype = ctypes.c_char_p
+        lib.Catenate.argtypes = [ctypes.c_char_p] * 4
+        lib.Numbered_Suffix.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_char_p]
+
+    def owned(lib, fn, *a):
+        # the helpers edit their argument in place for a moment (DB.c:118-121): give them a buffer
+        bufs = [ctypes.create_string_buffer(x) if isinstance(x, bytes) else x for x in a]
+        p = getattr(lib, fn)(*[ctypes.cast(b, ctypes.c_char_p) if b is not None else None for b in bufs])
+        if not p:
+            return None
+        s = ctypes.string_at(p)
+        libc.free(p)
+        return s
+
+    names = [b"x", b"x.fasta", b"x.FASTA", b"dir/x.fasta", b"/x.fasta", b"/abs/dir.d/x.y.z", b".fasta",
+             b"a.fasta.fasta", b"dir.fasta/x", b"", b"trailing/", b"x.quiva", b"./x", b"../x.dexqv"]
+    for n in names:
+        assert owned(L, "PathTo", n) == owned(R, "PathTo", n), n
+        for suf in (b".fasta", b".quiva", b".dexqv", b"", None):
+            assert owned(L, "Root", n, suf) == owned(R, "Root", n, suf), (n, suf)
+    for a in ((b".", b"/", b"x", b".dexqv"), (b"", b"", b"", b""), (b"/abs", b"/", b"r" * 500, b".q")):
+        assert L.Catenate(*a) == R.Catenate(*a)
+    for a in ((b"_", 17, b".las"), (b"", -3, b""), (b"x" * 300, 2**31 - 1, b"y")):
+        assert L.Numbered_Suffix(*a) == R.Numbered_Suffix(*a)
+    assert L.Catenate(None, b"", b"", b"") is None and L.Numbered_Suffix(None, 1, b"") is None
+
+
+def test_line_reader_matches_the_interactive_reference(ref, shim, tmp_path):
+    """Read_Lines of libdexcompat_i.so beside the reference's own (QV.c:751-798 compiled with
+    -DINTERACTIVE into oracle/_ref/libdbqv_ref_i.so): same return values, same lines, same line
+    counter, same Ebuffer text, call by call over well-formed and broken inputs."""
+    path = os.path.join(ROOT, "oracle", "_ref", "libdbqv_ref_i.so")
+    if not os.path.exists(path):
+        pytest.skip("oracle/_ref/libdbqv_ref_i.so not built")
+    R = ctypes.CDLL(path)
+    R.Read_Lines.argtypes = [ctypes.c_void_p, ctypes.c_int]
+    R.QVentry.restype = ctypes.c_void_p
+    shim.L.QVentry.restype = ctypes.c_void_p
+    rbuf = (ctypes.c_char * 1000).in_dll(R, "Ebuffer")
+    files = {
+        "good": b"@m/1/0_4 RQ=0.850\nabcd\nefgh\nijkl\nmnop\nqrst\n@m/2/0_2 RQ=0.8\nab\ncd\nef\ngh\nij\n",
+        "ragged": b"@h\nabc\nab\nabc\nabc\nabc\n",
+        "no_newline": b"@h\nabcd\nefgh\nijkl\nmnop\nqrs",
+        "short": b"@h\nabcd\nefgh\n",
+        "empty_lines": b"@h\n\n\n\n\n\n",
+        "empty": b"",
+        "long": b"@h\n" + b"".join(bytes([70 + k]) * 120_000 + b"\n" for k in range(5)),
+    }
+    for name, data in files.items():
+        p = tmp_path / name
+        p.write_bytes(data)
+        fr, fo = shim.open(p), shim.open(p)
+        R.Set_QV_Line(0); shim.L.Set_QV_Line(0)
+        for step in range(8):
+            nl = 1 if step % 2 == 0 else 5
+            rbuf.value = b""; shim.ebuf.value = b""
+            a, b = R.Read_Lines(fr, nl), shim.L.Read_Lines(fo, nl)
+            assert a == b, (name, step, a, b)
+            assert rbuf.value == shim.ebuf.value, (name, step)
+            assert R.Get_QV_Line() == shim.L.Get_QV_Line(), (name, step)
+            if a >= 0:
+                # the first line read sits at QVentry(); the reference keeps the newline, so compare up to it
+                ra = ctypes.string_at(R.QVentry(), a)
+                rb = ctypes.string_at(shim.L.QVentry(), a)
+                assert ra == rb, (name, step)
+            if a < 0:
+                break
+        shim.libc.fclose(fr); shim.libc.fclose(fo)
+    shim.L.QVentry.restype = ctypes.c_char_p
+
+
+class _QVcoding(ctypes.Structure):                          # QV.h:31-42
+    _fields_ = [("schemes", ctypes.c_void_p * 6), ("delChar", ctypes.c_int),
+                ("subChar", ctypes.c_int), ("flip", ctypes.c_int), ("prefix", ctypes.c_char_p)]
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_coding_header_io_matches_the_reference_functions(ref, tmp_path, seed):
+    """Read_QVcoding + Write_QVcoding of libdexcompat.so (host work) beside the reference's own
+    functions on real .dexqv files: same delChar / subChar / flip / prefix, same file position after
+    the read, same bytes written back -- and those are the bytes of the file's header."""
+    from tests import fuzz
+    path = os.path.join(ROOT, "oracle", "_ref", "libdbqv_ref.so")
+    if not os.path.exists(path):
+        pytest.skip("oracle/_ref/libdbqv_ref.so not built")
+    text, _ = fuzz.fuzz_quiva(seed)
+    data = ref.dexqv(text, lossy=bool(seed & 1))
+    src = tmp_path / "f.dexqv"
+    src.write_bytes(data)
+    libc = ctypes.CDLL(None)
+    libc.fopen.restype = ctypes.c_void_p
+    libc.fopen.argtypes = [ctypes.c_char_p, ctypes.c_char_p]
+    for fn in (libc.fclose, libc.ftell):
+        fn.argtypes = [ctypes.c_void_p]
+    libc.fseek.argtypes = [ctypes.c_void_p, ctypes.c_long, ctypes.c_int]
+    libc.ftell.restype = ctypes.c_long
+    seen = []
+    for lib in (ctypes.CDLL(path), _load("libdexcompat.so")):
+        lib.Read_QVcoding.restype = ctypes.POINTER(_QVcoding)
+        lib.Read_QVcoding.argtypes = [ctypes.c_void_p]
+        lib.Write_QVcoding.argtypes = [ctypes.c_void_p, ctypes.POINTER(_QVcoding)]
+        lib.Free_QVcoding.argtypes = [ctypes.POINTER(_QVcoding)]
+        f = libc.fopen(str(src).encode(), b"r")
+        libc.fseek(f, 2, 0)                                  # the caller reads the 0x55aa key itself
+        c = lib.Read_QVcoding(f)
+        assert c
+        pos = libc.ftell(f)
+        out = tmp_path / "w.bin"
+        g = libc.fopen(str(out).encode(), b"w")
+        lib.Write_QVcoding(g, c)
+        libc.fclose(g)
+        seen.append((c.contents.delChar, c.contents.subChar, c.contents.flip, c.contents.prefix,
+                     pos, out.read_bytes()))
+        lib.Free_QVcoding(c)                                 # frees prefix too (QV.c:1324-1334)
+        libc.fclose(f)
+    assert seen[0] == seen[1]
+    assert seen[0][5] == data[2:seen[0][4]]
