@@ -363,6 +363,8 @@ int Read_Lines(FILE *input, int nlines)
   S.nline++;
   if (fgets(S.line,S.rmax,input) == NULL) return -1;
   int len = (int) strlen(S.line);
+  if (len == 0)                                             // a NUL at the start of a line: the reference reads Read[-1] here
+    { DXC_MSG("Line %d: Last line does not end with a newline !\n",S.nline); DXC_EXIT(1,-2); }
   while (S.line[len-1] != '\n')
     { const int nmax = S.rmax + S.rmax/2 + 1000;               // only slot 0 is live here
       char *nl = (char *) malloc((size_t) 5*nmax);
