@@ -43,6 +43,72 @@ def split_entries(entry_starts, total_bytes: int, nshards: int):
     return out
 
 
+# ---- cutting ONE file into shards without knowing its entry starts --------------------------------------
+#
+# A .quiva entry is 6 lines (header + 5 streams, QV.c:751-798); a line that begins with '@' proves
+# nothing ('@' is QV 31), so entry starts in the middle of a file are found by COUNTING lines:
+#   1. rank r takes the byte range between two nominal cuts, each moved forward to the next line start
+#      (raw_line_cut on a small window around the nominal position);
+#   2. it counts the newlines of its range (on the GPU: the newline index of k_pred_slots);
+#   3. the counts are exclusive-scanned over the ranks (one word per rank in the all-gather): the
+#      global number of a rank's first line.  The rank skips lines_to_skip() lines to reach the next
+#      line whose number is a multiple of 6 -- its first entry start -- and those skipped lines belong
+#      to its predecessor's last entry;
+#   4. the starts are gathered (one more word): a rank whose range lies inside one long entry has no
+#      entry start and takes an empty shard (resolve_starts).
+
+def nominal_cuts(total_bytes: int, nshards: int):
+    """Equal byte targets (before they are moved to line starts)."""
+    return [total_bytes * r // nshards for r in range(nshards + 1)]
+
+
+def raw_line_cut(buf, pos: int) -> int:
+    """First line start at or after byte `pos` of buf (bytes / uint8 array): pos itself if it is 0 or
+    follows a newline, else one past the next newline; len(buf) if there is none."""
+    a = np.frombuffer(buf, dtype=np.uint8) if isinstance(buf, (bytes, bytearray, memoryview)) else np.asarray(buf)
+    n = len(a)
+    if pos <= 0:
+        return 0
+    if pos >= n:
+        return n
+    if a[pos - 1] == 10:
+        return pos
+    nl = np.flatnonzero(a[pos:] == 10)
+    return n if len(nl) == 0 else pos + int(nl[0]) + 1
+
+
+def lines_to_skip(line_counts, rank: int, lines_per_entry: int = 6) -> int:
+    """line_counts[q] = newlines in rank q's raw range.  -> how many whole lines at the start of rank's
+    range still belong to the previous rank's last entry."""
+    first_line = int(np.asarray(line_counts[:rank], dtype=np.int64).sum())
+    return (-first_line) % lines_per_entry
+
+
+def entry_aligned_start(newline_pos, raw_start: int, skip: int, raw_end: int) -> int:
+    """newline_pos: ascending offsets of the newlines inside [raw_start, raw_end).  -> offset of the
+    rank's first entry start, or -1 when no entry starts inside the range (it lies inside one long
+    entry, or is empty): such a rank gets an empty shard, see resolve_starts."""
+    if raw_start >= raw_end:
+        return -1
+    if skip == 0:
+        return raw_start
+    if len(newline_pos) < skip:
+        return -1
+    p = int(newline_pos[skip - 1]) + 1
+    return p if p < raw_end else -1
+
+
+def resolve_starts(starts, total_bytes: int):
+    """starts[r] as gathered from entry_aligned_start (one word per rank).  A rank without an entry
+    start takes its successor's, so shard r = [out[r], out[r+1]) is empty for it and the shards stay
+    contiguous and entry-aligned.  -> world + 1 offsets, out[0] == 0, out[-1] == total_bytes."""
+    out = [int(x) for x in starts] + [int(total_bytes)]
+    for r in range(len(starts) - 1, -1, -1):
+        if out[r] < 0:
+            out[r] = out[r + 1]
+    return out
+
+
 def pack_stats(st: Stats, last_well: int) -> np.ndarray:
     """One rank's contribution to the all-gather."""
     row = np.empty(STAT_WORDS, dtype=np.int64)

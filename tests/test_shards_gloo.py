@@ -181,3 +181,85 @@ def test_split_entries_properties():
         assert list(shards.shard_offsets([c[3] - c[2] for c in cuts])) == [c[2] for c in cuts]
 
     check()
+
+
+# ---- cutting one file by counting lines (no entry index) ----------------------------------------------------
+
+def _line_count_cuts(text: bytes, world: int):
+    """what every rank would compute, here in one process: raw cuts at line starts, newline counts,
+    skipped lines -> entry-aligned shard starts (the last element is len(text))"""
+    a = np.frombuffer(text, dtype=np.uint8)
+    nom = shards.nominal_cuts(len(text), world)
+    raw = [shards.raw_line_cut(a, p) for p in nom]
+    nls = [np.flatnonzero(a[raw[r]:raw[r + 1]] == 10) + raw[r] for r in range(world)]
+    counts = [len(x) for x in nls]
+    starts = []
+    for r in range(world):
+        k = shards.lines_to_skip(counts, r)
+        starts.append(shards.entry_aligned_start(nls[r], raw[r], k, raw[r + 1]))
+    return shards.resolve_starts(starts, len(text))
+
+
+def _at_sign_hook(i, streams):
+    # quality lines that begin with '@' (QV 31) and look like headers to a pattern matcher
+    for k in (0, 2, 3, 4):
+        streams[k][0] = ord("@")
+    if len(streams[2]) > 12:
+        streams[2][:12] = np.frombuffer(b"@m/1/0_9 RQ=", dtype=np.uint8)
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 4, 8])
+def test_line_count_cuts_land_on_entry_starts(world):
+    rng = np.random.default_rng(world)
+    for seed, lengths in ((1, synth.draw_lengths(rng, 40)), (2, [1, 2, 3, 1, 1, 5000, 1, 1]),
+                          (3, [7] * 5), (4, [30000])):
+        text = synth.make_quiva(seed, lengths, stream_hook=_at_sign_hook)
+        true_starts = {e[0] for e in _entries(text)} | {len(text)}
+        cuts = _line_count_cuts(text, world)
+        assert cuts[0] == 0 and cuts[-1] == len(text)
+        assert all(c in true_starts for c in cuts), (world, seed)
+        assert all(cuts[i] <= cuts[i + 1] for i in range(world)), (world, seed)
+        # balanced up to one entry: no shard start is further from its nominal cut than one entry
+        longest = 6 * (max(lengths) + 1) + 120
+        nom = shards.nominal_cuts(len(text), world)
+        assert all(0 <= cuts[r] - nom[r] <= longest for r in range(world) if cuts[r] < cuts[r + 1]), (world, seed)
+
+
+def _cut_worker(rank, world, port, text, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        a = np.frombuffer(text, dtype=np.uint8)
+        nom = shards.nominal_cuts(len(text), world)
+        lo, hi = shards.raw_line_cut(a, nom[rank]), shards.raw_line_cut(a, nom[rank + 1])
+        nl = np.flatnonzero(a[lo:hi] == 10) + lo                # on the GPU: the newline index
+        mine = torch.tensor([len(nl)], dtype=torch.int64)
+        counts = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
+        dist.all_gather(counts, mine)
+        counts = [int(c) for c in counts]
+        start = shards.entry_aligned_start(nl, lo, shards.lines_to_skip(counts, rank), hi)
+        starts = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
+        dist.all_gather(starts, torch.tensor([start], dtype=torch.int64))
+        q.put((rank, shards.resolve_starts([int(x) for x in starts], len(text))[rank]))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(180)
+def test_three_ranks_over_gloo_cut_one_file_at_entry_starts():
+    rng = np.random.default_rng(9)
+    text = synth.make_quiva(5, synth.draw_lengths(rng, 25), stream_hook=_at_sign_hook)
+    world, port = 3, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_cut_worker, args=(r, world, port, text, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    assert [got[r] for r in range(world)] == _line_count_cuts(text, world)[:world]
+    true_starts = {e[0] for e in _entries(text)}
+    assert all(got[r] in true_starts for r in range(world))
