@@ -96,3 +96,27 @@ def test_single_symbol_stream_is_rejected():
     with pytest.raises(dxl.DexError) as e:
         dxl.make_coding(st, False)
     assert e.value.code == -11
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_header_reader_survives_truncated_and_corrupt_headers(orc, seed):
+    """dx_qv_read_coding (host) on every truncation of a real header -- each must be refused -- and
+    on randomly corrupted headers, which must be refused or parsed but never read out of bounds
+    (the reference reads through fread and simply fails, QV.c:1214-1320)."""
+    text, _ = fuzz.fuzz_quiva(seed)
+    data = orc.dexqv(text)
+    _, _, used = dxl.read_coding(data[2:])
+    hdr = data[2:2 + used]
+    for k in range(len(hdr)):
+        with pytest.raises(dxl.DexError):
+            dxl.read_coding(hdr[:k])
+    rng = np.random.default_rng(seed)
+    for _ in range(500):
+        b = bytearray(hdr)
+        for _ in range(int(rng.integers(1, 4))):
+            b[int(rng.integers(0, len(b)))] = int(rng.integers(0, 256))
+        try:
+            _, _, n = dxl.read_coding(bytes(b))
+            assert 0 < n <= len(b)
+        except dxl.DexError:
+            pass
