@@ -6,14 +6,21 @@ timed on the same box.
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--size-gb G]
 
 A "step" is one pass of the hot path over one batch: dexqv (statistics scan, code construction,
-encode) of a synthetic .quiva shard followed by undexqv (decode) of the result.  Workload =
-BASELINE.json configs[1]: a 2 GB RS II-like .quiva per GPU (weak scaling: every rank holds its
-own 2 GB shard of one logical file; the ranks exchange only the histograms and a few integers).
+encode) of a synthetic .quiva shard followed by undexqv of the result, the decoder finding the
+entries of the image by itself as a file-to-file tool must.  Workload = BASELINE.json configs[1]:
+a 2 GB RS II-like .quiva per GPU (weak scaling: every rank holds its own 2 GB shard of one logical
+file; the ranks exchange only the histograms and a few integers).
 
 value   uncompressed GB/s summed over both directions (2*U / t), inputs resident in HBM, timed
         with CUDA events on the library's stream, max over ranks.
 e2e     the same step through the host-buffer C ABI (dx_dexqv_host / dx_undexqv_host): pinned
         host -> device copies of the inputs and device -> host copies of the results included.
+
+Control flow rule (round 1 died of breaking it): every collective is issued from the top level of
+run_ours() through `Comm`, by every rank, unconditionally.  Nothing under `if rank == 0` may
+synchronise with other ranks; rank-local timing uses Env.sync() only.  tests/test_bench_flow.py
+runs this file's flow in two gloo processes with a stand-in device and compares the ranks'
+collective sequences.
 """
 from __future__ import annotations
 
@@ -29,6 +36,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 GB = 1e9
+METRIC = "dexqv+undexqv uncompressed GB/s"
 
 
 def peaks():
@@ -81,6 +89,14 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def workload_config(args):
+    """The same object in both arms (the driver compares them)."""
+    return {"workload": "BASELINE.json configs[1]: dexqv/undexqv on a synthetic 2 GB RS II-like "
+                        ".quiva per GPU (5 QV streams)",
+            "uncompressed_bytes_per_gpu": int(args.size_gb * GB), "shards": args.gpus,
+            "l2": "inputs (2 GB) exceed the 126 MB L2; no explicit flush"}
+
+
 # ------------------------------------------------------------------------------------------------
 #  reference arm: the reference's own CPU tools (oracle/_ref), single threaded like the reference
 # ------------------------------------------------------------------------------------------------
@@ -88,34 +104,51 @@ class ClockSampler:
 _SAMPLES = {}
 
 
-def cpu_reference_sample(sample_mb: float, seed: int = 1, nproc: int = 1):
-    """dexqv + undexqv of a bounded sample with the reference binaries; returns timings.
-    nproc > 1: that many independent copies at once (the reference has no threads; independent
-    files are the only way it uses more cores), throughput = nproc * bytes / wall."""
+def _sample_text(kind: str, sample_mb: float, seed: int) -> bytes:
     import numpy as np
     from dextractor_b200 import synth
-    from oracle import orc
-    key = (sample_mb, seed)
+    key = (kind, sample_mb, seed)
     if key not in _SAMPLES:                     # generating the text is not part of the timing
         rng = np.random.default_rng(seed)
-        L = synth.lengths_for_bytes(rng, int(sample_mb * 1e6), 5.0)
-        _SAMPLES[key] = synth.make_quiva(seed, L)
-    text = _SAMPLES[key]
+        if kind == "quiva":
+            L = synth.lengths_for_bytes(rng, int(sample_mb * 1e6), 5.0)
+            _SAMPLES[key] = synth.make_quiva(seed, L)
+        else:
+            L = synth.lengths_for_bytes(rng, int(sample_mb * 1e6), 1.0125)
+            _SAMPLES[key] = synth.make_arrow(seed, L) if kind == "arrow" else synth.make_fasta(seed, L)
+    return _SAMPLES[key]
+
+
+_TOOLS = {"quiva": ("dexqv", "undexqv"), "fasta": ("dexta", "undexta"), "arrow": ("dexar", "undexar")}
+
+
+def cpu_reference_sample(sample_mb: float, seed: int = 1, nproc: int = 1, kind: str = "quiva"):
+    """compress + decompress a bounded sample with the reference binaries; returns timings.
+    nproc > 1: that many independent copies at once (the reference has no threads; independent
+    files are the only way it uses more cores), throughput = nproc * bytes / wall."""
+    from oracle import orc
+    text = _sample_text(kind, sample_mb, seed)
+    enc_tool, dec_tool = _TOOLS[kind]
     if orc.have_ref():
         if nproc > 1:
-            enc, t_enc = orc.ref_tool_parallel("dexqv", text, nproc)
-            back, t_dec = orc.ref_tool_parallel("undexqv", enc, nproc)
+            enc, t_enc = orc.ref_tool_parallel(enc_tool, text, nproc)
+            back, t_dec = orc.ref_tool_parallel(dec_tool, enc, nproc)
         else:
-            enc, t_enc = orc.ref_tool("dexqv", text, taskset=0)
-            back, t_dec = orc.ref_tool("undexqv", enc, taskset=0)
-        kind = "reference"
+            enc, t_enc = orc.ref_tool(enc_tool, text, taskset=0)
+            back, t_dec = orc.ref_tool(dec_tool, enc, taskset=0)
+        ref = "reference"
     else:                                   # the C restatement (oracle/dx_oracle.c)
         nproc = 1
-        t0 = time.perf_counter(); enc = orc.dexqv(text); t_enc = time.perf_counter() - t0
-        t0 = time.perf_counter(); back = orc.undexqv(enc); t_dec = time.perf_counter() - t0
-        kind = "port"
-    assert back == text
-    return {"bytes": len(text) * nproc, "t_enc": t_enc, "t_dec": t_dec, "kind": kind,
+        fe, fd = {"quiva": (orc.dexqv, orc.undexqv),
+                  "fasta": (orc.dexta, orc.undexta),
+                  "arrow": (lambda t: orc.dexta(t, arrow=True),
+                            lambda d: orc.undexta(d, arrow=True))}[kind]
+        t0 = time.perf_counter(); enc = fe(text); t_enc = time.perf_counter() - t0
+        t0 = time.perf_counter(); back = fd(enc); t_dec = time.perf_counter() - t0
+        ref = "port"
+    if kind != "arrow":                     # SN=%.2f headers pass through a float (SURVEY App. B.7)
+        assert back == text
+    return {"bytes": len(text) * nproc, "t_enc": t_enc, "t_dec": t_dec, "kind": ref,
             "compressed": len(enc) * nproc, "cores": nproc, "sample_bytes": len(text)}
 
 
@@ -139,7 +172,7 @@ def run_reference(args):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8", "data": "synthetic",
-        "config": workload_config(args, int(args.size_gb * GB)),
+        "config": workload_config(args),
         "cpu_baseline": {"value": val, "unit": "GB/s", "cores": nproc, "kind": times[0]["kind"],
                          "sample": f"{nproc} x {times[0]['sample_bytes']/1e6:.0f} MB synthetic .quiva per "
                                    f"step, dexqv then undexqv (reference binaries, one single-threaded "
@@ -153,230 +186,329 @@ def run_reference(args):
     print(json.dumps(line))
 
 
-METRIC = "dexqv+undexqv uncompressed GB/s"
-
-
-def workload_config(args, U):
-    return {"workload": "BASELINE.json configs[1]: dexqv/undexqv on a synthetic 2 GB RS II-like "
-                        ".quiva per GPU (5 QV streams)",
-            "uncompressed_bytes_per_gpu": int(U), "shards": args.gpus,
-            "l2": "inputs (2 GB) exceed the 126 MB L2; no explicit flush"}
-
-
 # ------------------------------------------------------------------------------------------------
-#  our arm
+#  our arm: the device-facing pieces behind Env (so the flow below can be exercised on CPU/gloo)
 # ------------------------------------------------------------------------------------------------
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--size-gb", type=float, default=2.0, help="uncompressed .quiva GB per GPU")
-    ap.add_argument("--ref-sample-mb", type=float, default=64.0, help="per process")
-    ap.add_argument("--ref-cores", type=int, default=0, help="reference arm processes (0 = all cores)")
-    ap.add_argument("--cpu-sample-mb", type=float, default=64.0, help="per process")
-    ap.add_argument("--no-extras", action="store_true", help="skip the dexta/undexta side numbers")
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+class Comm:
+    """Every inter-rank operation of the bench.  `log` records what was issued, in order."""
 
-    if args.impl == "reference":
-        return run_reference(args)
+    def __init__(self, world, rank, device):
+        self.world, self.rank, self.device, self.log = world, rank, device, []
 
+    def barrier(self):
+        self.log.append("barrier")
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+
+    def all_gather_i64(self, row):
+        """row: int64 tensor on the communication device -> [world, len(row)] tensor there"""
+        import torch
+        import torch.distributed as dist
+        self.log.append(f"all_gather:{row.numel()}")
+        if self.world == 1:
+            return row.view(1, -1).clone()
+        out = torch.empty(self.world * row.numel(), dtype=torch.int64, device=row.device)
+        dist.all_gather_into_tensor(out, row)
+        return out.view(self.world, -1)
+
+    def all_reduce(self, values, op="max", dtype=None):
+        """list of numbers -> list reduced over the ranks"""
+        import torch
+        import torch.distributed as dist
+        self.log.append(f"all_reduce:{op}:{len(values)}")
+        dtype = dtype or torch.float64
+        t = torch.tensor(list(values), dtype=dtype, device=self.device)
+        if self.world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX if op == "max" else dist.ReduceOp.SUM)
+        return [x for x in t.tolist()]
+
+    def broadcast_i64(self, values, src=0):
+        import torch
+        import torch.distributed as dist
+        self.log.append(f"broadcast:{len(values)}")
+        t = torch.tensor(list(values), dtype=torch.int64, device=self.device)
+        if self.world > 1:
+            dist.broadcast(t, src)
+        return [int(x) for x in t.tolist()]
+
+    def gather_bytes(self, blob):
+        """uint8 tensor on the communication device (any length per rank) -> list of per-rank host
+        bytes on EVERY rank (an all-gather of the sizes, then one of the padded blobs)"""
+        import torch
+        import torch.distributed as dist
+        sizes = self.all_gather_i64(torch.tensor([blob.numel()], dtype=torch.int64, device=self.device))
+        sizes = [int(x) for x in sizes.view(-1).tolist()]
+        self.log.append("all_gather_bytes")
+        if self.world == 1:
+            return [bytes(blob.cpu().numpy().tobytes())]
+        m = max(sizes)
+        pad = torch.zeros(m, dtype=torch.uint8, device=self.device)
+        pad[: blob.numel()] = blob
+        out = torch.empty(self.world * m, dtype=torch.uint8, device=self.device)
+        dist.all_gather_into_tensor(out, pad)
+        h = out.cpu().numpy()
+        return [bytes(h[r * m: r * m + sizes[r]].tobytes()) for r in range(self.world)]
+
+
+class CudaEnv:
+    """The B200 side: torch for buffers / NCCL, libdexb200.so for every codec call."""
+    name = "cuda"
+
+    def __init__(self, local, world):
+        import torch
+        import dextractor_b200 as dx
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
+        self.torch, self.dx = torch, dx
+        torch.cuda.set_device(local)
+        self.dev = torch.device("cuda", local)
+        self.local = local
+        if world > 1:
+            import torch.distributed as dist
+            # stdout carries ONE JSON line: keep NCCL's own banner out of it
+            if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
+                os.environ.pop("NCCL_DEBUG")
+            dist.init_process_group("nccl", device_id=self.dev)
+        self.ctx = dx.Context(local)
+        self.ext = torch.cuda.ExternalStream(self.ctx.stream, device=self.dev)
+
+    # buffers -------------------------------------------------------------------------------
+    def empty(self, n, pinned=False):
+        t = self.torch.empty(int(n), dtype=self.torch.uint8, device="cpu" if pinned else self.dev)
+        return t.pin_memory() if pinned else t
+
+    def make_quiva(self, seed, target, well_base=0, lengths=None):
+        from dextractor_b200 import synth_torch
+        r = synth_torch.make_quiva_device(seed, int(target), self.dev, well_base=well_base,
+                                          lengths=lengths)
+        self.sync()
+        return r
+
+    def make_fasta(self, seed, target, arrow=False):
+        from dextractor_b200 import synth_torch
+        r = synth_torch.make_fasta_device(seed, int(target), self.dev, arrow=arrow)
+        self.sync()
+        return r
+
+    def host_bytes(self, t, n=None):
+        return bytes(t[: (t.numel() if n is None else n)].cpu().numpy().tobytes())
+
+    def equal(self, a, b):
+        return bool(self.torch.equal(a, b))
+
+    def free_cached(self):
+        self.torch.cuda.empty_cache()
+
+    # timing --------------------------------------------------------------------------------
+    def sync(self):
+        self.torch.cuda.synchronize()
+
+    def timed_ms(self, fn):
+        """CUDA events on the library's stream around fn(); rank-local, no collective"""
+        tc = self.torch.cuda
+        self.sync()
+        with tc.stream(self.ext):
+            a = tc.Event(enable_timing=True); b = tc.Event(enable_timing=True)
+            a.record(self.ext); fn(); b.record(self.ext)
+        self.sync()
+        return a.elapsed_time(b)
+
+    def clock_sampler(self):
+        return ClockSampler(self.local)
+
+    def reference_dexqv(self, text: bytes):
+        """the checker (never timed here): the reference's dexqv, else the oracle port"""
+        from oracle import orc
+        if orc.have_ref():
+            return orc.ref_tool("dexqv", text)[0], "reference"
+        return orc.dexqv(text), "port"
+
+    def close(self):
+        self.ctx.close()
+
+
+def run_ours(args, env=None, out=print):
     import numpy as np
-    import torch
-    import torch.distributed as dist
-
-    import dextractor_b200 as dx
     from dextractor_b200 import lib as dxl
-    from dextractor_b200 import shards, synth_torch
+    from dextractor_b200 import shards
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        # stdout carries ONE JSON line: keep NCCL's own banner out of it ("NCCL version ..." goes to
-        # stdout at NCCL_DEBUG=VERSION and =WARN; this image sets one of them)
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
-            os.environ.pop("NCCL_DEBUG")
-        dist.init_process_group("nccl", device_id=dev)
-
-    ctx = dx.Context(local)
-    ext = torch.cuda.ExternalStream(ctx.stream, device=dev)
+    if env is None:
+        env = CudaEnv(local, world)
+    ctx = env.ctx
+    comm = Comm(world, rank, env.dev)
     hbm_peak, peak_src = peaks()
 
-    # ---- workload: one 2 GB shard per rank --------------------------------------------------
-    target = int(args.size_gb * GB)
-    text, nent, npos = synth_torch.make_quiva_device(100 + rank, target, dev,
-                                                     well_base=rank * 2_000_000)
-    torch.cuda.synchronize()
-    U = text.numel()
-    prefix = bytes(text[:200].cpu().numpy().tobytes())
-    prefix = prefix[: prefix.index(b"/", 1)]
-    enc = torch.empty(U // 2 + (1 << 20), dtype=torch.uint8, device=dev)
-    back = torch.empty(U + 4096, dtype=torch.uint8, device=dev)
-    state = {}
+    class Shard:
+        """one rank's share of a logical .quiva file and the dexqv / undexqv calls over it"""
 
-    def exchange_stats(st):
-        """the only inter-GPU exchange of the path, one NCCL all-gather per step: every rank's
-        6x256 histograms, its position / entry counts and the last well of its shard (the offset
-        hand-off); the sums are formed locally.  -> (summed statistics, last well of rank-1)"""
-        if world == 1:
-            return st, 0
-        if "xbuf" not in state:                      # pinned staging + device buffers, allocated once
-            k = 6 * 256 + 3
-            state["xbuf"] = (torch.empty(k, dtype=torch.int64).pin_memory(),
-                             torch.empty(k, dtype=torch.int64, device=dev),
-                             torch.empty(world * k, dtype=torch.int64, device=dev),
-                             torch.empty(world * k, dtype=torch.int64).pin_memory())
-        mine_h, mine_d, allt, all_h = state["xbuf"]
-        mine_h.numpy()[:] = shards.pack_stats(st, state["last_well"])
-        mine_d.copy_(mine_h, non_blocking=True)
-        dist.all_gather_into_tensor(allt, mine_d)
-        all_h.copy_(allt, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        # the run characters were fixed by the first shard (rank 0 resolves them in its first ~100 k
-        # positions) and handed to the other ranks before the loop
-        return shards.merge_stats(all_h.numpy(), rank, state["rc"])
+        def __init__(self, text, nent, prefix):
+            self.text, self.nent, self.prefix, self.U = text, nent, prefix, text.numel()
+            self.enc = env.empty(self.U // 2 + (1 << 20))
+            self.back = env.empty(self.U + 4096)
+            self.carry, self.rc, self.last_well = None, None, 0
+            self.st = {}
 
-    def carry_for_rank():
-        """rank r > 0 counts run lengths with rank 0's run characters from its first entry on"""
-        if world == 1 or rank == 0:
-            return None
-        return state["carry"]
+        def prepare(self):
+            """COLLECTIVE (one broadcast): rank 0 resolves the run characters in its first ~100 k
+            positions (QV.c:993-1015) and hands them on; a rank > 0 counts run lengths with them from
+            its first entry on.  The last well of the shard is what the next rank's first well
+            delta is coded against (dexqv.c:128-135)."""
+            st0 = ctx.qv_scan_dev(self.text.data_ptr(), self.U, None)
+            rc = comm.broadcast_i64([st0.delchar, st0.subchar], 0)
+            self.rc = (rc[0], rc[1])
+            if rank > 0:
+                c = dxl.Carry()
+                c.delchar, c.subchar, c.totchar = rc[0], rc[1], 200000
+                self.carry = c
+            key = self.prefix + b"/"                     # a QV line may start with '@' too
+            tail = env.host_bytes(self.text[-min(self.U, 400000):])
+            k = tail.rfind(b"\n" + key)
+            if k < 0 and not tail.startswith(key):
+                tail = env.host_bytes(self.text)
+                k = tail.rfind(b"\n" + key)
+            self.last_well = int(tail[k + 1:].split(b"/")[1])
 
-    def step_device():
-        """dexqv: scan -> (allreduce) -> code construction -> file header + encode.
-        The image is laid out as [header][entries] from enc[0] (16-byte aligned)."""
-        st = ctx.qv_scan_dev(text.data_ptr(), U, carry_for_rank())
-        tot, lwell_in = exchange_stats(st)
-        cd = dxl.make_coding(tot, False)
-        hdr = b"\xaa\x55" + dxl.write_coding(cd, prefix)
-        hl = len(hdr)
-        ctx.h2d(enc.data_ptr(), hdr)
-        body, lastw_out, offs = ctx.qv_encode_dev(text.data_ptr(), U, cd, False, lwell_in,
-                                                  enc.data_ptr() + hl, enc.numel() - hl,
-                                                  want_offsets=nent)
-        state.update(hdr=hdr, img_len=hl + body, offs=offs + hl, lwell_in=lwell_in)
-        return hl + body
+        def encode(self):
+            """COLLECTIVE (one all-gather): dexqv = scan -> statistics exchange -> code construction
+            -> file header + encode.  The image is [header][entries] from enc[0]."""
+            st = ctx.qv_scan_dev(self.text.data_ptr(), self.U, self.carry)
+            import torch
+            row = torch.from_numpy(shards.pack_stats(st, self.last_well)).to(comm.device)
+            rows = comm.all_gather_i64(row)
+            tot, lwell_in = shards.merge_stats(rows.cpu().numpy(), rank, self.rc)
+            cd = dxl.make_coding(tot, False)
+            hdr = b"\xaa\x55" + dxl.write_coding(cd, self.prefix)
+            hl = len(hdr)
+            ctx.h2d(self.enc.data_ptr(), hdr)
+            body, _, offs = ctx.qv_encode_dev(self.text.data_ptr(), self.U, cd, False, lwell_in,
+                                              self.enc.data_ptr() + hl, self.enc.numel() - hl,
+                                              want_offsets=self.nent)
+            self.st.update(hdr=hdr, img_len=hl + body, offs=offs + hl, lwell_in=lwell_in)
+            return hl + body
 
-    def decode_known():
-        m = ctx.undexqv_dev(enc.data_ptr(), state["img_len"], False, back.data_ptr(), back.numel(),
-                            entry_off=state["offs"], well_in=state["lwell_in"])
-        state["out_len"] = m
-        return m
+        def decode_known(self):
+            m = ctx.undexqv_dev(self.enc.data_ptr(), self.st["img_len"], False, self.back.data_ptr(),
+                                self.back.numel(), entry_off=self.st["offs"],
+                                well_in=self.st["lwell_in"])
+            self.st["out_len"] = m
+            return m
 
-    def decode_discover():
-        return ctx.undexqv_dev(enc.data_ptr(), state["img_len"], False, back.data_ptr(),
-                               back.numel(), well_in=state["lwell_in"])
+        def decode_discover(self):
+            m = ctx.undexqv_dev(self.enc.data_ptr(), self.st["img_len"], False, self.back.data_ptr(),
+                                self.back.numel(), well_in=self.st["lwell_in"])
+            self.st["out_len"] = m
+            return m
+
+        def round_trip_ok(self):
+            return self.st["out_len"] == self.U and env.equal(self.back[: self.U], self.text)
+
+    def first_prefix(text):
+        p = env.host_bytes(text, 200)
+        return p[: p.index(b"/", 1)]
+
+    # ---- parity of the sharded path against the reference, before anything is timed ------------
+    # every rank codes a small shard of one logical file exactly as the timed step does (scan with
+    # carry, statistics exchange, hand-off well, encode); the shard images are gathered and the
+    # file they form must be the reference dexqv's output for the concatenated text.
+    ptext, pnent, _ = env.make_quiva(900 + rank, args.parity_mb * 1e6, well_base=rank * 40 * 4000)
+    psh = Shard(ptext, pnent, first_prefix(ptext))
+    psh.prepare()
+    psh.encode()
+    hl = len(psh.st["hdr"])
+    bodies = comm.gather_bytes(psh.enc[hl: psh.st["img_len"]])
+    texts = comm.gather_bytes(psh.text)
+    psh.decode_discover(); ok_a = psh.round_trip_ok()
+    psh.decode_known(); ok_b = psh.round_trip_ok()
+    parity = {"shards": world, "bytes": sum(len(t) for t in texts), "round_trip": ok_a and ok_b}
+    if rank == 0:                                  # rank-local: no collective below this line
+        want, kind = env.reference_dexqv(b"".join(texts))
+        parity.update(checker=kind, equal=(psh.st["hdr"] + b"".join(bodies) == want))
+    del bodies, texts, ptext, psh
+    flags = comm.all_reduce([float(parity["round_trip"]), float(parity.get("equal", True))], "sum")
+    if flags[0] != world or flags[1] != world:
+        raise SystemExit(f"sharded dexqv differs from the reference ({parity})")
+    env.free_cached()
+
+    # ---- workload: one 2 GB shard per rank -----------------------------------------------------
+    text, nent, npos = env.make_quiva(100 + rank, args.size_gb * GB, well_base=rank * 2_000_000)
+    sh = Shard(text, nent, first_prefix(text))
+    U = sh.U
+    sh.prepare()
 
     def full_step():
-        step_device()
-        decode_known()
+        sh.encode()
+        sh.decode_discover()
 
-    # rank > 0 needs rank 0's run characters before its scan: resolve once, outside the loop
-    if world > 1:
-        st0 = ctx.qv_scan_dev(text.data_ptr(), U, None)
-        rc = torch.tensor([st0.delchar, st0.subchar], dtype=torch.int64, device=dev)
-        dist.broadcast(rc, 0)
-        c = dx.Carry()
-        c.delchar, c.subchar, c.totchar = int(rc[0]), int(rc[1]), 200000
-        state["carry"] = c
-        state["rc"] = (int(rc[0]), int(rc[1]))
-        # last well of this shard: parse the last header once
-        tail = bytes(text[-400000:].cpu().numpy().tobytes())
-        k = tail.rindex(b"\n" + prefix + b"/")          # a QV line may start with '@' too
-        state["last_well"] = int(tail[k + 1:].split(b"/")[1])
-    else:
-        state["last_well"] = 0
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # ---- warm-up, then K timed steps (device-resident) ---------------------------------------
     for _ in range(args.warmup):
         full_step()
-    # property check at full size: decode(encode(x)) == x
-    ok = bool(torch.equal(back[: state["out_len"]], text)) and state["out_len"] == U
-    if not ok:
+    ok = sh.round_trip_ok()                        # property at full size: decode(encode(x)) == x
+    sh.decode_known(); ok = ok and sh.round_trip_ok()
+    sh.decode_discover()
+    if comm.all_reduce([float(ok)], "sum")[0] != world:
         raise SystemExit("round trip at full size differs from the input")
 
-    barrier()
+    # ---- K timed steps (device-resident) --------------------------------------------------------
+    comm.barrier(); env.sync()
     ctx.launch_count(reset=True)
     ctx.profile(True); ctx.profile_report()
-    sampler = ClockSampler(local); sampler.start()
-    with torch.cuda.stream(ext):
-        ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)
-        ev0.record(ext)
-        marks = []
+    sampler = env.clock_sampler(); sampler.start()
+
+    def k_steps():
         for _ in range(args.steps):
-            t0 = time.perf_counter()
             full_step()
-            marks.append(time.perf_counter() - t0)
-        ev1.record(ext)
-    barrier()
-    ms = ev0.elapsed_time(ev1)
+
+    ms = env.timed_ms(k_steps)
+    comm.barrier()
     clocks = sampler.stop()
     launches = ctx.launch_count()
     prof = ctx.profile_report(); ctx.profile(False)
-    if world > 1:
-        tms = torch.tensor([ms], device=dev); dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-        ms = float(tms[0])
-        tb = torch.tensor([U, state["img_len"]], dtype=torch.int64, device=dev); dist.all_reduce(tb)
-        U_all, C_all = int(tb[0]), int(tb[1])
-    else:
-        U_all, C_all = U, state["img_len"]
+    ms = comm.all_reduce([ms], "max")[0]
+    U_all, C_all = [int(x) for x in comm.all_reduce([U, sh.st["img_len"]], "sum")]
     ms_step = ms / args.steps
     value = 2 * U_all / (ms_step * 1e-3) / GB
 
-    # per-direction timing (device resident), a few reps each
+    # ---- per-direction timing (every rank; encode holds the all-gather) ---------------------------
     def timed(fn, reps=3):
-        best = []
-        for _ in range(reps):
-            barrier()
-            with torch.cuda.stream(ext):
-                a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
-                a.record(ext); fn(); b.record(ext)
-            barrier()
-            best.append(a.elapsed_time(b))
-        return min(best), sorted(best)[len(best) // 2]
+        return min(env.timed_ms(fn) for _ in range(reps))
 
-    enc_ms, _ = timed(step_device)
-    dec_known_ms, _ = timed(decode_known)
-    decode_discover(); decode_discover()        # the scratch arena settles at this path's size
-    dec_disc_ms, _ = timed(decode_discover)
-    decode_known()
-    C = state["img_len"]
+    enc_ms = timed(sh.encode)
+    dec_known_ms = timed(sh.decode_known)
+    dec_disc_ms = timed(sh.decode_discover)
+    enc_ms, dec_known_ms, dec_disc_ms = comm.all_reduce([enc_ms, dec_known_ms, dec_disc_ms], "max")
+    C = sh.st["img_len"]
 
     # ---- roofline of the dominant kernel (CUDA events inside the library, timed region) -------
-    # algorithmic bytes per launch (DESIGN.md): hist 0.8U ; size U ; emit U+C ; decode C+U ; walk C
+    # algorithmic bytes per launch (DESIGN.md section 4)
     lines_bytes = 5 * (npos + nent)                    # the 5 QV lines incl. newlines
     algo = {"k_qv_hist_plain": 0.4 * lines_bytes, "k_qv_hist_run": 0.4 * lines_bytes,
+            "k_qv_scan1": 0.8 * lines_bytes + 0.2 * U,
             "k_qv_size": lines_bytes, "k_qv_emit": lines_bytes + C,
-            "k_qv_decode5": C + U, "k_qv_decode5_spec": C + lines_bytes, "k_qv_assemble": 2 * U,
-            "k_pred_slots": U}
+            "k_qv_decode5": C + U, "k_qv_decode5_spec": C + lines_bytes,
+            "k_qv_decode6": C + U, "k_qv_decode6_spec": C + lines_bytes,
+            "k_qv_assemble": 2 * U, "k_pred_slots": U}
     top = max(prof.items(), key=lambda kv: kv[1][1]) if prof else ("none", (1, 1.0))
     tname, (tcalls, ttot) = top
     tavg = ttot / max(tcalls, 1)
     achieved = algo.get(tname, U) / (tavg * 1e-3) / GB
-    traffic = None                              # dram bytes per launch from the committed ncu capture
-    try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
-        if tname in tr["kernels"]:
-            traffic = tr["kernels"][tname]["dram_bytes_per_text_byte"] * U
-    except Exception:
-        pass
+    traffic, traffic_src = None, None           # dram bytes per launch from the committed ncu capture
+    for tf in ("r02_traffic.json", "r01_traffic.json"):
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", tf)))
+            if tname in tr["kernels"]:
+                traffic = tr["kernels"][tname]["dram_bytes_per_text_byte"] * U
+                traffic_src = f"profiles/{tf} (ncu --set full capture of this kernel, scaled by U)"
+                break
+        except Exception:
+            pass
     roofline = {"bound": "hbm", "kernel": tname, "achieved": achieved, "peak": hbm_peak,
                 "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic,
-                "peak_source": peak_src, "avg_ms": tavg,
+                "traffic_source": traffic_src, "peak_source": peak_src, "avg_ms": tavg,
+                "algorithmic_bytes": algo.get(tname, U),
                 "share_of_step": ttot / max(sum(v[1] for v in prof.values()), 1e-9)}
     path = {"dexqv": {"algorithmic_bytes": 1.8 * U + C, "ms": enc_ms,
                       "frac": (1.8 * U + C) / (enc_ms * 1e-3) / GB / hbm_peak},
@@ -385,106 +517,87 @@ def main():
             "undexqv_offsets_discovered": {"algorithmic_bytes": 2 * C + U, "ms": dec_disc_ms,
                                            "frac": (2 * C + U) / (dec_disc_ms * 1e-3) / GB / hbm_peak}}
 
-    # ---- e2e: host buffers through the C ABI, copies inside the timed region -------------------
-    h_text = torch.empty(U, dtype=torch.uint8).pin_memory()
-    h_text.copy_(text)
-    h_enc = torch.empty(U // 2 + (1 << 20), dtype=torch.uint8).pin_memory()
-    h_back = torch.empty(U + 4096, dtype=torch.uint8).pin_memory()
-    import ctypes as C_
-    L = ctx.L
+    # ---- e2e: host buffers through the C ABI, copies inside the timed region (every rank) -------
+    h_text = env.empty(U, pinned=True); h_text.copy_(text)
+    h_enc = env.empty(U // 2 + (1 << 20), pinned=True)
+    h_back = env.empty(U + 4096, pinned=True)
+    env.sync()
+    e2e_n = {}
 
     def e2e_step():
-        n1 = C_.c_size_t(0)
-        ctx._check(L.dx_dexqv_host(ctx.h, h_text.data_ptr(), U, 0, h_enc.data_ptr(), h_enc.numel(),
-                                   C_.byref(n1)))
-        n2 = C_.c_size_t(0)
-        ctx._check(L.dx_undexqv_host(ctx.h, h_enc.data_ptr(), n1.value, 0, h_back.data_ptr(),
-                                     h_back.numel(), C_.byref(n2)))
-        return n1.value, n2.value
+        n1 = ctx.dexqv_host_ptr(h_text.data_ptr(), U, False, h_enc.data_ptr(), h_enc.numel())
+        n2 = ctx.undexqv_host_ptr(h_enc.data_ptr(), n1, False, h_back.data_ptr(), h_back.numel())
+        e2e_n.update(n1=n1, n2=n2)
 
-    e2e = None
-    if world == 1:
-        n1, n2 = e2e_step()
-        assert n2 == U and bool(torch.equal(h_back[:U], h_text))
-        barrier()
-        with torch.cuda.stream(ext):
-            a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
-            a.record(ext)
-            for _ in range(args.steps):
-                n1, n2 = e2e_step()
-            b.record(ext)
-        barrier()
-        e2e_ms = a.elapsed_time(b) / args.steps
-        e2e = {"value": 2 * U / (e2e_ms * 1e-3) / GB, "unit": "GB/s", "ms_per_step": e2e_ms,
-               "h2d_bytes_per_step": int(U + n1), "d2h_bytes_per_step": int(n1 + n2),
-               "api": "dx_dexqv_host + dx_undexqv_host (pinned host buffers; the decoder "
-                      "rediscovers entry offsets from the file)"}
-    else:
-        # every rank runs its own shard end to end through the same host-buffer calls
-        barrier()
-        t0 = time.perf_counter()
-        with torch.cuda.stream(ext):
-            a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
-            a.record(ext)
-            for _ in range(args.steps):
-                n1, n2 = e2e_step()
-            b.record(ext)
-        barrier()
-        tms = torch.tensor([a.elapsed_time(b) / args.steps], device=dev)
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-        e2e_ms = float(tms[0])
-        e2e = {"value": 2 * U_all / (e2e_ms * 1e-3) / GB, "unit": "GB/s", "ms_per_step": e2e_ms,
-               "h2d_bytes_per_step": int((U + n1) * world), "d2h_bytes_per_step": int((n1 + n2) * world),
-               "api": "dx_dexqv_host + dx_undexqv_host per rank on its own shard (independent "
-                      "per-shard files)"}
+    def e2e_steps():
+        for _ in range(args.steps):
+            e2e_step()
+
+    e2e_step()
+    e2e_ok = e2e_n["n2"] == U and env.equal(h_back[:U], h_text)
+    comm.barrier()
+    e2e_ms = env.timed_ms(e2e_steps) / args.steps
+    e2e_ms, = comm.all_reduce([e2e_ms], "max")
+    if comm.all_reduce([float(e2e_ok)], "sum")[0] != world:
+        raise SystemExit("host-buffer round trip differs from the input")
+    e2e = {"value": 2 * U_all / (e2e_ms * 1e-3) / GB, "unit": "GB/s", "ms_per_step": e2e_ms,
+           "h2d_bytes_per_step": int((U + e2e_n["n1"]) * world),
+           "d2h_bytes_per_step": int((e2e_n["n1"] + e2e_n["n2"]) * world),
+           "api": "dx_dexqv_host + dx_undexqv_host on pinned host buffers, per rank on its own shard "
+                  "(independent per-shard files at N > 1); the decoder rediscovers entry offsets"}
     del h_text, h_enc, h_back
 
     extras = {"dexqv_gbs": U / (enc_ms * 1e-3) / GB,
               "undexqv_offsets_known_gbs": U / (dec_known_ms * 1e-3) / GB,
               "undexqv_offsets_discovered_gbs": U / (dec_disc_ms * 1e-3) / GB,
-              "compressed_bytes": int(C), "ratio": U / C, "entries": nent,
+              "value_offsets_known": 2 * U_all / ((enc_ms + dec_known_ms) * 1e-3) / GB,
+              "uncompressed_bytes": int(U), "compressed_bytes": int(C), "ratio": U / C, "entries": nent,
+              "sharded_parity": parity,
               "kernels_ms_per_step": {k: round(v[1] / args.steps, 4) for k, v in sorted(prof.items())}}
+    del sh, text
+    env.free_cached()
 
-    # ---- side numbers: dexta/undexta on a 1 GB fasta (configs[0]) ---------------------------------
-    if not args.no_extras and rank == 0:
-        del back
-        torch.cuda.empty_cache()
-        fa, nfa = synth_torch.make_fasta_device(7, int(1.0 * GB), dev)
-        UF = fa.numel()
-        pk = torch.empty(UF // 3 + (1 << 20), dtype=torch.uint8, device=dev)
-        un = torch.empty(UF + 4096, dtype=torch.uint8, device=dev)
-        m = ctx.dexta_dev(dx.FASTA, fa.data_ptr(), UF, pk.data_ptr(), pk.numel())
-        k = ctx.undexta_dev(dx.FASTA, pk.data_ptr(), m, 80, False, un.data_ptr(), un.numel())
-        assert k == UF and bool(torch.equal(un[:UF], fa)), "dexta/undexta round trip differs"
-        pack_ms, _ = timed(lambda: ctx.dexta_dev(dx.FASTA, fa.data_ptr(), UF, pk.data_ptr(), pk.numel()))
-        unpack_ms, _ = timed(lambda: ctx.undexta_dev(dx.FASTA, pk.data_ptr(), m, 80, False,
-                                                     un.data_ptr(), un.numel()))
-        extras.update(dexta_gbs=UF / (pack_ms * 1e-3) / GB, undexta_gbs=UF / (unpack_ms * 1e-3) / GB,
-                      dexta_frac=(UF + m) / (pack_ms * 1e-3) / GB / hbm_peak,
-                      undexta_frac=(UF + m) / (unpack_ms * 1e-3) / GB / hbm_peak,
-                      fasta_bytes=int(UF), dexta_bytes=int(m))
-        del fa, pk, un
-        torch.cuda.empty_cache()
+    # ---- configs[0] / configs[2]: dexta/undexta and dexar/undexar on 1 GB per rank (every rank;
+    #      the 2-bit path needs no exchange at all, so the only collective is the max of the times)
+    two_bit = [0.0] * 4
+    if not args.no_extras:
+        for j, arrow in enumerate((False, True)):
+            kind = env.dx.ARROW if arrow else env.dx.FASTA
+            fa, nfa = env.make_fasta(7 + 2 * j + 10 * rank, 1.0 * GB, arrow=arrow)
+            UF = fa.numel()
+            pk = env.empty(UF // 3 + (1 << 20)); un = env.empty(UF + 4096)
+            m = ctx.dexta_dev(kind, fa.data_ptr(), UF, pk.data_ptr(), pk.numel())
+            k = ctx.undexta_dev(kind, pk.data_ptr(), m, 80, False, un.data_ptr(), un.numel())
+            if not arrow:
+                assert k == UF and env.equal(un[:UF], fa), "dexta/undexta round trip differs"
+            else:
+                # SN=%.2f headers pass through a float and lose up to 0.01 per trip:
+                # same length, and only SNR digits of the header lines may differ
+                ndiff = int((un[:UF] != fa).sum()) if k == UF else -1
+                assert 0 <= ndiff <= 16 * nfa, "dexar/undexar round trip differs outside the SNR digits"
+            t_p = timed(lambda: ctx.dexta_dev(kind, fa.data_ptr(), UF, pk.data_ptr(), pk.numel()))
+            t_u = timed(lambda: ctx.undexta_dev(kind, pk.data_ptr(), m, 80, False, un.data_ptr(),
+                                                un.numel()))
+            two_bit[2 * j], two_bit[2 * j + 1] = t_p, t_u
+            nm = ("dexar", "undexar", "arrow") if arrow else ("dexta", "undexta", "fasta")
+            extras.update({f"{nm[2]}_bytes_per_gpu": int(UF), f"{nm[0]}_bytes_per_gpu": int(m)})
+            del fa, pk, un
+            env.free_cached()
+    two_bit = comm.all_reduce(two_bit, "max")
+    if not args.no_extras:
+        UF, m = extras["fasta_bytes_per_gpu"], extras["dexta_bytes_per_gpu"]
+        UA, ma = extras["arrow_bytes_per_gpu"], extras["dexar_bytes_per_gpu"]
+        extras.update(dexta_gbs=world * UF / (two_bit[0] * 1e-3) / GB,
+                      undexta_gbs=world * UF / (two_bit[1] * 1e-3) / GB,
+                      dexta_frac=(UF + m) / (two_bit[0] * 1e-3) / GB / hbm_peak,
+                      undexta_frac=(UF + m) / (two_bit[1] * 1e-3) / GB / hbm_peak,
+                      dexar_gbs=world * UA / (two_bit[2] * 1e-3) / GB,
+                      undexar_gbs=world * UA / (two_bit[3] * 1e-3) / GB,
+                      dexar_frac=(UA + ma) / (two_bit[2] * 1e-3) / GB / hbm_peak,
+                      undexar_frac=(UA + ma) / (two_bit[3] * 1e-3) / GB / hbm_peak)
 
-        # configs[2]: dexar/undexar on a synthetic 1 GB Sequel-style .arrow
-        ar, nar = synth_torch.make_fasta_device(9, int(1.0 * GB), dev, arrow=True)
-        UA = ar.numel()
-        pk = torch.empty(UA // 3 + (1 << 20), dtype=torch.uint8, device=dev)
-        un = torch.empty(UA + 4096, dtype=torch.uint8, device=dev)
-        m = ctx.dexta_dev(dx.ARROW, ar.data_ptr(), UA, pk.data_ptr(), pk.numel())
-        k = ctx.undexta_dev(dx.ARROW, pk.data_ptr(), m, 80, False, un.data_ptr(), un.numel())
-        # SN=%.2f headers pass through a float and lose up to 0.01 per trip, so the
-        # property at full size is: same length, and only SNR digits of the header lines may differ
-        ndiff = int((un[:UA] != ar).sum()) if k == UA else -1
-        assert k == UA and 0 <= ndiff <= 16 * nar, "dexar/undexar round trip differs outside the SNR digits"
-        par_ms, _ = timed(lambda: ctx.dexta_dev(dx.ARROW, ar.data_ptr(), UA, pk.data_ptr(), pk.numel()))
-        unar_ms, _ = timed(lambda: ctx.undexta_dev(dx.ARROW, pk.data_ptr(), m, 80, False,
-                                                   un.data_ptr(), un.numel()))
-        extras.update(dexar_gbs=UA / (par_ms * 1e-3) / GB, undexar_gbs=UA / (unar_ms * 1e-3) / GB,
-                      arrow_bytes=int(UA), dexar_bytes=int(m))
-        del ar, pk, un
-        torch.cuda.empty_cache()
-
+    # ======== from here on: rank-local work only (NO collective until the final barrier) ========
+    if rank == 0 and world == 1 and not args.no_extras:
         # configs[4]: mixed short/long subread lengths (500 bp - 50 kb), 0.5 GB each
         sweep = {}
         rs = np.random.default_rng(5)
@@ -495,10 +608,9 @@ def main():
         for name, draw in dists.items():
             Ls = np.asarray(draw(200000), dtype=np.int64)
             Ls = Ls[: int(np.searchsorted(np.cumsum(Ls), npos_t)) + 1]
-            tx, ne, npz = synth_torch.make_quiva_device(50, 0, dev, lengths=Ls)
+            tx, ne, npz = env.make_quiva(50, 0, lengths=Ls)
             Us = tx.numel()
-            e2 = torch.empty(Us // 2 + (1 << 20), dtype=torch.uint8, device=dev)
-            b2 = torch.empty(Us + 4096, dtype=torch.uint8, device=dev)
+            e2 = env.empty(Us // 2 + (1 << 20)); b2 = env.empty(Us + 4096)
             st2 = {}
 
             def enc2():
@@ -508,20 +620,21 @@ def main():
                 st2["m"] = ctx.undexqv_dev(e2.data_ptr(), st2["n"], False, b2.data_ptr(), b2.numel())
 
             enc2(); dec2(); dec2()
-            assert st2["m"] == Us and bool(torch.equal(b2[:Us], tx)), "length sweep round trip differs"
-            t_e, _ = timed(enc2)
-            t_d, _ = timed(dec2)
+            assert st2["m"] == Us and env.equal(b2[:Us], tx), "length sweep round trip differs"
+            t_e = timed(enc2)
+            t_d = timed(dec2)
             sweep[name] = {"entries": int(ne), "bytes": int(Us), "dexqv_gbs": Us / (t_e * 1e-3) / GB,
                            "undexqv_discovered_gbs": Us / (t_d * 1e-3) / GB}
             del tx, e2, b2
-            torch.cuda.empty_cache()
+            env.free_cached()
         extras["length_sweep"] = sweep
 
     # ---- CPU baseline beside it (rank 0, N=1 only) ---------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
+        ncore = os.cpu_count() or 1
         r1 = cpu_reference_sample(args.cpu_sample_mb, seed=1, nproc=1)
-        r = cpu_reference_sample(args.cpu_sample_mb, seed=1, nproc=os.cpu_count() or 1)
+        r = cpu_reference_sample(args.cpu_sample_mb, seed=1, nproc=ncore)
         t = r["t_enc"] + r["t_dec"]
         cpu = {"value": 2 * r["bytes"] / t / GB, "unit": "GB/s", "cores": r["cores"], "kind": r["kind"],
                "sample": f"{r['cores']} x {r['sample_bytes']/1e6:.0f} MB synthetic .quiva (same generator "
@@ -532,29 +645,63 @@ def main():
                             "dexqv_gbs": r1["bytes"] / r1["t_enc"] / GB,
                             "undexqv_gbs": r1["bytes"] / r1["t_dec"] / GB},
                "host_cores_available": os.cpu_count()}
+        for kind in ("fasta", "arrow"):          # the 2-bit tools, single threaded and on every core
+            a1 = cpu_reference_sample(args.cpu_sample_mb, seed=2, nproc=1, kind=kind)
+            an = cpu_reference_sample(args.cpu_sample_mb, seed=2, nproc=ncore, kind=kind)
+            e, d = _TOOLS[kind]
+            cpu["one_core"].update({f"{e}_gbs": a1["bytes"] / a1["t_enc"] / GB,
+                                    f"{d}_gbs": a1["bytes"] / a1["t_dec"] / GB})
+            cpu.update({f"{e}_gbs": an["bytes"] / an["t_enc"] / GB,
+                        f"{d}_gbs": an["bytes"] / an["t_dec"] / GB})
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
-                "data": "synthetic", "config": workload_config(args, U),
+                "data": "synthetic", "config": workload_config(args),
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
                 "roofline": roofline, "path_roofline": path, "cpu_baseline": cpu,
                 "extra": extras}
-        print(json.dumps(line), flush=True)
-    # Teardown order matters: the pinned staging buffers of exchange_stats were used on the
-    # library's stream (`ext`), and torch's pinned-memory allocator records an event on every
-    # stream that used a block when the block is freed.  Freed after ctx.close() had destroyed
-    # that stream, the record threw "CUDA error: context is destroyed" from a tensor destructor
-    # and every rank of an N>1 run ended in SIGABRT after printing its line.  So: drop them first.
-    state.clear()
+        out(json.dumps(line))
+        sys.stdout.flush()
+    # Teardown order matters: tensors that were used on the library's stream must be gone before
+    # dx_close destroys it (torch's caching allocators record events on every stream that used a
+    # block when the block is freed), and the process group must go before the context.
     import gc
     gc.collect()
-    torch.cuda.synchronize()
+    env.sync()
+    comm.barrier()
     if world > 1:
-        dist.barrier()
+        import torch.distributed as dist
         dist.destroy_process_group()
-    ctx.close()
+    env.close()
+    return comm.log
+
+
+def parse_args(argv=None):
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--size-gb", type=float, default=2.0, help="uncompressed .quiva GB per GPU")
+    ap.add_argument("--parity-mb", type=float, default=48.0,
+                    help="per-rank shard of the pre-timing parity check against the reference")
+    ap.add_argument("--ref-sample-mb", type=float, default=64.0, help="per process")
+    ap.add_argument("--ref-cores", type=int, default=0, help="reference arm processes (0 = all cores)")
+    ap.add_argument("--cpu-sample-mb", type=float, default=64.0, help="per process")
+    ap.add_argument("--no-extras", action="store_true", help="skip the dexta/undexta side numbers")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args(argv)
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    return args
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    run_ours(args)
 
 
 if __name__ == "__main__":

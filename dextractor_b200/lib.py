@@ -265,6 +265,17 @@ class Context:
                                            out.ctypes.data, out.size, C.byref(n)))
         return out[: n.value].tobytes()
 
+    def dexqv_host_ptr(self, h_text: int, n: int, lossy: bool, h_out: int, cap: int) -> int:
+        """dx_dexqv_host on raw HOST addresses (e.g. pinned torch tensors): copies included"""
+        m = C.c_size_t(0)
+        self._check(self.L.dx_dexqv_host(self.h, h_text, n, int(lossy), h_out, cap, C.byref(m)))
+        return m.value
+
+    def undexqv_host_ptr(self, h_in: int, n: int, upper: bool, h_out: int, cap: int) -> int:
+        m = C.c_size_t(0)
+        self._check(self.L.dx_undexqv_host(self.h, h_in, n, int(upper), h_out, cap, C.byref(m)))
+        return m.value
+
     # ---- device-pointer API ---------------------------------------------------------------------
     def dexta_dev(self, kind, d_text, n, d_out, cap) -> int:
         _wait_for_torch()
