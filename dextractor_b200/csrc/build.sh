@@ -7,21 +7,21 @@ NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC,-Wall,-Wno-unused-function -I../../include -I."
 mkdir -p build
 objs=""
-for f in dx_frame.cu dx_qv_stats.cu dx_qv_encode.cu dx_qv_decode.cu dx_qv_decode2.cu dx_qv_decode3.cu dx_qv_decode4.cu dx_qv_decode5.cu dx_qv_plan.cu dx_pack.cu dx_pack2.cu dx_pack3.cu; do
-  o=build/${f%.cu}.o
-  if [ ! -f $o ] || [ $f -nt $o ] || [ dx_common.cuh -nt $o ] || [ dx_bits.cuh -nt $o ] || [ dx_internal.h -nt $o ] || [ ../../include/dexb200.h -nt $o ]; then
-    $NVCC $FLAGS ${PTXAS_V:+-Xptxas -v} -c $f -o $o &
+pids=""
+HDRS="dx_common.cuh dx_bits.cuh dx_internal.h ../../include/dexb200.h"
+newer() { for h in $HDRS $1; do [ $h -nt $2 ] && return 0; done; return 1; }
+for f in dx_frame.cu dx_qv_stats.cu dx_qv_encode.cu dx_qv_decode.cu dx_qv_decode5.cu dx_qv_decode6.cu dx_qv_plan.cu dx_pack.cu dx_pack2.cu dx_pack3.cu dx_api.cpp dx_coding.cpp dx_pipe.cpp; do
+  [ -f $f ] || continue
+  o=build/${f%.*}.o
+  if [ ! -f $o ] || newer $f $o; then
+    rm -f $o                       # a failed compile must not leave a stale object for the link
+    $NVCC $FLAGS ${PTXAS_V:+-Xptxas -v} -x cu -c $f -o $o &
+    pids="$pids $!"
   fi
   objs="$objs $o"
 done
-for f in dx_api.cpp dx_coding.cpp; do
-  o=build/${f%.cpp}.o
-  if [ ! -f $o ] || [ $f -nt $o ] || [ dx_internal.h -nt $o ] || [ ../../include/dexb200.h -nt $o ]; then
-    $NVCC $FLAGS -x cu -c $f -o $o &
-  fi
-  objs="$objs $o"
-done
-wait
+for p in $pids; do wait $p || { echo "compile failed" >&2; exit 1; }; done
+for o in $objs; do [ -f $o ] || { echo "missing $o" >&2; exit 1; }; done
 $NVCC -shared -gencode arch=compute_100a,code=sm_100a -o $OUT $objs -lcudart_static -lpthread -ldl -lrt
 echo "built $OUT"
 # libdexcompat.so: the reference's QV.h / DB.h symbols over libdexb200.so

@@ -18,7 +18,7 @@
 // wall-clock marks of the host phases of a call, printed with DEXB200_DEBUG set
 struct DxPhases
 { bool on; std::chrono::steady_clock::time_point t0; char buf[512]; size_t len;
-  DxPhases() : on(getenv("DEXB200_DEBUG") != NULL), len(0) { buf[0] = 0; t0 = std::chrono::steady_clock::now(); }
+  explicit DxPhases(const dx_ctx *ctx) : on(ctx->route[DXR_DEBUG] != 0), len(0) { buf[0] = 0; t0 = std::chrono::steady_clock::now(); }
   void mark(const char *what)
   { if (!on) return;
     auto t1 = std::chrono::steady_clock::now();
@@ -214,6 +214,7 @@ extern "C" int dx_open(int device, dx_ctx **out)
       return DX_E_CUDA;
     }
   ctx->sm_count = prop.multiProcessorCount;
+  ctx->route[DXR_DEBUG] = (getenv("DEXB200_DEBUG") != NULL);      // read once, here; never in a call
   *out = ctx;
   return DX_OK;
 }
@@ -242,6 +243,22 @@ extern "C" void dx_close(dx_ctx *ctx)
 extern "C" const char *dx_strerror(const dx_ctx *ctx) { return ctx ? ctx->err : "no context"; }
 extern "C" int64_t     dx_error_line(const dx_ctx *ctx) { return ctx ? ctx->err_line : 0; }
 extern "C" void       *dx_stream(dx_ctx *ctx) { return ctx ? (void *) ctx->stream : NULL; }
+
+extern "C" int dx_route(dx_ctx *ctx, const char *name, int64_t value)
+{ static const char *names[DXR_COUNT] = { "no_fast", "no_spec", "exact_index", "exact_pack", "pack2", "two_pass",
+                                          "chain_scan", "decoder", "lane_max_rlen", "lane_min_entries", "debug",
+                                          "serial_io" };
+  if (ctx == NULL || name == NULL) return DX_E_ARG;
+  if (strcmp(name,"default") == 0)
+    { const int64_t dbg = ctx->route[DXR_DEBUG];
+      memset(ctx->route,0,sizeof(ctx->route));
+      ctx->route[DXR_DEBUG] = dbg;
+      return DX_OK;
+    }
+  for (int k = 0; k < DXR_COUNT; k++)
+    if (strcmp(name,names[k]) == 0) { ctx->route[k] = value; return DX_OK; }
+  return dx_fail(ctx,DX_E_ARG,"dx_route: unknown route '%s'",name);
+}
 
 extern "C" int dx_keep_index(dx_ctx *ctx, int keep)
 { if (ctx == NULL) return DX_E_ARG;
@@ -463,7 +480,7 @@ extern "C" int dx_dexta_dev(dx_ctx *ctx, int kind, const uint8_t *d_text, size_t
 { // first the vectorised kernels, which take the symbol counts from the line lattice and verify them
   // while packing; a file whose lines do not form the lattice is redone with the exact counts
   bool redo = false;
-  int rc = dexta_impl(ctx,kind,d_text,n,d_out,cap,out_len,getenv("DEXB200_EXACT_PACK") != NULL,&redo);
+  int rc = dexta_impl(ctx,kind,d_text,n,d_out,cap,out_len,ctx->route[DXR_EXACT_PACK] != 0,&redo);
   if (rc == DX_OK && redo) rc = dexta_impl(ctx,kind,d_text,n,d_out,cap,out_len,true,&redo);
   return rc;
 }
@@ -596,7 +613,7 @@ static int dexta_impl(dx_ctx *ctx, int kind, const uint8_t *d_text, size_t n,
   else
     { // d_flags: [1] pack error, [2..3] ticket, [4] entries left to k_fa_pack2, [6..7] its ticket
       int32_t res[4] = { 0, 0, 0, 0 };
-      if (getenv("DEXB200_PACK2") != NULL)
+      if (ctx->route[DXR_PACK2])
         rc = dxk_fa_pack2(ctx,kind,d_text,ent,0,d_out + hbytes,d_flags + 1,(unsigned long long *) (d_flags + 2),0);
       else
         rc = dxk_fa_pack3(ctx,kind,d_text,n,ent,0,d_out + hbytes,d_flags + 1,d_flags + 4,
@@ -756,7 +773,7 @@ static int undexta_fast(dx_ctx *ctx, int kind, const uint8_t *d_in, size_t n, in
                         uint8_t *d_out, size_t cap, size_t *out_len, bool *handled)
 { int rc;
   *handled = false;
-  if (width < 16 || getenv("DEXB200_NO_FAST") != NULL) return DX_OK;
+  if (width < 16 || ctx->route[DXR_NO_FAST]) return DX_OK;
   std::vector<uint8_t> head;
   if ((rc = peek(ctx,d_in,n,0,6,head)) != DX_OK) return rc;
   if (head.size() < 6) return DX_OK;
@@ -829,7 +846,7 @@ static int undexta_fast(dx_ctx *ctx, int kind, const uint8_t *d_in, size_t n, in
   const size_t total = (size_t) *h_total;
   if (d_out != NULL)
     { if (total > cap) return dx_fail(ctx,DX_E_CAP,"output needs %zu bytes, buffer has %zu",total,cap);
-      if (getenv("DEXB200_PACK2") != NULL)
+      if (ctx->route[DXR_PACK2])
         rc = dxk_unpack2(ctx,kind,upper,width,d_in,n,d_ent,(int64_t) M,d_prefix,plen,d_out,d_ticket);
       else
         rc = dxk_unpack3(ctx,kind,upper,width,d_in,n,d_ent,(int64_t) M,d_prefix,plen,d_out,d_ticket);
@@ -898,7 +915,7 @@ extern "C" int dx_compress_reads_dev(dx_ctx *ctx, int kind, const uint8_t *d_src
 { if (ctx == NULL || nreads < 0) return DX_E_ARG;
   cudaSetDevice(ctx->device);
   dx_arena_reset(ctx);
-  if (getenv("DEXB200_EXACT_PACK") != NULL)
+  if (ctx->route[DXR_EXACT_PACK])
     return dxk_compress_reads(ctx,kind,d_src,d_src_off,d_len,nreads,d_dst,d_dst_off);
   return dxk_compress_reads2(ctx,kind,d_src,d_src_off,d_len,nreads,d_dst,d_dst_off);
 }
@@ -909,7 +926,7 @@ extern "C" int dx_uncompress_reads_dev(dx_ctx *ctx, int kind, int upper, const u
 { if (ctx == NULL || nreads < 0) return DX_E_ARG;
   cudaSetDevice(ctx->device);
   dx_arena_reset(ctx);
-  if (getenv("DEXB200_EXACT_PACK") != NULL)
+  if (ctx->route[DXR_EXACT_PACK])
     return dxk_uncompress_reads(ctx,kind,upper,d_src,d_src_off,d_len,nreads,d_dst,d_dst_off);
   return dxk_uncompress_reads2(ctx,kind,upper,d_src,d_src_off,d_len,nreads,d_dst,d_dst_off);
 }
@@ -1247,14 +1264,12 @@ static bool build_dec_tables4(const dx_qv_coding *c, QvDecTables4 *t)
 
 struct QvPlan
 { std::vector<QvDecEntry> ent;
-  bool         v2;            // parallel decoder usable
-  int          ver;           // which parallel kernel: 2, 3, 4 or 5 (default)
+  bool         v2;            // parallel decoders usable (tables fit shared memory)
   QvDecTables4 *d_tab4;
   int64_t     *d_soff;        // v1 only: [count][6] device
   int64_t     *d_start;       // v2: first stream byte of every entry
   int32_t     *d_rlen;        // v2
   QvDecTables  *d_tab;
-  QvDecTables2 *d_tab2;
   char        *d_prefix;
   int          plen;
   dx_qv_coding coding;
@@ -1283,12 +1298,57 @@ static void ticket_order(const int32_t *rlen, size_t N, int32_t *order)
   for (size_t i = 0; i < N; i++) order[count[bucket(rlen[i])]++] = (int32_t) i;
 }
 
-static void lpt_order(const std::vector<CandInfo> &info, std::vector<int32_t> &order)
+// ... and the cut between the two parallel decoders: the first n_coop tickets (the longest entries)
+// go to the warp-per-entry kernel, the others are decoded one entry per lane (dx_qv_decode6.cu).
+// A lane walks its entry alone, ~kLaneNs per position, so the lane kernel lasts at least as long as
+// its longest entry; below that bound it is limited by instruction issue (kLaneGBs of text), the
+// warp kernel always is (kCoopGBs).  The cut that minimises the sum of the two launches is found on
+// the 512 length buckets of the counting sort.
+static int64_t ticket_plan(const dx_ctx *ctx, const int32_t *rlen, size_t N, int32_t *order)
+{ enum { kBuckets = 512 };
+  const double kLaneNs = 55e-9, kLaneGBs = 1500e9, kCoopGBs = 460e9, kLaunch = 8e-6;
+  ticket_order(rlen,N,order);
+  const int64_t mode = ctx->route[DXR_DECODER];
+  if (mode == 5 || N == 0) return (int64_t) N;
+  if (mode == 6) return 0;
+  static thread_local double bsum[kBuckets];
+  static thread_local int64_t bcnt[kBuckets];
+  for (int b = 0; b < kBuckets; b++) { bsum[b] = 0; bcnt[b] = 0; }
+  double all = 0;
+  for (size_t i = 0; i < N; i++)
+    { const int32_t rl = rlen[i];
+      const int b = (rl <= 0) ? 0 : ((rl >> 9) >= kBuckets ? kBuckets - 1 : (rl >> 9));
+      bsum[b] += (rl > 0) ? 5.0*rl : 0.0; bcnt[b]++;
+      all += (rl > 0) ? 5.0*rl : 0.0;
+    }
+  if (ctx->route[DXR_LANE_MAX_RLEN] > 0)
+    { int64_t nc = 0;
+      const int64_t cutb = ctx->route[DXR_LANE_MAX_RLEN] >> 9;
+      for (int b = kBuckets - 1; b > cutb; b--) nc += bcnt[b];
+      return nc;
+    }
+  // cut after bucket c: buckets > c coop, <= c lane
+  double best = all / kCoopGBs + kLaunch, coop = 0;
+  int64_t best_n = (int64_t) N, ncoop = 0;
+  for (int c = kBuckets - 1; c >= 0; c--)
+    { // lane part = buckets 0..c
+      const double lane_bytes = all - coop;
+      const double t_lane = std::max((double) ((c + 1) << 9) * kLaneNs,lane_bytes / kLaneGBs) + kLaunch;
+      const double t = t_lane + (ncoop > 0 ? coop / kCoopGBs + kLaunch : 0.0);
+      if (t < best && (int64_t) N - ncoop > 0) { best = t; best_n = ncoop; }
+      coop += bsum[c]; ncoop += bcnt[c];
+    }
+  const int64_t minlane = ctx->route[DXR_LANE_MIN_ENTRIES] > 0 ? ctx->route[DXR_LANE_MIN_ENTRIES] : 1;
+  if ((int64_t) N - best_n < minlane) return (int64_t) N;
+  return best_n;
+}
+
+static int64_t lpt_order(const dx_ctx *ctx, const std::vector<CandInfo> &info, std::vector<int32_t> &order)
 { const size_t N = info.size();
   std::vector<int32_t> rl(N);
   for (size_t i = 0; i < N; i++) rl[i] = le32(info[i].field+4) - le32(info[i].field);
   order.resize(N);
-  ticket_order(rl.data(),N,order.data());
+  return ticket_plan(ctx,rl.data(),N,order.data());
 }
 
 struct QvWalkUser
@@ -1301,12 +1361,9 @@ static int qv_walk(dx_ctx *ctx, const uint8_t *d_in, size_t n, const QvPlan &pla
                    const int64_t *d_start, const int32_t *d_rlen, int64_t count,
                    int64_t *d_soff, int32_t *d_stat)
 { const dx_qv_coding &cd = plan.coding;
-  if (plan.v2 && plan.ver >= 4)
-    return (plan.ver == 5 ? dxk_qv_decode5 : dxk_qv_decode4)(ctx,d_in,n,plan.d_tab4,cd.delchar,cd.subchar,0,0,count,d_start,d_rlen,
-                          NULL,NULL,0,NULL,d_soff,d_stat);
   if (plan.v2)
-    return (plan.ver == 3 ? dxk_qv_decode3 : dxk_qv_decode2)(ctx,d_in,n,plan.d_tab2,cd.delchar,cd.subchar,
-                          0,0,count,d_start,d_rlen,NULL,NULL,0,NULL,d_soff,d_stat);
+    return dxk_qv_decode5(ctx,d_in,n,plan.d_tab4,cd.delchar,cd.subchar,0,0,count,d_start,d_rlen,
+                          NULL,NULL,0,NULL,d_soff,d_stat);
   return dxk_qv_walk(ctx,d_in,n,plan.d_tab,cd.delchar,cd.subchar,cd.flip,d_start,d_rlen,count,
                      d_soff,d_stat);
 }
@@ -1354,39 +1411,22 @@ static int plan_undexqv(dx_ctx *ctx, const uint8_t *d_in, size_t n, const int64_
   if (plan.coding.flip)
     return dx_fail(ctx,DX_E_KEY,"foreign-endian .dexqv is not supported");
   const size_t first = 2 + used;
-  DxPhases ph;
+  DxPhases ph(ctx);
   plan.plen = (int) strlen(prefix.data());
-  plan.d_soff = NULL; plan.d_start = NULL; plan.d_rlen = NULL; plan.d_tab = NULL; plan.d_tab2 = NULL;
+  plan.d_soff = NULL; plan.d_start = NULL; plan.d_rlen = NULL; plan.d_tab = NULL;
   plan.spec = false; plan.d_tmp = NULL; plan.tmp_n = 0; plan.src.clear();
 
-  { QvDecTables2 *h2 = (QvDecTables2 *) malloc(sizeof(QvDecTables2));
-    if (h2 == NULL) return DX_E_NOMEM;
-    plan.v2 = build_dec_tables2(&plan.coding,h2);
-    { const char *force = getenv("DEXB200_DECODER");        // "v1": sequential kernels (testing)
-      if (force != NULL && strcmp(force,"v1") == 0) plan.v2 = false;
-      plan.ver = 5;
-      if (force != NULL && strcmp(force,"v4") == 0) plan.ver = 4;
-      if (force != NULL && strcmp(force,"v2") == 0) plan.ver = 2;
-      if (force != NULL && strcmp(force,"v3") == 0) plan.ver = 3;
-    }
+  { // 12-bit shared-memory tables for the parallel kernels; a coding they cannot hold (more long
+    // codes than the sub-tables take) is decoded by the sequential kernels of dx_qv_decode.cu
+    QvDecTables4 *h4 = (QvDecTables4 *) malloc(sizeof(QvDecTables4));
+    if (h4 == NULL) return DX_E_NOMEM;
+    plan.v2 = (ctx->route[DXR_DECODER] != 1) && build_dec_tables4(&plan.coding,h4);
     plan.d_tab4 = NULL;
-    if (plan.v2 && plan.ver >= 4)
-      { QvDecTables4 *h4 = (QvDecTables4 *) malloc(sizeof(QvDecTables4));
-        if (h4 == NULL) { free(h2); return DX_E_NOMEM; }
-        if (build_dec_tables4(&plan.coding,h4))
-          { plan.d_tab4 = (QvDecTables4 *) dx_arena_get(ctx,sizeof(QvDecTables4));
-            rc = plan.d_tab4 ? upload(ctx,plan.d_tab4,h4,1) : DX_E_NOMEM;
-          }
-        else
-          plan.ver = 3;
-        free(h4);
-        if (rc != DX_OK) { free(h2); return rc; }
+    if (plan.v2)
+      { plan.d_tab4 = (QvDecTables4 *) dx_arena_get(ctx,sizeof(QvDecTables4));
+        rc = plan.d_tab4 ? upload(ctx,plan.d_tab4,h4,1) : DX_E_NOMEM;
       }
-    if (plan.v2 && plan.ver < 4)
-      { plan.d_tab2 = (QvDecTables2 *) dx_arena_get(ctx,sizeof(QvDecTables2));
-        rc = plan.d_tab2 ? upload(ctx,plan.d_tab2,h2,1) : DX_E_NOMEM;
-      }
-    free(h2);
+    free(h4);
     if (rc != DX_OK) return rc;
   }
   if (!plan.v2)
@@ -1472,7 +1512,7 @@ static int plan_undexqv(dx_ctx *ctx, const uint8_t *d_in, size_t n, const int64_
       if ((rc = download(ctx,d_info,N,info)) != DX_OK) return rc;
       ph.mark("context");
       std::vector<int64_t> tmp_off(N + 1,0);
-      if (need_streams && plan.v2 && plan.ver == 5 && getenv("DEXB200_NO_SPEC") == NULL)
+      if (need_streams && plan.v2 && !ctx->route[DXR_NO_SPEC])
         { // decode every candidate right away into a scratch image laid out by the candidates'
           // own lengths; the chain below decides which of them are entries
           for (size_t i = 0; i < N; i++)
@@ -1527,20 +1567,20 @@ static int plan_undexqv(dx_ctx *ctx, const uint8_t *d_in, size_t n, const int64_
                 { rl[i] = -1; skipped++; }
             if (skipped)
               if ((rc = upload(ctx,d_rlen,rl.data(),N)) != DX_OK) return rc;
-            if (getenv("DEXB200_DEBUG") != NULL)
+            if (ctx->route[DXR_DEBUG])
               fprintf(stderr,"[dexb200 debug] undexqv: %zu of %zu candidates cannot fit (min %d bits/position)\n",
                       skipped,N,minbits);
           }
           std::vector<int32_t> order;
-          lpt_order(info,order);
+          const int64_t n_coop = lpt_order(ctx,info,order);
           int64_t *d_limit = (int64_t *) dx_arena_get(ctx,N*8);
           int32_t *d_order = (int32_t *) dx_arena_get(ctx,N*4);
           if (!d_limit || !d_order) return DX_E_NOMEM;
           if ((rc = upload(ctx,d_limit,limit.data(),N)) != DX_OK) return rc;
           if ((rc = upload(ctx,d_order,order.data(),N)) != DX_OK) return rc;
           const dx_qv_coding &cd = plan.coding;
-          if ((rc = dxk_qv_decode5x(ctx,d_in,n,plan.d_tab4,cd.delchar,cd.subchar,upper,2,nc,d_fs,d_rlen,
-                                    d_cent,NULL,0,plan.d_tmp,d_soffc,d_stat,d_limit,d_order,NULL)) != DX_OK) return rc;
+          if ((rc = dxk_qv_decode6x(ctx,d_in,n,plan.d_tab4,cd.delchar,cd.subchar,upper,2,nc,d_fs,d_rlen,
+                                    d_cent,NULL,0,plan.d_tmp,d_soffc,d_stat,d_limit,d_order,NULL,n_coop)) != DX_OK) return rc;
           plan.spec = true;
         }
       else if ((rc = qv_walk(ctx,d_in,n,plan,d_fs,d_rlen,nc,d_soffc,d_stat)) != DX_OK) return rc;
@@ -1558,7 +1598,7 @@ static int plan_undexqv(dx_ctx *ctx, const uint8_t *d_in, size_t n, const int64_
         return rc;
       ph.mark("chain");
       const size_t M = chain.size();
-      if (getenv("DEXB200_DEBUG") != NULL)
+      if (ctx->route[DXR_DEBUG])
         { int64_t sumrl = 0, maxrl = 0;
           for (size_t i = 0; i < N; i++)
             { const int64_t rl = (int64_t) le32(info[i].field+4) - le32(info[i].field);
@@ -1633,10 +1673,8 @@ static int undexqv_fast(dx_ctx *ctx, const uint8_t *d_in, size_t n, int upper, u
                         bool *handled)
 { int rc;
   *handled = false;
-  DxPhases ph;
-  { const char *force = getenv("DEXB200_DECODER");
-    if (force != NULL || getenv("DEXB200_NO_SPEC") != NULL || getenv("DEXB200_NO_FAST") != NULL) return DX_OK;
-  }
+  DxPhases ph(ctx);
+  if (ctx->route[DXR_DECODER] == 1 || ctx->route[DXR_NO_SPEC] || ctx->route[DXR_NO_FAST]) return DX_OK;
   std::vector<uint8_t> head;
   if ((rc = peek(ctx,d_in,n,0,2 + 16384 + 100000,head)) != DX_OK) return rc;
   if (head.size() < 2) return DX_OK;
@@ -1723,10 +1761,10 @@ static int undexqv_fast(dx_ctx *ctx, const uint8_t *d_in, size_t n, int upper, u
       if (h_tail->flag == 2) return dx_fail(ctx,DX_E_FORMAT,"unusable read length in an entry header");
       if ((size_t) h_tail->total > cap)
         return dx_fail(ctx,DX_E_CAP,"output needs %lld bytes, buffer has %zu",(long long) h_tail->total,cap);
-      ticket_order(h_rlen,N,h_order);
+      const int64_t n_coop = ticket_plan(ctx,h_rlen,N,h_order);
       DX_CUDA(ctx,cudaMemcpyAsync(d_order,h_order,N*4,cudaMemcpyHostToDevice,ctx->stream));
-      if ((rc = dxk_qv_decode5x(ctx,d_in,n,d_tab4,coding.delchar,coding.subchar,upper,1,(int64_t) N,pa.fs,pa.rlen,
-                                d_ent,d_prefix,plen,d_out,NULL,d_stat1,NULL,d_order,NULL)) != DX_OK) return rc;
+      if ((rc = dxk_qv_decode6x(ctx,d_in,n,d_tab4,coding.delchar,coding.subchar,upper,1,(int64_t) N,pa.fs,pa.rlen,
+                                d_ent,d_prefix,plen,d_out,NULL,d_stat1,NULL,d_order,NULL,n_coop)) != DX_OK) return rc;
       DX_CUDA(ctx,cudaMemcpyAsync(&h_tail->flag,d_stat1,4,cudaMemcpyDeviceToHost,ctx->stream));
       DX_CUDA(ctx,cudaStreamSynchronize(ctx->stream));
       ph.mark("decode");
@@ -1791,13 +1829,13 @@ static int undexqv_fast(dx_ctx *ctx, const uint8_t *d_in, size_t n, int upper, u
   DX_CUDA(ctx,cudaMemcpyAsync(&h_tail->total,d_toff+N,8,cudaMemcpyDeviceToHost,ctx->stream));
   DX_CUDA(ctx,cudaStreamSynchronize(ctx->stream));
   ph.mark("prep");
-  ticket_order(h_rlen,N,h_order);
+  const int64_t n_coop = ticket_plan(ctx,h_rlen,N,h_order);
   DX_CUDA(ctx,cudaMemcpyAsync(d_order,h_order,N*4,cudaMemcpyHostToDevice,ctx->stream));
   const size_t tmp_n = (size_t) h_tail->total;
   uint8_t *d_tmp = (uint8_t *) dx_arena_get(ctx,tmp_n + 64);
   if (d_tmp == NULL) return DX_E_NOMEM;
-  if ((rc = dxk_qv_decode5x(ctx,d_in,n,d_tab4,coding.delchar,coding.subchar,upper,2,nc,pa.fs,pa.rlen,NULL,NULL,0,
-                            d_tmp,d_soff,d_stat,d_limit,d_order,d_toff)) != DX_OK) return rc;
+  if ((rc = dxk_qv_decode6x(ctx,d_in,n,d_tab4,coding.delchar,coding.subchar,upper,2,nc,pa.fs,pa.rlen,NULL,NULL,0,
+                            d_tmp,d_soff,d_stat,d_limit,d_order,d_toff,n_coop)) != DX_OK) return rc;
   DX_CUDA(ctx,cudaMemcpyAsync(h_soff,d_soff,N*48,cudaMemcpyDeviceToHost,ctx->stream));
   DX_CUDA(ctx,cudaMemcpyAsync(h_stat,d_stat,N*4,cudaMemcpyDeviceToHost,ctx->stream));
   DX_CUDA(ctx,cudaStreamSynchronize(ctx->stream));
@@ -1923,13 +1961,9 @@ extern "C" int dx_undexqv_dev(dx_ctx *ctx, const uint8_t *d_in, size_t n, int up
                               plan.d_prefix,plan.plen,d_out,NULL,d_stat);
         }
     }
-  else if (plan.v2 && plan.ver >= 4)
-    rc = (plan.ver == 5 ? dxk_qv_decode5 : dxk_qv_decode4)(ctx,d_in,n,plan.d_tab4,cd.delchar,cd.subchar,upper,1,(int64_t) N,
-                        plan.d_start,plan.d_rlen,d_ent,plan.d_prefix,plan.plen,d_out,NULL,d_stat);
   else if (plan.v2)
-    rc = (plan.ver == 3 ? dxk_qv_decode3 : dxk_qv_decode2)(ctx,d_in,n,plan.d_tab2,cd.delchar,cd.subchar,
-                        upper,1,(int64_t) N,plan.d_start,plan.d_rlen,d_ent,plan.d_prefix,plan.plen,
-                        d_out,NULL,d_stat);
+    rc = dxk_qv_decode5(ctx,d_in,n,plan.d_tab4,cd.delchar,cd.subchar,upper,1,(int64_t) N,
+                        plan.d_start,plan.d_rlen,d_ent,plan.d_prefix,plan.plen,d_out,NULL,d_stat);
   else
     rc = dxk_qv_decode(ctx,d_in,n,plan.d_tab,cd.delchar,cd.subchar,cd.flip,upper,d_ent,plan.d_soff,
                        (int64_t) N,plan.d_prefix,plan.plen,d_out,d_stat);

@@ -252,7 +252,7 @@ k_chain_scan(const uint32_t *count, int64_t n, int64_t *prefix, unsigned long lo
 
 // exclusive scan of n 32-bit values into 64-bit offsets, total at prefix[n]
 static int launch_scan(dx_ctx *ctx, const uint32_t *d_in, int64_t n, int64_t *d_prefix, const char *what)
-{ const bool small_tiles = (getenv("DEXB200_CHAIN_SCAN") != NULL);       // tests: tiles of 256 values
+{ const bool small_tiles = (ctx->route[DXR_CHAIN_SCAN] != 0);       // tests: tiles of 256 values
   if (n == 0 || (n <= 2*kChainTile && !small_tiles))
     { DX_PROF_BEGIN(ctx); k_tile_scan<<<1,1024,0,ctx->stream>>>(d_in,n,d_prefix);
       DX_LAUNCHED(ctx,what);
@@ -459,7 +459,7 @@ int index_positions(dx_ctx *ctx, const uint8_t *buf, size_t n, size_t first,
 { const int64_t ntiles = (int64_t) ((n + kTileBytes - 1) / kTileBytes);
   *d_pos = NULL; *count = 0;
   if (ntiles == 0) return DX_OK;
-  if (getenv("DEXB200_EXACT_INDEX") != NULL) return index_positions_exact<PRED>(ctx,buf,n,first,d_pos,count);
+  if (ctx->route[DXR_EXACT_INDEX]) return index_positions_exact<PRED>(ctx,buf,n,first,d_pos,count);
   uint32_t *d_cnt  = (uint32_t *) dx_arena_get(ctx,(size_t) ntiles*4 + 16);
   int64_t  *d_pre  = (int64_t *)  dx_arena_get(ctx,(size_t) (ntiles+1)*8);
   int64_t  *d_slot = (int64_t *)  dx_arena_get(ctx,(size_t) ntiles*kSlot*8);

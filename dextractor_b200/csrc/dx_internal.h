@@ -69,6 +69,16 @@ struct QvDecTables4
 
 struct DxBlock { uint8_t *p; size_t cap, top; };
 
+// Routes: which of the alternative paths a call takes.  All zero = the product's defaults; the
+// others exist so that tests can force every path (dx_route, include/dexb200.h).  Read from the
+// context, never from the environment, inside the entry points.
+enum { DXR_NO_FAST = 0, DXR_NO_SPEC, DXR_EXACT_INDEX, DXR_EXACT_PACK, DXR_PACK2, DXR_TWO_PASS, DXR_CHAIN_SCAN,
+       DXR_DECODER,            // 0 default (lane per entry + warp per entry for long ones), 1 sequential,
+                               // 5 warp per entry only, 6 lane per entry only
+       DXR_LANE_MAX_RLEN,      // > 0: entries longer than this go to the warp-per-entry kernel
+       DXR_LANE_MIN_ENTRIES,   // > 0: fewer lane-sized entries than this -> warp per entry for all
+       DXR_DEBUG, DXR_SERIAL_IO, DXR_COUNT };
+
 struct dx_ctx
 { int          device;
   cudaStream_t stream;
@@ -76,6 +86,7 @@ struct dx_ctx
   char         err[512];
   int64_t      err_line;
   uint64_t     launches;
+  int64_t      route[DXR_COUNT];
 
   // scratch arena in HBM: a bump allocator over a few cudaMalloc'ed blocks, reset per call and
   // consolidated into one block when a call needed more than one
@@ -168,24 +179,6 @@ int dxk_qv_decode(dx_ctx *ctx, const uint8_t *d_in, size_t n, const QvDecTables 
                   const int64_t *d_soff, int64_t count, const char *d_prefix, int plen,
                   uint8_t *d_out, int32_t *d_status /*[1]*/);
 
-// dx_qv_decode2.cu : one CTA per entry, speculative parallel decoding inside every stream.
-// write = 0: only walk (d_soff[count][6], d_status[count]); write = 1: produce the text.
-int dxk_qv_decode2(dx_ctx *ctx, const uint8_t *d_in, size_t n, const QvDecTables2 *d_tab,
-                   int delchar, int subchar, int upper, int write, int64_t count,
-                   const int64_t *d_start, const int32_t *d_rlen, const QvDecEntry *d_ent,
-                   const char *d_prefix, int plen, uint8_t *d_out, int64_t *d_soff, int32_t *d_status);
-
-// dx_qv_decode3.cu : same contract as dxk_qv_decode2; checkpointed speculation, staged bit window
-int dxk_qv_decode3(dx_ctx *ctx, const uint8_t *d_in, size_t n, const QvDecTables2 *d_tab,
-                   int delchar, int subchar, int upper, int write, int64_t count,
-                   const int64_t *d_start, const int32_t *d_rlen, const QvDecEntry *d_ent,
-                   const char *d_prefix, int plen, uint8_t *d_out, int64_t *d_soff, int32_t *d_status);
-
-int dxk_qv_decode4(dx_ctx *ctx, const uint8_t *d_in, size_t n, const QvDecTables4 *d_tab,
-                   int delchar, int subchar, int upper, int write, int64_t count,
-                   const int64_t *d_start, const int32_t *d_rlen, const QvDecEntry *d_ent,
-                   const char *d_prefix, int plen, uint8_t *d_out, int64_t *d_soff, int32_t *d_status);
-
 // dx_qv_decode5.cu : one warp per entry, tables resident in shared memory (same contract)
 int dxk_qv_decode5(dx_ctx *ctx, const uint8_t *d_in, size_t n, const QvDecTables4 *d_tab,
                    int delchar, int subchar, int upper, int write, int64_t count,
@@ -199,6 +192,14 @@ int dxk_qv_decode5x(dx_ctx *ctx, const uint8_t *d_in, size_t n, const QvDecTable
                     const int64_t *d_start, const int32_t *d_rlen, const QvDecEntry *d_ent,
                     const char *d_prefix, int plen, uint8_t *d_out, int64_t *d_soff, int32_t *d_status,
                     const int64_t *d_limit, const int32_t *d_order, const int64_t *d_toff);
+
+// dx_qv_decode6.cu : one LANE per entry for tickets [n_coop, count), the warp-per-entry kernel for
+// tickets [0, n_coop) (the longest entries); write = 1 or 2
+int dxk_qv_decode6x(dx_ctx *ctx, const uint8_t *d_in, size_t n, const QvDecTables4 *d_tab,
+                    int delchar, int subchar, int upper, int write, int64_t count,
+                    const int64_t *d_start, const int32_t *d_rlen, const QvDecEntry *d_ent,
+                    const char *d_prefix, int plen, uint8_t *d_out, int64_t *d_soff, int32_t *d_status,
+                    const int64_t *d_limit, const int32_t *d_order, const int64_t *d_toff, int64_t n_coop);
 
 // move speculatively decoded lines (scratch image d_tmp, entry e at d_src[e], < 0 = skip) to their
 // final place and write the header lines

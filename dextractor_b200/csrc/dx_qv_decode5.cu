@@ -702,27 +702,11 @@ int dxk_qv_decode5x(dx_ctx *ctx, const uint8_t *d_in, size_t n, const QvDecTable
   a.ticket = d_ticket;
   a.limit = d_limit; a.order = d_order; a.toff = d_toff;
   a.dbg = NULL;
-  if (getenv("DEXB200_DEBUG_DEC") != NULL)
-    { a.dbg = (unsigned long long *) dx_arena_get(ctx,32*8);
-      if (a.dbg == NULL) return DX_E_NOMEM;
-      DX_CUDA(ctx,cudaMemsetAsync(a.dbg,0,32*8,ctx->stream));
-    }
   const size_t smem = sizeof(Shared5);
   DX_CUDA(ctx,cudaFuncSetAttribute(k_qv_decode5,cudaFuncAttributeMaxDynamicSharedMemorySize,(int) smem));
   int64_t grid = (count + kWarps - 1) / kWarps;
   if (grid > ctx->sm_count) grid = ctx->sm_count;
   DX_PROF_BEGIN(ctx); k_qv_decode5<<<(unsigned) grid,kThreads,smem,ctx->stream>>>(a);
   DX_LAUNCHED(ctx,write == 1 ? "k_qv_decode5" : write == 2 ? "k_qv_decode5_spec" : "k_qv_walk5");
-  if (a.dbg != NULL)
-    { unsigned long long h[32];
-      DX_CUDA(ctx,cudaMemcpyAsync(h,a.dbg,sizeof(h),cudaMemcpyDeviceToHost,ctx->stream));
-      DX_CUDA(ctx,cudaStreamSynchronize(ctx->stream));
-      for (int k = 0; k < 5; k++)
-        if (h[k*4+2])
-          fprintf(stderr,"[dexb200 debug] v5 table %d: streams %llu windows/stream %.2f rounds/window %.2f "
-                         "restarts/window %.1f\n",
-                  k,h[k*4+2],(double) h[k*4+1]/h[k*4+2],(double) h[k*4]/(h[k*4+1] ? h[k*4+1] : 1),
-                  (double) h[k*4+3]/(h[k*4+1] ? h[k*4+1] : 1));
-    }
   return DX_OK;
 }

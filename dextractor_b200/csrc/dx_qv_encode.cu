@@ -545,7 +545,7 @@ int dxk_qv_encode(dx_ctx *ctx, const uint8_t *d_text, size_t text_n, QvEntries e
       DX_LAUNCHED(ctx,"k_qv_offsets");
       return dxk_scan_u32(ctx,d_tot,n,d_off);
     };
-  if (getenv("DEXB200_TWO_PASS") == NULL)
+  if (!ctx->route[DXR_TWO_PASS])
     { // code into a scratch image first, then move the streams to where their lengths put them
       const size_t sbytes = ((text_n + (size_t) n*40 + 15) & ~(size_t) 15) + 32;
       uint8_t *d_scratch = (uint8_t *) dx_arena_get(ctx,sbytes);

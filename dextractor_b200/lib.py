@@ -19,7 +19,7 @@ ERRNAMES = {-1: "FORMAT", -2: "CAP", -3: "TRUNC", -4: "KEY", -5: "LINELEN", -6: 
 SYMBOLS = [
     "dx_open", "dx_close", "dx_strerror", "dx_error_line", "dx_sync", "dx_stream",
     "dx_device_alloc", "dx_device_free", "dx_pinned_alloc", "dx_pinned_free", "dx_h2d", "dx_d2h",
-    "dx_launch_count", "dx_profile", "dx_profile_report",
+    "dx_launch_count", "dx_profile", "dx_profile_report", "dx_route",
     "dx_dexta_dev", "dx_dexta_host", "dx_undexta_dev", "dx_undexta_host", "dx_undexta_size_host",
     "dx_undexta_size_dev",
     "dx_compress_reads_dev", "dx_uncompress_reads_dev",
@@ -108,6 +108,7 @@ def load_library():
         "dx_d2h": (C.c_int, [vp, vp, vp, sz]),
         "dx_launch_count": (C.c_uint64, [vp, C.c_int]),
         "dx_profile": (C.c_int, [vp, C.c_int]),
+        "dx_route": (C.c_int, [vp, C.c_char_p, i64]),
         "dx_profile_report": (C.c_int, [vp, C.c_char_p, sz]),
         "dx_dexta_dev": (C.c_int, [vp, C.c_int, vp, sz, vp, sz, szp]),
         "dx_dexta_host": (C.c_int, [vp, C.c_int, vp, sz, vp, sz, szp]),
@@ -215,6 +216,10 @@ class Context:
         src = np.frombuffer(data, dtype=np.uint8)
         self._check(self.L.dx_h2d(self.h, d_dst, src.ctypes.data, len(data)))
         self.sync()
+
+    def route(self, name: str = "default", value: int = 1):
+        """test hook: force an alternative path (dx_route); route() resets every route"""
+        self._check(self.L.dx_route(self.h, name.encode(), int(value)))
 
     def profile(self, enable: bool):
         self._check(self.L.dx_profile(self.h, int(enable)))

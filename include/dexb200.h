@@ -63,6 +63,14 @@ int   dx_d2h(dx_ctx *ctx, void *h_dst, const void *d_src, size_t bytes);   /* as
 /* launches issued by this context since the last reset (for the bench's gpu_launches claim) */
 uint64_t dx_launch_count(dx_ctx *ctx, int reset);
 
+/* Test hook: force one of the library's alternative paths on this context (the default for every
+ * route is 0 = the product's choice).  Names: "no_fast", "no_spec" (host-planned undex* paths),
+ * "exact_index", "exact_pack", "pack2", "two_pass", "chain_scan", "decoder" (1 sequential kernels,
+ * 5 warp-per-entry kernel only, 6 lane-per-entry kernel only), "lane_max_rlen", "lane_min_entries",
+ * "serial_io" (the *_host calls copy, compute, copy without overlap), "debug"; "default" resets all.
+ * No reference counterpart; nothing in the library reads the environment inside a call. */
+int dx_route(dx_ctx *ctx, const char *name, int64_t value);
+
 /* Per-kernel device timing.  While enabled every kernel launch of this context is bracketed by
  * CUDA events on the context's stream; dx_profile_report waits for the stream, writes one line
  * per kernel name -- "name calls total_ms" -- into buf and clears the records. */

@@ -1,21 +1,21 @@
 #!/bin/bash
-# development loop on the GPU box: parity tests (stop at first failure), one bench, and a small
-# run with the decoder's debug counters.  args: bench size in GB (default 2), extra bench args
+# development loop: targeted tests, then a short bench.   usage: gpu_dev.sh "<pytest -k expr>" [bench args...]
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-make -s -C tools > /dev/null 2>&1
-echo "== pytest gpu" ; timeout 1500 python -m pytest tests -m gpu -q --tb=short -p no:cacheprovider -x > gpurun_out/pytest_gpu.log 2>&1 ; echo "pytest rc=$?" ; tail -25 gpurun_out/pytest_gpu.log
-echo "== bench" ; timeout 1500 python bench.py --size-gb ${1:-2} --no-cpu $2 $3 $4 > gpurun_out/bench.json 2> gpurun_out/bench.err ; echo "rc=$?" ; python - <<'PY'
+K=${1:-lane}; shift
+timeout 900 python -m pytest tests -q -m gpu -x -k "$K" > gpurun_out/dev_pytest.log 2>&1; echo "pytest rc=$?"; tail -25 gpurun_out/dev_pytest.log
+if [ "$1" != "nobench" ]; then
+timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu "$@" > gpurun_out/dev_bench.json 2> gpurun_out/dev_bench.err; echo "bench rc=$?"
+tail -3 gpurun_out/dev_bench.err
+python - <<'PY'
 import json
 try:
-    d=json.load(open('gpurun_out/bench.json'))
-    print("value",round(d['value'],2),"GB/s  ms/step",round(d['ms_per_step'],2),"e2e",round(d['e2e']['value'],2))
-    print({k:(round(v,2) if isinstance(v,float) else v) for k,v in d['extra'].items() if k!='kernels_ms_per_step'})
+    d=json.loads(open('gpurun_out/dev_bench.json').read().strip().splitlines()[-1])
+    print({k:d[k] for k in ('value','ms_per_step','gpu_launches')}, 'e2e', d['e2e']['value'])
+    print(d['roofline'])
+    print({k:v['ms'] for k,v in d['path_roofline'].items()})
     print(d['extra']['kernels_ms_per_step'])
-    print(d['roofline']); print(d['path_roofline'])
-except Exception as e:
-    print("bench parse failed",e)
+    print({k:v for k,v in d['extra'].items() if k in ('dexta_gbs','undexta_gbs','dexar_gbs','undexar_gbs','length_sweep')})
+except Exception as e: print('no bench line', e)
 PY
-tail -15 gpurun_out/bench.err
-echo "== debug counters (0.25 GB)"
-DEXB200_DEBUG=1 timeout 600 python bench.py --size-gb 0.25 --steps 1 --warmup 3 --no-cpu --no-extras 2>&1 >/dev/null | grep debug | tail -12
+fi

@@ -9,6 +9,7 @@ import pytest
 import dextractor_b200 as dx
 from dextractor_b200 import synth
 from tests import cases
+from tests.test_gpu_parity import first_diff
 
 pytestmark = pytest.mark.gpu
 
@@ -26,22 +27,37 @@ def ctx():
 
 ROUTES = [
     {},                                                  # the default routes
-    {"DEXB200_NO_FAST": "1"},                            # host-planned decoders
-    {"DEXB200_NO_FAST": "1", "DEXB200_NO_SPEC": "1"},    # ... with a separate walk of all candidates
-    {"DEXB200_EXACT_INDEX": "1"},                        # two-pass position index
-    {"DEXB200_EXACT_PACK": "1"},                         # counted symbol lengths, byte-serial packer
-    {"DEXB200_PACK2": "1"},                              # input-centric vectorised 2-bit kernels (scan + bit writer)
-    {"DEXB200_TWO_PASS": "1"},                           # dexqv with a size pass instead of the scratch image
-    {"DEXB200_CHAIN_SCAN": "1"},                         # the multi-CTA prefix sums also on small arrays
-    {"DEXB200_DECODER": "v1"},                           # sequential decode kernels
-    {"DEXB200_DECODER": "v4"},                           # CTA-per-entry parallel decoder
+    {"no_fast": 1},                                      # host-planned decoders
+    {"no_fast": 1, "no_spec": 1},                        # ... with a separate walk of all candidates
+    {"exact_index": 1},                                  # two-pass position index
+    {"exact_pack": 1},                                   # counted symbol lengths, byte-serial packer
+    {"pack2": 1},                                        # input-centric vectorised 2-bit kernels (scan + bit writer)
+    {"two_pass": 1},                                     # dexqv with a size pass instead of the scratch image
+    {"chain_scan": 1},                                   # the multi-CTA prefix sums also on small arrays
+    {"decoder": 1},                                      # sequential decode kernels
+    {"decoder": 5},                                      # warp-per-entry decoder for every entry
+    {"decoder": 6},                                      # lane-per-entry decoder for every entry
+    {"lane_max_rlen": 3000},                             # both parallel decoders in one call
+    {"decoder": 6, "no_fast": 1},                        # lane-per-entry decoder behind the host-planned path
 ]
 
 
-@pytest.mark.parametrize("env", ROUTES, ids=lambda e: "+".join(sorted(e)) or "default")
-def test_every_route_gives_the_same_bytes(ctx, orc, monkeypatch, env):
+def _route_id(e):
+    return "+".join(f"{k}={v}" for k, v in sorted(e.items())) or "default"
+
+
+@pytest.fixture
+def routed(ctx):
+    """ctx with routes set by the test; every route back to its default afterwards"""
+    yield ctx
+    ctx.route("default")
+
+
+@pytest.mark.parametrize("env", ROUTES, ids=_route_id)
+def test_every_route_gives_the_same_bytes(routed, orc, env):
+    ctx = routed
     for k, v in env.items():
-        monkeypatch.setenv(k, v)
+        ctx.route(k, v)
     for name in ("lognormal_40", "edge_lengths", "long_runs", "big_well_gaps", "no_n_tags"):
         text = QUIVA[name]
         enc = orc.dexqv(text)
@@ -141,16 +157,17 @@ def test_output_buffer_too_small_is_an_error(ctx, orc):
     assert e.value.code == -2                            # DX_E_CAP
 
 
-@pytest.mark.parametrize("env", [{}, {"DEXB200_EXACT_PACK": "1"}], ids=["vectorised", "byte_serial"])
+@pytest.mark.parametrize("env", [{}, {"exact_pack": 1}], ids=["vectorised", "byte_serial"])
 @pytest.mark.parametrize("arrow", [False, True])
-def test_batched_reads_many(ctx, orc, monkeypatch, env, arrow):
+def test_batched_reads_many(routed, orc, env, arrow):
     """dx_compress_reads_dev / dx_uncompress_reads_dev (the Dazzler DB loader form, DB.c:1389-1441,
     1556-1614) on 1500 reads at ragged offsets, against Number_Read/Number_Arrow + Compress_Read and
     Uncompress_Read + Lower_/Upper_Read/Letter_Arrow of the oracle, read by read."""
     import ctypes as C
     import torch
+    ctx = routed
     for k, v in env.items():
-        monkeypatch.setenv(k, v)
+        ctx.route(k, v)
     rng = np.random.default_rng(77)
     lens = np.concatenate([np.arange(0, 40), rng.integers(1, 6000, size=1460)]).astype(np.int32)
     alpha = np.frombuffer(b"1234G0x" if arrow else b"acgtACGTnN-", dtype=np.uint8)
@@ -241,10 +258,11 @@ def test_lattice_kernels_at_every_width(ctx, orc, width):
     assert ctx.undexta(enc, kind=dx.ARROW, width=width) == orc.undexta(enc, arrow=True, width=width)
 
 
-def test_multi_cta_scan_with_look_back(ctx, orc, monkeypatch):
-    """DEXB200_CHAIN_SCAN runs the multi-CTA prefix sums with tiles of 256 values, so a few hundred
+def test_multi_cta_scan_with_look_back(routed, orc):
+    """The chain_scan route runs the multi-CTA prefix sums with tiles of 256 values, so a few hundred
     entries already span several tiles and exercise the look-back over published tile totals."""
-    monkeypatch.setenv("DEXB200_CHAIN_SCAN", "1")
+    ctx = routed
+    ctx.route("chain_scan", 1)
     rng = np.random.default_rng(77)
     fasta = synth.make_fasta(77, [int(x) for x in rng.integers(1, 300, size=1500)])
     enc = orc.dexta(fasta)
@@ -254,3 +272,51 @@ def test_multi_cta_scan_with_look_back(ctx, orc, monkeypatch):
     enc = orc.dexqv(quiva)
     assert ctx.dexqv(quiva) == enc
     assert ctx.undexqv(enc) == quiva
+
+
+# ---- the lane-per-entry decoder (dx_qv_decode6.cu) forced on inputs of every shape -----------------
+
+@pytest.mark.parametrize("name", sorted(QUIVA))
+def test_lane_decoder_on_every_case(routed, orc, name):
+    """Small files never reach the lane-per-entry kernel by themselves (the planner keeps them on the
+    warp-per-entry kernel), so force it: discovered and known entry offsets, -U, lossy codings."""
+    import torch
+    ctx = routed
+    ctx.route("decoder", 6)
+    text = QUIVA[name]
+    for lossy in (False, True):
+        enc = orc.dexqv(text, lossy=lossy)
+        want = orc.undexqv(enc)
+        got = ctx.undexqv(enc)
+        assert got == want, (lossy, first_diff(got, want))
+    assert ctx.undexqv(enc, upper=True) == orc.undexqv(enc, upper=True)
+    enc = orc.dexqv(text)
+    want = orc.undexqv(enc)
+    nent = text.count(b"\n") // 6
+    offs = orc.dexqv_offsets(enc, nent)
+    img = torch.frombuffer(bytearray(enc), dtype=torch.uint8).cuda()
+    back = torch.empty(len(want) + 64, dtype=torch.uint8, device="cuda")
+    m = ctx.undexqv_dev(img.data_ptr(), len(enc), False, back.data_ptr(), back.numel(), entry_off=offs)
+    got = back[:m].cpu().numpy().tobytes()
+    assert got == want, first_diff(got, want)
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_lane_decoder_fuzz(routed, orc, seed):
+    from tests import fuzz
+    ctx = routed
+    ctx.route("decoder", 6)
+    text, _ = fuzz.fuzz_quiva(seed)
+    for lossy in (False, True):
+        enc = orc.dexqv(text, lossy=lossy)
+        got, want = ctx.undexqv(enc), orc.undexqv(enc)
+        assert got == want, (lossy, first_diff(got, want))
+
+
+def test_lane_decoder_on_a_truncated_image_fails_cleanly(routed, orc):
+    ctx = routed
+    ctx.route("decoder", 6)
+    enc = orc.dexqv(QUIVA["lognormal_40"])
+    for cut in (len(enc) - 1, len(enc) - 40, len(enc) // 2):
+        with pytest.raises(dx.DexError):
+            ctx.undexqv(enc[:cut])
