@@ -1255,6 +1255,21 @@ static bool build_dec_tables4(const dx_qv_coding *c, QvDecTables4 *t)
           erun[k] += q * (escape ? 400.0 : (double) i);
         }
     }
+  for (int k = 0; k < 6; k++)
+    { const dx_scheme &s = c->tab[k];
+      const bool isrun = (k == 1 || k == 5);
+      int n = 0;
+      for (int i = 0; i < 256; i++)
+        { const int len = s.lens[i];
+          if (len <= 12 || len > 16) continue;
+          const bool folded = (i < 255 && s.lens[255] == len && s.bits[255] == s.bits[i] &&
+                               (isrun || s.type == 2));
+          if (folded) continue;
+          t->longs[k][n++] = (((s.bits[i] << (16 - len)) & 0xffffu) << 16) | ((uint32_t) len << 8) | (uint32_t) i;
+        }
+      std::sort(t->longs[k],t->longs[k] + n);
+      t->nlong[k] = n;
+    }
   t->abits[0] = (float) (c->delchar >= 0 ? (ab[0] + ab[1]) / (erun[1] + 1.0) : ab[0]);
   t->abits[2] = (float) ab[2];
   t->abits[3] = (float) ab[3];
@@ -1306,7 +1321,9 @@ static void ticket_order(const int32_t *rlen, size_t N, int32_t *order)
 // the 512 length buckets of the counting sort.
 static int64_t ticket_plan(const dx_ctx *ctx, const int32_t *rlen, size_t N, int32_t *order)
 { enum { kBuckets = 512 };
-  const double kLaneNs = 55e-9, kLaneGBs = 1500e9, kCoopGBs = 460e9, kLaunch = 8e-6;
+  // measured on B200 (profiles/r02_decoders.txt): a lane needs 280 ns per position (the 60 000-position
+  // entries of the 2 GB bench file keep k_qv_decode6 busy for 16.9 ms), the warp kernel decodes 460 GB/s
+  const double kLaneNs = 280e-9, kLaneGBs = 1500e9, kCoopGBs = 460e9, kLaunch = 8e-6;
   ticket_order(rlen,N,order);
   const int64_t mode = ctx->route[DXR_DECODER];
   if (mode == 5 || N == 0) return (int64_t) N;

@@ -63,6 +63,11 @@ struct QvDecTables4
   uint16_t single[6][4096];
   float    abits[6];
   QvDecTables2 t2;
+  // codes longer than 12 bits, sorted by their left-aligned 16-bit value: code16 << 16 | len << 8 | sym
+  // (prefix-free codes own disjoint intervals of 16-bit windows, so the code of a window is the last
+  // entry at or below it).  Symbols folded onto the escape appear once, as 255.
+  uint32_t longs[6][256];
+  int32_t  nlong[6];
 };
 
 // ---- context --------------------------------------------------------------------------------

@@ -6,27 +6,34 @@
 // A Huffman stream stores no code boundaries, so a stream can only be split among threads by
 // speculation (dx_qv_decode5.cu: every symbol is decoded 2-3 times and a third of the lanes idle).
 // But a 2 GB file holds ~40 000 independent entries: here every lane of a warp decodes ONE WHOLE
-// ENTRY sequentially -- exactly the reference's loop, one table lookup per one or two symbols, no
-// speculation, no warp collective anywhere in the kernel.  The 32 entries of a warp are neighbours
-// in the longest-first ticket order, so their lengths agree within a few percent and the lanes
-// stay busy together.  Entries too long for this (a lane needs ~100 cycles per position) go to the
-// warp-per-entry kernel; the host picks the cut (dxk_qv_decode6x).
+// ENTRY sequentially -- the reference's loop, one table lookup per one or two symbols, no
+// speculation.  The 32 entries of a warp are neighbours in the longest-first ticket order, so their
+// lengths agree within a few percent and the lanes stay busy together.  A lane is a single chain
+// of dependent lookups (~50-100 cycles per lookup), so the kernel lasts as long as its longest
+// entry: entries too long for that go to the warp-per-entry kernel; the host picks the cut
+// (dxk_qv_decode6x, ticket_plan in dx_api.cpp).
 //
-// What makes a sequential lane fast enough:
-//   * decode tables for all four streams resident in shared memory (64 KB per CTA, 12-bit index,
-//     two symbols per lookup on the plain streams);
-//   * the lane's bit window is a left-aligned 64-bit register pair; it is refilled one 32-bit word
-//     at a time from a 16-word per-lane ring in shared memory ([word][lane]: conflict free), and
-//     the ring is topped up with 16-byte global loads issued two quads ahead (software pipelined:
-//     the lane never waits for HBM).  The byte misalignment of a stream is removed when a quad
-//     enters the ring, so the hot loop sees aligned stream words;
-//   * output goes through a 64-byte per-lane ring in shared memory (stride 68 bytes: lanes at the
-//     same offset hit different banks) and leaves in aligned 16-byte stores; the five lines of an
-//     entry are contiguous in the text, so one byte stream per lane runs through all of them and only
-//     the first and last block of an entry are written bytewise.  Run-length streams keep the ring
-//     pre-filled with the run character: a run is an addition to the write pointer;
-//   * rare per-lane events (ring top-up, block flush) are polled every 8 lookups, not every lookup:
-//     what is rare for a lane happens in almost every iteration of a 32-lane warp.
+// What a sequential lane needs to be fast (every item below was measured with ncu first):
+//   * the five lines of an entry are five PHASES of one loop, and the warp re-joins with
+//     __syncwarp at every phase boundary -- left to the compiler's reconvergence the lanes drifted
+//     apart after the second line and ran alone (1.0 threads per instruction);
+//   * 12-bit decode tables for all four streams in shared memory; plain streams decode two symbols
+//     per lookup, run-length streams a whole (run, symbol) item per lookup;
+//   * no branch inside a batch of 8 lookups: a table entry that needs anything special (escape,
+//     code longer than 12 bits, long run) takes no bits and gives no symbols, so a lane that meets
+//     one idles until the end of the batch, where the slow step handles it -- from shared memory
+//     (one-code tables, sorted lists of the long codes), never from global memory;
+//   * the bit window is 96 bits in registers (hi always full, so a refill never sits on the
+//     lookup -> shift -> lookup chain), refilled without a branch every second lookup from a 16-word
+//     per-lane ring in shared memory ([word][lane]: conflict free); the ring is topped up with
+//     16-byte global loads issued three quads ahead; the byte misalignment of a stream is removed
+//     when a quad enters the ring;
+//   * output goes through a 64-byte per-lane ring in shared memory (pitch 84: lanes at the same
+//     offset hit different banks) and leaves in aligned 16-byte stores; a batch writes past the
+//     ring's end into 20 bytes of slack that are wrapped around once per batch.  The five lines of an
+//     entry are contiguous in the text, so only the first and last block of an entry are written
+//     bytewise.  Run-length streams keep the ring pre-filled with the run character: a run is an
+//     addition to the write pointer.
 
 #include <stdio.h>
 #include <stdlib.h>
@@ -35,11 +42,13 @@
 
 namespace {
 
-constexpr int kWarps6   = 8;
-constexpr int kThreads6 = kWarps6 * 32;
+constexpr int kMaxWarps6 = 16;                  // warps per CTA: chosen per launch, <= this
 constexpr int kRingW    = 16;                   // stream words per lane in the input ring
 constexpr int kOutRing  = 64;                   // bytes per lane in the output ring
-constexpr int kOutPitch = 68;                   // ... and its pitch (17 words: odd, so conflict free)
+constexpr int kOutSlack = 20;                   // a batch of the plain loop may run this far past the ring's end
+constexpr int kOutPitch = 84;                   // pitch of a lane's ring (21 words: odd, so conflict free)
+constexpr int kBatch    = 8;                    // lookups between two polls of the rings
+constexpr uint32_t kFastRun = 31;               // longest run the one-lookup (run, symbol) table holds
 
 struct Dec6Args
 { const uint8_t *in;
@@ -60,100 +69,146 @@ struct Dec6Args
   const int32_t *order;        // ticket -> entry (long entries first), NULL: identity
 };
 
-struct Shared6
-{ uint32_t tab[4][4096];                        // del, ins, mrg, sub: one multi table or run|sym u16 tables
-  uint32_t ring[kWarps6][kRingW][32];
-  uint32_t outr[kWarps6][32*kOutPitch/4];
+// shared memory: the tables, then per warp an input ring and an output ring
+struct Tables6
+{ uint32_t tab[4][4096];       // del, ins, mrg, sub: two-symbol table or (run, symbol) table
+  uint16_t one[2][2][4096];    // run-length streams (0 del, 1 sub): run codes, symbol codes (slow step)
+  uint32_t longs[6][256];      // codes longer than 12 bits (QvDecTables4::longs)
+  int32_t  nlong[8];
+  int32_t  type[8];
 };
+constexpr size_t kWarpBytes6 = (size_t) kRingW*32*4 + 32*kOutPitch + 4*32*16;   // + the del-line ring of the tag phase
 
 extern __shared__ __align__(16) uint8_t dx_dec6_smem[];
 
+// ---- asynchronous global -> shared copies (LDGSTS): the data never passes through registers, so
+//      nothing waits for it until cp_wait says so (a register pipeline of quads had the compiler
+//      rotate registers with MOVs that stalled on the youngest load)
+__device__ __forceinline__ void cp_async4(void *smem, const void *g, bool ok)
+{ const uint32_t d = (uint32_t) __cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" :: "r"(d), "l"(g), "r"(ok ? 4 : 0) : "memory");   // 0: zero fill, nothing read
+}
+__device__ __forceinline__ void cp_async16_cg(void *smem, const void *g)
+{ const uint32_t d = (uint32_t) __cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(d), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+
 // ---- the lane's input: a bit window over a byte-aligned stream of little-endian 32-bit words ----
+// The ring holds RAW aligned words of the image ([word][lane], 16 words); stream word j is
+// funnel(raw[sw+j], raw[sw+j+1]) by the stream's byte skew, formed when the window is refilled.
+// Quads are copied in by cp.async, one commit group each; the two youngest groups may be in flight.
 struct BitIn
-{ uint32_t hi, lo;             // the next `valid` stream bits, left aligned in hi:lo
-  int32_t  valid;
-  uint32_t cons;               // bits consumed since the stream's start
-  uint32_t rd, st;             // ring: next word to read / words stored (indices of aligned words)
+{ uint32_t hi;                 // the next 32 stream bits, always all valid
+  uint32_t mid, lo;            // the `s` bits after them, left aligned in mid:lo (zero beyond)
+  int32_t  s;                  // > 32 after every refill; a step may take up to 24
+  uint32_t praw;               // raw word rd-1
+  uint32_t rd, st, rd0;        // ring: next raw word to read / raw words issued / rd of the first word
   uint32_t sb8;                // byte skew of the stream against the aligned words, in bits
-  const uint4 *src, *end16;    // next quad to load / first quad that may not be read
-  uint4    pa, pb;             // quads st/4 and st/4 + 1 (pb may still be in flight)
+  const uint32_t *src, *endw;  // next raw quad to copy / first word that may not be read
+  const uint32_t *safe;        // an address that may always be named (copies of size 0 past the image)
   uint32_t *ring;              // &ring[warp][0][lane]
-  uint64_t base;               // address of aligned word 0
+  uint64_t base;               // address of raw word 0
 
-  __device__ __forceinline__ uint4 load(const uint4 *p) const
-  { return (p < end16) ? __ldg(p) : make_uint4(0,0,0,0); }
-
-  // aligned quad pa (its successor's first word is pb.x) -> four stream-aligned words in the ring
-  __device__ __forceinline__ void store_quad()
+  __device__ __forceinline__ void issue_quad()
   { uint32_t *r = ring + (st & (kRingW-1))*32;
-    r[0]  = __funnelshift_r(pa.x,pa.y,sb8);
-    r[32] = __funnelshift_r(pa.y,pa.z,sb8);
-    r[64] = __funnelshift_r(pa.z,pa.w,sb8);
-    r[96] = __funnelshift_r(pa.w,pb.x,sb8);
-    st += 4;
-    pa = pb;
-    pb = load(src); src++;
+    const bool ok = (src < endw);                            // quads are 16-byte aligned, endw too
+    const uint32_t *q = ok ? src : safe;
+    cp_async4(r,q,ok); cp_async4(r + 32,q + 1,ok); cp_async4(r + 64,q + 2,ok); cp_async4(r + 96,q + 3,ok);
+    cp_commit();
+    st += 4; src += 4;
+  }
+  // at least 5 complete words ahead of rd (the two youngest quads do not count)
+  __device__ __forceinline__ void top_up()
+  { while (st - rd <= 12u) issue_quad();
+    cp_wait<2>();
+  }
+  // ... the same for the fast loops, whose batches take at most 3 words: one quad is enough
+  __device__ __forceinline__ void top_up_once()
+  { if (st - rd <= 12u) issue_quad();
+    cp_wait<2>();
   }
 
-  // at least 9 words buffered ahead of rd (a poll interval consumes at most 7)
-  __device__ __forceinline__ void top_up()
-  { while (st - rd <= 8u) store_quad(); }
+  // bits consumed since the stream's first bit
+  __device__ __forceinline__ uint32_t cons() const { return (rd - rd0 - 1u)*32u - 32u - (uint32_t) s; }
+
+  __device__ __forceinline__ uint32_t next_word()
+  { const uint32_t cur = ring[(rd & (kRingW-1))*32];
+    const uint32_t x = __funnelshift_r(praw,cur,sb8);
+    praw = cur;
+    return x;
+  }
 
   template <bool SWAP>         // SWAP: the stream is a byte string, first byte first (packed tags)
   __device__ __forceinline__ void refill()
-  { if (valid <= 32)
-      { uint32_t x = ring[(rd & (kRingW-1))*32];
+  { if (s <= 32)
+      { uint32_t x = next_word();
         if (SWAP) x = __byte_perm(x,0,0x0123);
         rd++;
-        hi |= __funnelshift_rc(x,0u,(uint32_t) valid);
-        lo  = __funnelshift_lc(0u,x,32u - (uint32_t) valid);
-        valid += 32;
+        mid |= __funnelshift_rc(x,0u,(uint32_t) s);
+        lo   = __funnelshift_lc(0u,x,32u - (uint32_t) s);
+        s += 32;
       }
+  }
+  // the same without a branch (fast loops): for s > 32 both shifts clamp to "nothing"
+  __device__ __forceinline__ void refill_flat()
+  { const uint32_t cur = ring[(rd & (kRingW-1))*32];
+    const uint32_t x = __funnelshift_r(praw,cur,sb8);
+    mid |= __funnelshift_rc(x,0u,(uint32_t) s);
+    lo  |= __funnelshift_lc(0u,x,(uint32_t) (32 - s));
+    const bool p = (s <= 32);
+    praw = p ? cur : praw;
+    rd += p ? 1u : 0u;
+    s  += p ? 32 : 0;
   }
 
   template <bool SWAP>
   __device__ __forceinline__ void init(const uint8_t *p, const uint8_t *image_end, uint32_t *ring_lane)
   { const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    cp_wait<0>();                                            // nothing of the previous stream in flight
     ring = ring_lane;
-    src = reinterpret_cast<const uint4 *>(a & ~(uintptr_t) 15);
-    end16 = reinterpret_cast<const uint4 *>((reinterpret_cast<uintptr_t>(image_end) + 15) & ~(uintptr_t) 15);
+    src = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t) 15);
+    endw = reinterpret_cast<const uint32_t *>((reinterpret_cast<uintptr_t>(image_end) + 15) & ~(uintptr_t) 15);
     base = (uint64_t) (a & ~(uintptr_t) 15);
+    safe = reinterpret_cast<const uint32_t *>((reinterpret_cast<uintptr_t>(image_end) - 16) & ~(uintptr_t) 15);
     sb8 = (uint32_t) (a & 3) * 8u;
-    rd = (uint32_t) (a & 15) >> 2; st = 0;
-    const uint4 q0 = load(src), q1 = load(src+1), q2 = load(src+2), q3 = load(src+3);
-    pa = q0; pb = q1; src += 2;
-    // (store_quad loads the quad after pb itself: unroll the first three by hand so that the four
-    //  loads above are in flight together)
-    { uint32_t *r = ring;
-      r[0]   = __funnelshift_r(q0.x,q0.y,sb8); r[32]  = __funnelshift_r(q0.y,q0.z,sb8);
-      r[64]  = __funnelshift_r(q0.z,q0.w,sb8); r[96]  = __funnelshift_r(q0.w,q1.x,sb8);
-      r[128] = __funnelshift_r(q1.x,q1.y,sb8); r[160] = __funnelshift_r(q1.y,q1.z,sb8);
-      r[192] = __funnelshift_r(q1.z,q1.w,sb8); r[224] = __funnelshift_r(q1.w,q2.x,sb8);
-      r[256] = __funnelshift_r(q2.x,q2.y,sb8); r[288] = __funnelshift_r(q2.y,q2.z,sb8);
-      r[320] = __funnelshift_r(q2.z,q2.w,sb8); r[352] = __funnelshift_r(q2.w,q3.x,sb8);
-    }
-    st = 12; pa = q3; src = reinterpret_cast<const uint4 *>(a & ~(uintptr_t) 15) + 4;
-    pb = load(src); src++;
-    hi = 0; lo = 0; valid = 0; cons = 0;
-    refill<SWAP>(); refill<SWAP>();
+    rd0 = (uint32_t) (a & 15) >> 2; rd = rd0; st = 0;
+    issue_quad(); issue_quad(); issue_quad(); issue_quad();
+    cp_wait<2>();                                            // raw words 0..7 are there
+    praw = ring[(rd & (kRingW-1))*32]; rd++;
+    uint32_t w0 = next_word(); rd++;
+    uint32_t w1 = next_word(); rd++;
+    uint32_t w2 = next_word(); rd++;
+    if (SWAP) { w0 = __byte_perm(w0,0,0x0123); w1 = __byte_perm(w1,0,0x0123); w2 = __byte_perm(w2,0,0x0123); }
+    hi = w0; mid = w1; lo = w2; s = 64;
   }
 
-  __device__ __forceinline__ void take(uint32_t len)           // len < 32, len <= valid
-  { hi = __funnelshift_l(lo,hi,len);
+  __device__ __forceinline__ void take(uint32_t len)           // len < 32, len <= s
+  { hi  = __funnelshift_l(mid,hi,len);
+    mid = __funnelshift_l(lo,mid,len);
     lo <<= len;
-    valid -= (int32_t) len;
-    cons += len;
+    s -= (int32_t) len;
   }
 
   // first byte of the image that has not been handed to the window yet
   __device__ __forceinline__ uint64_t reached() const { return base + (uint64_t) rd*4u; }
 };
 
+// the first block of an entry shares its 16 bytes with the end of the entry before it: bytes
+// [head, 16) only.  Out of line (by value): once per entry, but inlined at every flush otherwise.
+__device__ __noinline__ void store_head6(uint8_t *g, uint4 v, uint32_t head)
+{ const uint32_t w[4] = { v.x, v.y, v.z, v.w };
+#pragma unroll
+  for (int k = 0; k < 16; k++)
+    if ((uint32_t) k >= head) g[k] = (uint8_t) (w[k >> 2] >> (8*(k & 3)));
+}
+
 // ---- the lane's output: bytes appended to one contiguous span of the text -------------------------
 struct OutSt
 { uint8_t *gbase;              // 16-byte aligned; byte counter t <-> gbase + t
   uint32_t wr, fl, head;       // appended / flushed (multiple of 16) / bytes of block 0 that are not ours
-  uint8_t *ring;               // this lane's 64 bytes of shared memory
+  uint8_t *ring;               // this lane's 64 (+ slack) bytes of shared memory
 
   __device__ __forceinline__ void init(uint8_t *dst, uint8_t *ring_lane)
   { const uintptr_t a = reinterpret_cast<uintptr_t>(dst);
@@ -162,22 +217,22 @@ struct OutSt
   }
   __device__ __forceinline__ void put(uint32_t c) { ring[wr & (kOutRing-1)] = (uint8_t) c; wr++; }
 
-  // FILL != 0: a flushed block is filled with the byte again (run-length streams)
+  // one complete block, if there is one; FILL: the block is filled with the byte again (run streams)
   template <bool FILL>
-  __device__ __forceinline__ void flush(uint32_t fill4)
-  { while (wr - fl >= 16u)
+  __device__ __forceinline__ void flush_one(uint32_t fill4)
+  { if (wr - fl >= 16u)
       { uint32_t *b = reinterpret_cast<uint32_t *>(ring + (fl & (kOutRing-1)));
         const uint4 v = make_uint4(b[0],b[1],b[2],b[3]);
-        if (fl == 0 && head != 0)
-          { const uint8_t *bb = reinterpret_cast<const uint8_t *>(b);
-            for (uint32_t k = head; k < 16u; k++) gbase[k] = bb[k];
-          }
-        else
-          dx_stg16(gbase + fl,v);
+        if (fl == 0 && head != 0) store_head6(gbase,v,head);
+        else                      dx_stg16(gbase + fl,v);
         if (FILL) { b[0] = fill4; b[1] = fill4; b[2] = fill4; b[3] = fill4; }
         fl += 16;
       }
   }
+  template <bool FILL>
+  __device__ __forceinline__ void flush(uint32_t fill4)
+  { while (wr - fl >= 16u) flush_one<FILL>(fill4); }
+
   // every byte appended so far is in global memory afterwards; the state does not change
   __device__ __forceinline__ void sync_partial()
   { flush<false>(0);
@@ -200,30 +255,36 @@ struct OutSt
   }
 };
 
-// codes longer than 12 bits (same tables as the warp-per-entry kernel)
-__device__ __forceinline__ uint32_t lookup_long6(const QvDecTables2 *t, int k, uint32_t w16)
-{ uint32_t e = __ldg(&t->prim[k][w16 >> 5]);
-  if (e & 0x8000u)
-    e = __ldg(&t->sub[k][(e & 0x7fffu)*32u + (w16 & 31u)]);
-  return e;
+// ---- slow steps: everything comes from shared memory -----------------------------------------------
+// a code longer than 12 bits: sym | len << 8, or 0x100 | E6_BAD1 when no code owns the window (garbage)
+#define E6_BAD   0x2000u                /* multi entries: bit 13 */
+#define E6_BAD1  0x8000u                /* single entries: bit 15 */
+__device__ __noinline__ uint32_t long_code6(const uint32_t *lg, int n, uint32_t w)
+{ const uint32_t w16 = w >> 16;
+  int lo = 0, hi = n;                                   // last entry whose code16 <= w16
+  while (lo < hi)
+    { const int m = (lo + hi) >> 1;
+      if ((lg[m] >> 16) <= w16) lo = m + 1; else hi = m;
+    }
+  if (lo == 0) return 0x100u | E6_BAD1;
+  const uint32_t e = lg[lo-1];
+  const uint32_t len = (e >> 8) & 0xffu;
+  if (((e >> 16) ^ w16) >> (16u - len)) return 0x100u | E6_BAD1;
+  return e & 0xffffu;
 }
-__device__ __noinline__ uint32_t long_entry6(const QvDecTables2 *t, int k, uint32_t w, uint32_t *bad)
-{ const uint32_t f = lookup_long6(t,k,w >> 16);
-  uint32_t len = (f >> 8) & 31u;
-  const uint32_t c = f & 0xffu;
-  if (len == 0) { len = 1; *bad = 1; }
-  if (t->type[k] == 2 && c == 255u)
-    return (len + 8u) | (1u << 5) | 0x80u | (len << 8) | (255u << 16);
-  return len | (1u << 5) | (len << 8) | (c << 16);
-}
-__device__ __noinline__ uint32_t long_single6(const QvDecTables2 *t, int k, uint32_t w, uint32_t *bad)
-{ uint32_t f = lookup_long6(t,k,w >> 16) & 0x1fffu;
-  if ((f >> 8) == 0u) { f |= 0x100u; *bad = 1; }
-  return f;
+// ... as an entry of the plain-stream table
+__device__ __forceinline__ uint32_t long_entry6(const uint32_t *lg, int n, int type, uint32_t w)
+{ const uint32_t f = long_code6(lg,n,w);
+  const uint32_t len = (f >> 8) & 31u, c = f & 0xffu;
+  const uint32_t bad = (f & E6_BAD1) ? E6_BAD : 0u;
+  if (type == 2 && c == 255u)
+    return (len + 8u) | (1u << 5) | 0x80u | (len << 8) | (255u << 16) | bad;
+  return len | (1u << 5) | (len << 8) | (c << 16) | bad;
 }
 
 // multi entry (QvDecTables4): bits 0-4 total length, 5-6 symbols, 7 escape, 8-12 length of the first
-// code, 16-23 / 24-31 the symbols
+// code, 16-23 / 24-31 the symbols.  In shared memory an escape entry keeps bits 7-12 only: to the
+// fast loop it is "no bits, no symbols" like the empty entry of a long code.
 #define E6_LEN(e)   ((e) & 31u)
 #define E6_N(e)     (((e) >> 5) & 3u)
 #define E6_LEN0(e)  (((e) >> 8) & 31u)
@@ -234,140 +295,211 @@ struct Lane
   uint64_t lim;                // address the entry may not read past
 };
 
-// one plain stream of L symbols (QV.c:510-599); returns the bytes the stream occupies in the file
-__device__ __forceinline__ uint32_t plain_stream(Lane &ln, const uint32_t *mt, const QvDecTables2 *t2, int symtab,
-                                                 uint32_t L, bool wr, uint32_t *kept_all)
+// one symbol of a plain stream the slow way; returns the position of the last item read
+__device__ __forceinline__ uint32_t plain_step(Lane &ln, const uint32_t *mt, const uint32_t *lg, int nlg, int type)
+{ BitIn &in = ln.in;
+  const uint32_t w = in.hi;
+  uint32_t e = mt[w >> 20];
+  if (e == 0u) { e = long_entry6(lg,nlg,type,w); ln.bad |= e & E6_BAD; }
+  const uint32_t l0 = E6_LEN0(e);
+  uint32_t c0 = (e >> 16) & 0xffu, adv = l0, last = in.cons();
+  if (e & 0x80u) { c0 = (w << l0) >> 24; last += l0; adv += 8u; }
+  ln.out.put(c0);
+  in.take(adv);
+  in.refill<false>();
+  return last;
+}
+
+// one plain stream of L symbols (QV.c:510-599); returns the bytes the stream occupies in the file.
+// `act`: the lanes of the warp that enter together.  Every loop head is a __ballot_sync over the
+// lanes still in the loop: it is the loop condition AND the point where the lanes re-join (left to
+// the compiler, lanes that finish a poll early start the next batch alone).
+__device__ __forceinline__ uint32_t plain_stream(Lane &ln, uint32_t act, const uint32_t *mt, const uint32_t *lg,
+                                                 int nlg, int type, uint32_t L)
 { BitIn &in = ln.in; OutSt &out = ln.out;
   uint32_t cnt = 0, last = 0;
-  // two symbols per lookup while at least three are still to come
-  while (cnt + 2u < L)
-    {
-#pragma unroll 1
-      for (int it = 0; it < 8 && cnt + 2u < L; it++)
-        { const uint32_t w = in.hi;
-          uint32_t e = mt[w >> 20];
-          if (e == 0u) e = long_entry6(t2,symtab,w,&ln.bad);
-          uint32_t c0 = (e >> 16) & 0xffu;
-          if (e & 0x80u) c0 = (w << E6_LEN0(e)) >> 24;            // the literal after the escape
-          if (wr)
-            { out.ring[out.wr & (kOutRing-1)] = (uint8_t) c0;
-              out.ring[(out.wr + 1u) & (kOutRing-1)] = (uint8_t) (e >> 24);
-              out.wr += E6_N(e);
-            }
-          cnt += E6_N(e);
+  if (L > 0) in.top_up();
+  // ---- fast: batches of kBatch lookups, up to two symbols each, no branch inside a batch ----------
+  while (true)
+    { const bool go = (cnt + 2u*kBatch + 2u < L);
+      act = __ballot_sync(act,go);
+      if (!go) break;
+      const uint32_t wo = out.wr & (kOutRing-1);
+      uint8_t *p = out.ring + wo;
+#pragma unroll
+      for (int it = 0; it < kBatch; it++)
+        { const uint32_t e = mt[in.hi >> 20];
+          p[0] = (uint8_t) (e >> 16);
+          p[1] = (uint8_t) (e >> 24);
+          p += E6_N(e);
           in.take(E6_LEN(e));
-          in.refill<false>();
+          if (it & 1) in.refill_flat();                     // two lookups take at most 24 bits
         }
-      in.top_up();
-      if (wr) out.flush<false>(0);
-      if (in.reached() > ln.lim) { ln.bad = 1; return 0; }
+      const uint32_t made = (uint32_t) (p - (out.ring + wo));
+      out.wr += made; cnt += made;
+      if (wo + made > (uint32_t) kOutRing)                  // ran into the slack: wrap it around
+        { const uint32_t *src = reinterpret_cast<const uint32_t *>(out.ring + kOutRing);
+          uint32_t *dst = reinterpret_cast<uint32_t *>(out.ring);
+#pragma unroll
+          for (int k = 0; k < kOutSlack/4; k++) dst[k] = src[k];
+        }
+      out.flush_one<false>(0);                              // 15 pending + 16 made: at most one block
+      in.top_up_once();
+      // an entry the fast loop cannot take under the window: symbols the slow way until it is gone
+      while (E6_N(mt[in.hi >> 20]) == 0u && cnt + 2u < L)
+        { plain_step(ln,mt,lg,nlg,type);
+          cnt++;
+          out.flush_one<false>(0);
+          in.top_up();
+        }
+      if (in.reached() > ln.lim) { ln.bad = 1; cnt = L; last = 0; }
     }
-  // the last one or two symbols one at a time: `last` is the position of the last item (the
-  // literal of an escape), which fixes the stream's length in the file (QV.c:537-551)
+  // ---- the last symbols one at a time: the position of the last item (the literal of an escape)
+  //      fixes the stream's length in the file (QV.c:537-551)
   while (cnt < L)
-    { const uint32_t w = in.hi;
-      uint32_t e = mt[w >> 20];
-      if (e == 0u) e = long_entry6(t2,symtab,w,&ln.bad);
-      uint32_t c0 = (e >> 16) & 0xffu;
-      const uint32_t l0 = E6_LEN0(e);
-      uint32_t adv = l0;
-      last = in.cons;
-      if (e & 0x80u) { c0 = (w << l0) >> 24; last += l0; adv += 8u; }
-      if (wr) out.put(c0);
+    { last = plain_step(ln,mt,lg,nlg,type);
       cnt++;
-      in.take(adv);
-      in.refill<false>();
+      out.flush_one<false>(0);
+      in.top_up_once();
     }
-  if (kept_all != NULL) *kept_all = L;
-  return (L == 0) ? 0u : ((last + 47u) >> 5) * 4u;
+  return (L == 0 || ln.bad) ? 0u : ((last + 47u) >> 5) * 4u;
 }
 
 // one run-length stream (QV.c:604-691): (run of rc, one other symbol)*
-__device__ __forceinline__ uint32_t run_stream(Lane &ln, const uint16_t *rt, const uint16_t *st,
-                                               const QvDecTables2 *t2, int symtab, int runtab, bool esc,
-                                               uint32_t rc, uint32_t L, bool wr, uint32_t *kept_out)
+// pt: the stream's (run, symbol) table -- one lookup decodes a whole item when the run is at most
+// kFastRun, both codes together have at most 12 bits and nothing is escaped: bits 0-4 the item's
+// length, 8-15 the run, 16-23 the symbol; 0 = everything else (slow step: rt / st, the one-code tables).
+__device__ __forceinline__ uint32_t run_stream(Lane &ln, uint32_t act, const uint32_t *pt, const uint16_t *rt, const uint16_t *st,
+                                               const uint32_t *lgr, int nlgr, const uint32_t *lgs, int nlgs,
+                                               bool esc, uint32_t rc, uint32_t L, uint32_t *kept_out)
 { BitIn &in = ln.in; OutSt &out = ln.out;
   const uint32_t rc4 = rc * 0x01010101u;
   uint32_t cnt = 0, last = 0, kept = 0;
-  if (wr) out.prefill(rc);
-  while (cnt < L)
-    {
-#pragma unroll 1
-      for (int it = 0; it < 4 && cnt < L; it++)
-        { uint32_t w = in.hi;
-          uint32_t e = rt[w >> 20];
-          if (e == 0u) e = long_single6(t2,runtab,w,&ln.bad);
-          uint32_t r = e & 0xffu;
-          last = in.cons;
-          in.take(e >> 8);
-          in.refill<false>();
-          if (r == 255u)
-            { r = in.hi >> 16; last = in.cons;
-              in.take(16);
-              in.refill<false>();
+  *kept_out = 0;
+  if (L > 0) { out.prefill(rc); in.top_up(); }
+  while (true)
+    { const bool go = (cnt < L);
+      act = __ballot_sync(act,go);
+      if (!go) break;
+      // ---- fast: whole items by one lookup, while no item can reach the end of the line -----------
+      if (cnt + 4u*(kFastRun + 1u) < L)
+        {
+#pragma unroll
+          for (int it = 0; it < 4; it++)
+            { const uint32_t e = pt[in.hi >> 20];
+              const uint32_t r = (e >> 8) & 0xffu;
+              const uint32_t adv = (e != 0u) ? r + 1u : 0u;
+              if (e != 0u) out.ring[(out.wr + r) & (kOutRing-1)] = (uint8_t) (e >> 16);
+              out.wr += adv; cnt += adv; kept += (e != 0u) ? 1u : 0u;
+              in.take(E6_LEN(e));
+              if (it & 1) in.refill_flat();
+              out.flush_one<true>(rc4);                      // 15 pending + 32: at most two blocks
+              out.flush_one<true>(rc4);
             }
-          if (r > L - cnt) { r = L - cnt; ln.bad = 1; }
-          cnt += r;
-          if (wr) out.skip(r,rc4);
-          if (cnt >= L) break;
-          w = in.hi;
-          e = st[w >> 20];
-          if (e == 0u) e = long_single6(t2,symtab,w,&ln.bad);
-          uint32_t c = e & 0xffu;
-          last = in.cons;
-          in.take(e >> 8);
-          in.refill<false>();
-          if (esc && c == 255u)
-            { c = in.hi >> 24; last = in.cons;
-              in.take(8);
-              in.refill<false>();
-            }
-          if (wr) out.put(c);
-          cnt++;
-          kept += (c != rc);
+          in.top_up_once();
+          if (pt[in.hi >> 20] != 0u) continue;
         }
-      in.top_up();
-      if (in.reached() > ln.lim) { ln.bad = 1; break; }
+      // ---- one item the slow way ------------------------------------------------------------------------
+      { uint32_t w = in.hi;
+        uint32_t e = rt[w >> 20];
+        if (e == 0u) { e = long_code6(lgr,nlgr,w); ln.bad |= e & E6_BAD1; e &= 0x1fffu; }
+        uint32_t r = e & 0xffu;
+        last = in.cons();
+        in.take(e >> 8);
+        in.refill<false>();
+        if (r == 255u)
+          { r = in.hi >> 16; last = in.cons();
+            in.take(16);
+            in.refill<false>();
+          }
+        if (r > L - cnt) { r = L - cnt; ln.bad = 1; }
+        cnt += r;
+        out.skip(r,rc4);
+        if (cnt < L)
+          { w = in.hi;
+            e = st[w >> 20];
+            if (e == 0u) { e = long_code6(lgs,nlgs,w); ln.bad |= e & E6_BAD1; e &= 0x1fffu; }
+            uint32_t c = e & 0xffu;
+            last = in.cons();
+            in.take(e >> 8);
+            in.refill<false>();
+            if (esc && c == 255u)
+              { c = in.hi >> 24; last = in.cons();
+                in.take(8);
+                in.refill<false>();
+              }
+            out.put(c);
+            cnt++;
+            kept += (c != rc);
+          }
+        in.top_up();
+        out.flush<true>(rc4);
+        if (in.reached() > ln.lim) { ln.bad = 1; cnt = L; }
+      }
     }
-  if (wr) out.flush<true>(rc4);
+  out.flush<true>(rc4);
   *kept_out = kept;
-  return (L == 0 || ln.bad) ? ((L == 0) ? 0u : ((last + 47u) >> 5) * 4u) : ((last + 47u) >> 5) * 4u;
+  return (L == 0) ? 0u : ((last + 47u) >> 5) * 4u;
 }
 
 // the tag line (Unpack_Tag, QV.c:837-847): 'n' where the deletion QV is the run character, the next
-// packed tag elsewhere.  The del line is read back from global memory (the lane's own stores) in
-// aligned 16-byte blocks; the packed tags are a bit stream of their own.
-__device__ __forceinline__ void tag_line(Lane &ln, const uint8_t *del, uint32_t L, int32_t delchar, uint32_t upper)
+// packed tag elsewhere.  The del line is read back from global memory (the lane's own stores, through
+// L2) in aligned 16-byte blocks, copied by cp.async three blocks ahead into a 4-block ring; the packed
+// tags are a bit stream of their own: the (at most 16) tags of a block are taken from the window in two
+// pieces.
+__device__ __forceinline__ void tag_line(Lane &ln, uint32_t act, uint4 *dring, const uint8_t *del, uint32_t L,
+                                         int32_t delchar, uint32_t upper)
 { BitIn &in = ln.in; OutSt &out = ln.out;
   const uint32_t caseoff = upper ? 32u : 0u;
   const uint32_t nch = 'n' - caseoff, n4 = nch * 0x01010101u;
-  out.prefill(nch);
+  const uint32_t acgt = 0x74676361u - caseoff*0x01010101u;
   const uintptr_t a = reinterpret_cast<uintptr_t>(del);
   const uint4 *blk = reinterpret_cast<const uint4 *>(a & ~(uintptr_t) 15);
   int32_t p = -(int32_t) (a & 15);                    // line position of the block's first byte
-  uint32_t polled = 0;
-  while (p < (int32_t) L)
-    { const int lo = max(0,-p), hi = min(16,(int32_t) L - p);
+  const int32_t nblk = (L > 0) ? (int32_t) (((a & 15) + L + 15) >> 4) : 0;
+  if (L > 0)
+    { out.prefill(nch);
+      in.top_up();
+      // (the packed-tag stream's quads are commit groups too: wait for ALL groups before a block
+      //  is read -- the tag stream advances one word per block at most, so nothing is lost)
+      if (delchar >= 0)
+        for (int j = 0; j < 3; j++)
+          { if (j < nblk) cp_async16_cg(dring + 32*j,blk + j);
+            cp_commit();
+          }
+    }
+  int32_t bi = 0;
+  while (true)
+    { const bool go = (bi < nblk);
+      act = __ballot_sync(act,go);
+      if (!go) break;
+      const int lo = max(0,-p), hi = min(16,(int32_t) L - p);
       uint32_t m = dx_range16(lo,hi);
       if (delchar >= 0)
-        { const uint4 v = __ldcg(blk);
+        { if (bi + 3 < nblk) cp_async16_cg(dring + 32*((bi + 3) & 3),blk + bi + 3);
+          cp_commit();
+          cp_wait<3>();                                     // block bi is there (and older tag quads)
+          const uint4 v = dring[32*(bi & 3)];
           m &= ~dx_eq_mask16(v,(uint32_t) delchar);
         }
-      int at = lo;                                    // next block byte not yet written
+      const uint32_t k = __popc(m);
+      // the block's tags: 2k <= 32 bits, in two pieces of at most 16
+      const uint32_t k1 = min(k,8u), k2 = k - k1;
+      uint32_t tg = 0;                                      // tag j of the block in bits 31-2j, 30-2j
+      if (k1) { tg = (in.hi >> (32u - 2u*k1)) << (32u - 2u*k1); in.take(2u*k1); in.refill<true>(); }
+      if (k2) { tg |= (in.hi >> (32u - 2u*k2)) << (16u - 2u*k2); in.take(2u*k2); in.refill<true>(); }
+      const uint32_t w0 = out.wr - (uint32_t) lo;            // ring counter of block byte 0
       while (m)
-        { const int k = __ffs(m) - 1; m &= m - 1;
-          out.skip((uint32_t) (k - at),n4);
-          const uint32_t code = in.hi >> 30;
-          in.take(2);
-          in.refill<true>();
-          out.put(((0x74676361u >> (8u*code)) & 0xffu) - caseoff);
-          at = k + 1;
-          if (((++polled) & 7u) == 0u) in.top_up();
+        { const int i = __ffs(m) - 1; m &= m - 1;
+          out.ring[(w0 + (uint32_t) i) & (kOutRing-1)] = (uint8_t) (acgt >> (8u*(tg >> 30)));
+          tg <<= 2;
         }
-      out.skip((uint32_t) (hi - at),n4);
-      in.top_up();
-      blk++; p += 16;
+      out.wr += (uint32_t) (hi - lo);
+      out.flush_one<true>(n4);
+      if (in.st - in.rd <= 12u) { in.issue_quad(); cp_wait<3>(); }
+      p += 16; bi++;
     }
+  cp_wait<0>();
   out.flush<true>(n4);
 }
 
@@ -381,131 +513,153 @@ __device__ int fmt_int6(uint8_t *p, int32_t v)
   return len;
 }
 
-__global__ void __launch_bounds__(kThreads6,2)
+__global__ void __launch_bounds__(kMaxWarps6*32,1)
 k_qv_decode6(Dec6Args a)
-{ Shared6 &sm = *reinterpret_cast<Shared6 *>(dx_dec6_smem);
-  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+{ Tables6 &sm = *reinterpret_cast<Tables6 *>(dx_dec6_smem);
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, nthreads = blockDim.x;
+  uint8_t *wmem = dx_dec6_smem + sizeof(Tables6) + (size_t) warp*kWarpBytes6;
 
-  // resident tables: slot 0 del, 1 ins, 2 mrg, 3 sub
+  // resident tables (see plain_stream / run_stream); slot 0 del, 1 ins, 2 mrg, 3 sub
   { const QvDecTables4 *T = a.tab;
     for (int s = 0; s < 4; s++)
       { const int symtab = (s == 0) ? 0 : (s == 1) ? 2 : (s == 2) ? 3 : 4;
         const int runtab = (s == 0) ? 1 : 5;
-        const bool run = (s == 0 && a.delchar >= 0) || (s == 3 && a.subchar >= 0);
-        if (run)
-          { const uint32_t *gr = reinterpret_cast<const uint32_t *>(T->single[runtab]);
-            const uint32_t *gs = reinterpret_cast<const uint32_t *>(T->single[symtab]);
-            for (int j = threadIdx.x; j < 2048; j += kThreads6)
-              { sm.tab[s][j] = __ldg(gr + j); sm.tab[s][2048 + j] = __ldg(gs + j); }
+        const int32_t rci = (s == 0) ? a.delchar : (s == 3) ? a.subchar : -1;
+        if (rci >= 0)
+          { const uint16_t *gr = T->single[runtab], *gs = T->single[symtab];
+            const bool esc = (T->t2.type[symtab] == 2);
+            uint16_t *o_r = sm.one[s == 0 ? 0 : 1][0], *o_s = sm.one[s == 0 ? 0 : 1][1];
+            for (int j = threadIdx.x; j < 4096; j += nthreads)
+              { const uint32_t e1 = __ldg(gr + j);
+                const uint32_t r = e1 & 0xffu, l1 = e1 >> 8;
+                o_r[j] = (uint16_t) e1; o_s[j] = __ldg(gs + j);
+                uint32_t v = 0;
+                if (e1 != 0u && r <= kFastRun && l1 < 12u)
+                  { const uint32_t e2 = __ldg(gs + ((j << l1) & 0xfff));
+                    const uint32_t c = e2 & 0xffu, l2 = e2 >> 8;
+                    if (e2 != 0u && l1 + l2 <= 12u && !(esc && c == 255u) && c != (uint32_t) rci)
+                      v = (l1 + l2) | (r << 8) | (c << 16);
+                  }
+                sm.tab[s][j] = v;
+              }
           }
         else
-          for (int j = threadIdx.x; j < 4096; j += kThreads6) sm.tab[s][j] = __ldg(T->multi[symtab] + j);
+          for (int j = threadIdx.x; j < 4096; j += nthreads)
+            { const uint32_t e = __ldg(T->multi[symtab] + j);
+              sm.tab[s][j] = (e & 0x80u) ? (e & 0x00ff1f80u) : e;
+            }
       }
+    for (int j = threadIdx.x; j < 6*256; j += nthreads) sm.longs[j >> 8][j & 255] = __ldg(&T->longs[j >> 8][j & 255]);
+    if (threadIdx.x < 6) { sm.nlong[threadIdx.x] = T->nlong[threadIdx.x]; sm.type[threadIdx.x] = T->t2.type[threadIdx.x]; }
   }
   __syncthreads();
 
-  const int64_t t = a.first + ((int64_t) blockIdx.x*kWarps6 + warp)*32 + lane;
-  if (t >= a.count) return;
+  // No lane leaves before the end: the lanes of a warp re-join at every phase boundary below
+  // (__syncwarp over the lanes that hold a ticket).
+  const int64_t t = a.first + ((int64_t) blockIdx.x*(nthreads >> 5) + warp)*32 + lane;
+  const bool ticket = (t < a.count);
+  const uint32_t live = __ballot_sync(DX_FULL,ticket);
+  if (!ticket) return;
   const int64_t e = (a.order != NULL) ? (int64_t) a.order[t] : t;
   const int32_t Ls = a.rlen[e];
-  if (Ls < 0)                                               // ruled out by the host
-    { if (a.write != 1) a.status[e] = 1;
-      return;
-    }
-  const uint32_t L = (uint32_t) Ls;
-  const QvDecTables2 *t2 = &a.tab->t2;
+  const uint32_t L = (Ls > 0) ? (uint32_t) Ls : 0u;
   const uint8_t *image_end = a.in + a.n;
+  const int64_t lim = (a.limit != NULL) ? a.limit[e] : a.n;
   Lane ln;
   ln.bad = 0;
-  ln.lim = reinterpret_cast<uint64_t>(a.in) + (uint64_t) ((a.limit != NULL) ? a.limit[e] : a.n) + 80u;
-  uint32_t *ring_lane = &sm.ring[warp][0][lane];
-  uint8_t  *line;
-  if (a.write == 2 && a.ent == NULL)
-    line = a.out + a.toff[e];
-  else
-    { const QvDecEntry en = a.ent[e];
-      line = a.out + en.text_off;
-      if (a.write == 1)
-        { uint8_t *h = a.out + en.out_off;                  // "%s/%d/%d_%d RQ=0.%d\n" (undexqv.c:182)
-          int hl = 0;
-          for (int k = 0; k < a.plen; k++) h[hl++] = (uint8_t) a.prefix[k];
-          h[hl++] = '/'; hl += fmt_int6(h+hl,en.well);
-          h[hl++] = '/'; hl += fmt_int6(h+hl,en.beg);
-          h[hl++] = '_'; hl += fmt_int6(h+hl,en.end);
-          const char *rq = " RQ=0.";
-          for (int k = 0; k < 6; k++) h[hl++] = (uint8_t) rq[k];
-          hl += fmt_int6(h+hl,en.qv);
-          h[hl++] = '\n';
-        }
-    }
-  ln.out.init(line,reinterpret_cast<uint8_t *>(sm.outr[warp]) + lane*kOutPitch);
-
-  int64_t at = a.start[e];
-  int64_t o[6];
-  for (int k = 0; k < 6; k++) o[k] = at;
-  const uint16_t *tab16[4];
-  for (int s = 0; s < 4; s++) tab16[s] = reinterpret_cast<const uint16_t *>(sm.tab[s]);
-
-  do
-    { uint32_t kept = L, bytes;
-      // deletion QVs
-      if (at > a.n) { ln.bad = 1; break; }
-      if (L > 0) ln.in.init<false>(a.in + at,image_end,ring_lane);
-      if (a.delchar >= 0)
-        bytes = run_stream(ln,tab16[0],tab16[0] + 4096,t2,0,1,t2->type[0] == 2,(uint32_t) a.delchar,L,true,&kept);
+  ln.lim = reinterpret_cast<uint64_t>(a.in) + (uint64_t) lim + 80u;
+  uint32_t *ring_lane = reinterpret_cast<uint32_t *>(wmem) + lane;
+  uint8_t  *line = a.out;
+  bool dead = (Ls < 0);                                     // ruled out by the host, or given up
+  if (!dead)
+    { if (a.write == 2 && a.ent == NULL)
+        line = a.out + a.toff[e];
       else
-        bytes = plain_stream(ln,sm.tab[0],t2,0,L,true,NULL);
-      ln.out.put('\n');
-      at += bytes; o[1] = at;
-      if (ln.bad && a.write != 1) break;
-      // deletion tags
-      const uint32_t clen = (a.delchar < 0) ? L : kept;
-      const int64_t tbytes = (clen + 3) >> 2;
-      if (at + tbytes <= a.n)
-        { if (L > 0)
-            { ln.out.sync_partial();                         // the del line is complete in global memory
-              ln.in.init<true>(a.in + at,image_end,ring_lane);
-              tag_line(ln,line,L,a.delchar,(uint32_t) a.upper);
+        { const QvDecEntry en = a.ent[e];
+          line = a.out + en.text_off;
+          if (a.write == 1)
+            { uint8_t *h = a.out + en.out_off;              // "%s/%d/%d_%d RQ=0.%d\n" (undexqv.c:182)
+              int hl = 0;
+              for (int k = 0; k < a.plen; k++) h[hl++] = (uint8_t) a.prefix[k];
+              h[hl++] = '/'; hl += fmt_int6(h+hl,en.well);
+              h[hl++] = '/'; hl += fmt_int6(h+hl,en.beg);
+              h[hl++] = '_'; hl += fmt_int6(h+hl,en.end);
+              const char *rq = " RQ=0.";
+              for (int k = 0; k < 6; k++) h[hl++] = (uint8_t) rq[k];
+              hl += fmt_int6(h+hl,en.qv);
+              h[hl++] = '\n';
             }
         }
-      else
+    }
+  ln.out.init(line,wmem + kRingW*32*4 + lane*kOutPitch);
+
+  int64_t at = a.start[e];
+  if (a.soff != NULL) a.soff[e*6] = at;
+  uint32_t kept = L;
+  int done = 0;                                             // phases completed
+  // phases: 0 deletion QVs, 1 deletion tags, 2 insertion QVs, 3 merge QVs, 4 substitution QVs
+#pragma unroll 1
+  for (int ph = 0; ph < 5; ph++)
+    { // who takes part in this phase is settled BEFORE the ballot: every lane of `act` then calls the
+      // phase's stream function exactly once (its loop heads are ballots over these lanes)
+      bool part = !dead;
+      if (part && at > a.n)
         { ln.bad = 1;
-          for (uint32_t k = 0; k < L; k++) ln.out.put('n'), ln.out.flush<false>(0);
+          if (a.write != 1) { dead = true; part = false; } else at = a.n;
+        }
+      uint32_t Lp = L;
+      int64_t tbytes = 0;
+      if (ph == 1)
+        { const uint32_t clen = (a.delchar < 0) ? L : kept;
+          tbytes = (clen + 3) >> 2;
+          if (at + tbytes > a.n) Lp = 0;                     // the packed tags are cut off: no tag stream
+        }
+      const uint32_t act = __ballot_sync(live,part);        // also where the lanes re-join
+      if (!part) continue;
+      if (ph == 1)
+        { if (Lp > 0)
+            { ln.out.sync_partial();                         // the del line is complete in global memory
+              ln.in.init<true>(a.in + at,image_end,ring_lane);
+            }
+          tag_line(ln,act,reinterpret_cast<uint4 *>(wmem + kRingW*32*4 + 32*kOutPitch) + lane,
+                   line,Lp,a.delchar,(uint32_t) a.upper);
+          if (Lp != L)
+            { ln.bad = 1;
+              for (uint32_t k = 0; k < L; k++) { ln.out.put('n'); ln.out.flush<false>(0); }
+            }
+          at += tbytes;
+        }
+      else
+        { const int slot = (ph == 0) ? 0 : ph - 1;
+          const int symtab = (ph == 0) ? 0 : ph;
+          const int runtab = (ph == 0) ? 1 : 5;
+          const int rci = (ph == 0) ? a.delchar : (ph == 4) ? a.subchar : -1;
+          uint32_t bytes;
+          if (L > 0) ln.in.init<false>(a.in + at,image_end,ring_lane);
+          if (rci >= 0)
+            { uint32_t k2 = 0;
+              const int w = (ph == 0) ? 0 : 1;
+              bytes = run_stream(ln,act,sm.tab[slot],sm.one[w][0],sm.one[w][1],sm.longs[runtab],sm.nlong[runtab],
+                                 sm.longs[symtab],sm.nlong[symtab],sm.type[symtab] == 2,(uint32_t) rci,L,&k2);
+              if (ph == 0) kept = k2;
+            }
+          else
+            bytes = plain_stream(ln,act,sm.tab[slot],sm.longs[symtab],sm.nlong[symtab],sm.type[symtab],L);
+          at += bytes;
         }
       ln.out.put('\n');
-      at += tbytes; o[2] = at;
-      if (at > a.n) { ln.bad = 1; if (a.write != 1) break; at = a.n; }
-      // insertion and merge QVs
-      if (L > 0) ln.in.init<false>(a.in + at,image_end,ring_lane);
-      bytes = plain_stream(ln,sm.tab[1],t2,2,L,true,NULL);
-      ln.out.put('\n');
-      at += bytes; o[3] = at;
-      if (ln.bad && a.write != 1) break;
-      if (at > a.n) { ln.bad = 1; if (a.write != 1) break; at = a.n; }
-      if (L > 0) ln.in.init<false>(a.in + at,image_end,ring_lane);
-      bytes = plain_stream(ln,sm.tab[2],t2,3,L,true,NULL);
-      ln.out.put('\n');
-      at += bytes; o[4] = at;
-      if (ln.bad && a.write != 1) break;
-      if (at > a.n) { ln.bad = 1; if (a.write != 1) break; at = a.n; }
-      // substitution QVs
-      if (L > 0) ln.in.init<false>(a.in + at,image_end,ring_lane);
-      if (a.subchar >= 0)
-        bytes = run_stream(ln,tab16[3],tab16[3] + 4096,t2,4,5,t2->type[4] == 2,(uint32_t) a.subchar,L,true,&kept);
-      else
-        bytes = plain_stream(ln,sm.tab[3],t2,4,L,true,NULL);
-      ln.out.put('\n');
-      at += bytes; o[5] = at;
-      ln.out.sync_partial();
+      ln.out.flush_one<false>(0);
+      if (a.soff != NULL) a.soff[e*6 + ph + 1] = at;
+      done = ph + 1;
+      if (ln.bad && a.write != 1) dead = true;
     }
-  while (false);
-
-  const int64_t lim = (a.limit != NULL) ? a.limit[e] : a.n;
-  if (at > lim) ln.bad = 1;
+  __syncwarp(live);
+  if (Ls >= 0) ln.out.sync_partial();
+  if (at > lim || Ls < 0) ln.bad = 1;
   if (a.soff != NULL)
-    for (int k = 0; k < 6; k++) a.soff[e*6 + k] = (k == 0 || o[k] >= o[k-1]) ? o[k] : at;
+    for (int k = done + 1; k < 6; k++) a.soff[e*6 + k] = at;
   if (a.write == 1) { if (ln.bad) atomicExch(a.status,1); }
-  else a.status[e] = (int32_t) ln.bad;
+  else a.status[e] = (ln.bad != 0);
 }
 
 }  // namespace
@@ -530,10 +684,17 @@ int dxk_qv_decode6x(dx_ctx *ctx, const uint8_t *d_in, size_t n, const QvDecTable
   a.first = n_coop; a.count = count; a.start = d_start; a.rlen = d_rlen; a.ent = d_ent;
   a.toff = d_toff; a.prefix = d_prefix; a.plen = plen; a.out = d_out; a.soff = d_soff; a.status = d_status;
   a.limit = d_limit; a.order = d_order;
-  const size_t smem = sizeof(Shared6);
-  DX_CUDA(ctx,cudaFuncSetAttribute(k_qv_decode6,cudaFuncAttributeMaxDynamicSharedMemorySize,(int) smem));
-  const int64_t grid = (count - n_coop + kThreads6 - 1) / kThreads6;
-  DX_PROF_BEGIN(ctx); k_qv_decode6<<<(unsigned) grid,kThreads6,smem,ctx->stream>>>(a);
+  // one CTA per SM (the tables take 102 KB): as many warps per CTA as it takes to have every entry
+  // in flight at once, up to 16; more entries than that run in waves, longest first
+  const int64_t nwarps = (count - n_coop + 31) / 32;
+  int64_t wpc = (nwarps + ctx->sm_count - 1) / ctx->sm_count;
+  if (wpc < 1) wpc = 1;
+  if (wpc > kMaxWarps6) wpc = kMaxWarps6;
+  const size_t smem = sizeof(Tables6) + (size_t) wpc*kWarpBytes6;
+  DX_CUDA(ctx,cudaFuncSetAttribute(k_qv_decode6,cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int) (sizeof(Tables6) + (size_t) kMaxWarps6*kWarpBytes6)));
+  const int64_t grid = (nwarps + wpc - 1) / wpc;
+  DX_PROF_BEGIN(ctx); k_qv_decode6<<<(unsigned) grid,(unsigned) (wpc*32),smem,ctx->stream>>>(a);
   DX_LAUNCHED(ctx,write == 1 ? "k_qv_decode6" : "k_qv_decode6_spec");
   return DX_OK;
 }
