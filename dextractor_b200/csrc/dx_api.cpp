@@ -306,6 +306,12 @@ extern "C" void dx_pinned_free(dx_ctx *ctx, void *p) { (void) ctx; if (p) cudaFr
 
 extern "C" int dx_h2d(dx_ctx *ctx, void *d, const void *h, size_t n)
 { DX_CUDA(ctx,cudaMemcpyAsync(d,h,n,cudaMemcpyHostToDevice,ctx->stream)); return DX_OK; }
+extern "C" int dx_d2d(dx_ctx *ctx, void *d_dst, const void *d_src, size_t n)
+{ if (ctx == NULL) return DX_E_ARG;
+  cudaSetDevice(ctx->device);
+  if (n > 0) DX_CUDA(ctx,cudaMemcpyAsync(d_dst,d_src,n,cudaMemcpyDeviceToDevice,ctx->stream));
+  return DX_OK;
+}
 extern "C" int dx_d2h(dx_ctx *ctx, void *h, const void *d, size_t n)
 { DX_CUDA(ctx,cudaMemcpyAsync(h,d,n,cudaMemcpyDeviceToHost,ctx->stream)); return DX_OK; }
 
@@ -1106,8 +1112,50 @@ extern "C" int dx_qv_encode_dev(dx_ctx *ctx, const uint8_t *d_text, size_t n,
     }
   QvEncTables tab;
   pack_tables(coding,&tab);
-  return dxk_qv_encode(ctx,d_text,n,ctx->qv_ent,&tab,coding->delchar,coding->subchar,lossy,lwell_in,
-                       d_out,cap,out_len,last_well,h_entry_off,max_entries);
+  rc = dxk_qv_encode(ctx,d_text,n,ctx->qv_ent,&tab,coding->delchar,coding->subchar,lossy,lwell_in,
+                     d_out,cap,out_len,last_well,h_entry_off,max_entries);
+  // The framing of dx_qv_scan_dev serves ONE encode of the same buffer: a caller that refills the
+  // buffer (same address, same size) and encodes again must not meet the offsets of the old text.
+  ctx->qv_text = NULL; ctx->qv_n = 0;
+  return rc;
+}
+
+extern "C" int dx_qv_forget(dx_ctx *ctx)
+{ if (ctx == NULL) return DX_E_ARG;
+  ctx->qv_text = NULL; ctx->qv_n = 0; ctx->qv_ent.n = 0;
+  return DX_OK;
+}
+
+extern "C" int dx_qv_last_well(dx_ctx *ctx, int32_t *well)
+{ if (ctx == NULL || well == NULL) return DX_E_ARG;
+  *well = 0;
+  if (ctx->qv_text == NULL || ctx->qv_ent.n == 0) return DX_OK;
+  cudaSetDevice(ctx->device);
+  DX_CUDA(ctx,cudaMemcpyAsync(well,ctx->qv_ent.well + (ctx->qv_ent.n - 1),4,cudaMemcpyDeviceToHost,ctx->stream));
+  DX_CUDA(ctx,cudaStreamSynchronize(ctx->stream));
+  return DX_OK;
+}
+
+extern "C" int dx_text_lines_dev(dx_ctx *ctx, const uint8_t *d_text, size_t n, int64_t skip,
+                                 int64_t *nlines, int64_t *skip_off)
+{ if (ctx == NULL || nlines == NULL || skip < 0) return DX_E_ARG;
+  int rc;
+  *nlines = 0;
+  if (skip_off) *skip_off = (skip == 0) ? 0 : -1;
+  if (n == 0) return DX_OK;
+  if ((rc = check_buf(ctx,d_text,"text")) != DX_OK) return rc;
+  cudaSetDevice(ctx->device);
+  dx_arena_reset(ctx);
+  int64_t *d_nl = NULL, cnt = 0;
+  if ((rc = dxk_index_positions(ctx,DX_PRED_NEWLINE,d_text,n,0,&d_nl,&cnt)) != DX_OK) return rc;
+  *nlines = cnt;
+  if (skip_off != NULL && skip > 0 && skip <= cnt)
+    { int64_t at = -1;
+      DX_CUDA(ctx,cudaMemcpyAsync(&at,d_nl + (skip - 1),8,cudaMemcpyDeviceToHost,ctx->stream));
+      DX_CUDA(ctx,cudaStreamSynchronize(ctx->stream));
+      *skip_off = at + 1;
+    }
+  return DX_OK;
 }
 
 extern "C" int dx_dexqv_dev(dx_ctx *ctx, const uint8_t *d_text, size_t n, int lossy,

@@ -18,14 +18,15 @@ ERRNAMES = {-1: "FORMAT", -2: "CAP", -3: "TRUNC", -4: "KEY", -5: "LINELEN", -6: 
 # every symbol include/dexb200.h declares (checked by tests/test_abi.py)
 SYMBOLS = [
     "dx_open", "dx_close", "dx_strerror", "dx_error_line", "dx_sync", "dx_stream",
-    "dx_device_alloc", "dx_device_free", "dx_pinned_alloc", "dx_pinned_free", "dx_h2d", "dx_d2h",
+    "dx_device_alloc", "dx_device_free", "dx_pinned_alloc", "dx_pinned_free", "dx_h2d", "dx_d2h", "dx_d2d",
     "dx_launch_count", "dx_profile", "dx_profile_report", "dx_route",
     "dx_dexta_dev", "dx_dexta_host", "dx_undexta_dev", "dx_undexta_host", "dx_undexta_size_host",
     "dx_undexta_size_dev",
     "dx_compress_reads_dev", "dx_uncompress_reads_dev",
     "dx_qv_scan_dev", "dx_qv_make_coding", "dx_qv_write_coding", "dx_qv_read_coding",
     "dx_qv_encode_dev", "dx_dexqv_dev", "dx_dexqv_host", "dx_undexqv_dev", "dx_undexqv_host",
-    "dx_undexqv_size_dev", "dx_keep_index", "dx_last_index",
+    "dx_undexqv_size_dev", "dx_keep_index", "dx_last_index", "dx_qv_forget", "dx_qv_last_well",
+    "dx_text_lines_dev",
 ]
 
 
@@ -106,6 +107,7 @@ def load_library():
         "dx_pinned_free": (None, [vp, vp]),
         "dx_h2d": (C.c_int, [vp, vp, vp, sz]),
         "dx_d2h": (C.c_int, [vp, vp, vp, sz]),
+        "dx_d2d": (C.c_int, [vp, vp, vp, sz]),
         "dx_launch_count": (C.c_uint64, [vp, C.c_int]),
         "dx_profile": (C.c_int, [vp, C.c_int]),
         "dx_route": (C.c_int, [vp, C.c_char_p, i64]),
@@ -130,6 +132,9 @@ def load_library():
         "dx_undexqv_host": (C.c_int, [vp, vp, sz, C.c_int, vp, sz, szp]),
         "dx_undexqv_size_dev": (C.c_int, [vp, vp, sz, szp]),
         "dx_keep_index": (C.c_int, [vp, C.c_int]),
+        "dx_qv_forget": (C.c_int, [vp]),
+        "dx_qv_last_well": (C.c_int, [vp, C.POINTER(i32)]),
+        "dx_text_lines_dev": (C.c_int, [vp, vp, sz, i64, C.POINTER(i64), C.POINTER(i64)]),
         "dx_last_index": (C.c_int, [vp, vp, i64, C.POINTER(i64)]),
     }
     for name, (res, args) in sig.items():
@@ -343,6 +348,21 @@ class Context:
             self._check(self.L.dx_undexqv_dev(self.h, d_in, n, int(upper), d_out, cap, C.byref(m),
                                               None, 0, well_in))
         return m.value
+
+    def qv_forget(self):
+        self._check(self.L.dx_qv_forget(self.h))
+
+    def qv_last_well(self) -> int:
+        w = C.c_int32(0)
+        self._check(self.L.dx_qv_last_well(self.h, C.byref(w)))
+        return w.value
+
+    def text_lines_dev(self, d_text, n, skip: int = 0):
+        """-> (newlines in the buffer, offset just behind the skip-th newline or -1)"""
+        _wait_for_torch()
+        cnt, off = C.c_int64(0), C.c_int64(0)
+        self._check(self.L.dx_text_lines_dev(self.h, d_text, n, skip, C.byref(cnt), C.byref(off)))
+        return cnt.value, off.value
 
     def keep_index(self, keep: bool = True):
         self._check(self.L.dx_keep_index(self.h, int(keep)))

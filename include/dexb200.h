@@ -59,6 +59,7 @@ void *dx_pinned_alloc(dx_ctx *ctx, size_t bytes);
 void  dx_pinned_free (dx_ctx *ctx, void *p);
 int   dx_h2d(dx_ctx *ctx, void *d_dst, const void *h_src, size_t bytes);   /* async on stream */
 int   dx_d2h(dx_ctx *ctx, void *h_dst, const void *d_src, size_t bytes);   /* async on stream */
+int   dx_d2d(dx_ctx *ctx, void *d_dst, const void *d_src, size_t bytes);   /* async; no overlap */
 
 /* launches issued by this context since the last reset (for the bench's gpu_launches claim) */
 uint64_t dx_launch_count(dx_ctx *ctx, int reset);
@@ -186,6 +187,22 @@ int dx_qv_read_coding (const uint8_t *in, size_t n, dx_qv_coding *coding,
 int dx_qv_encode_dev(dx_ctx *ctx, const uint8_t *d_text, size_t n, const dx_qv_coding *coding,
                      int lossy, int32_t lwell_in, uint8_t *d_out, size_t cap, size_t *out_len,
                      int32_t *last_well, int64_t *h_entry_off, int64_t max_entries);
+
+/* The framing kept by dx_qv_scan_dev serves the NEXT dx_qv_encode_dev on the same buffer and is
+ * dropped after it (a second encode frames the text again).  The text must not change between the
+ * two calls; dx_qv_forget drops the framing explicitly.  dx_qv_last_well: the well number of the last
+ * entry of the buffer scanned last -- what the next shard's first well delta is coded against
+ * (dexqv.c:128-135); 0 for an empty shard. */
+int dx_qv_forget(dx_ctx *ctx);
+int dx_qv_last_well(dx_ctx *ctx, int32_t *well);
+
+/* Cutting one .quiva file into shards without parsing it (a line that starts with '@' proves
+ * nothing, '@' is QV 31; entries are found by COUNTING lines, QV.c:751-798 reads 6 per entry):
+ * *nlines = newlines in d_text[0..n); *skip_off = offset just behind the skip-th newline (0 for
+ * skip == 0, -1 when the buffer has fewer).  A rank whose range starts at global line g skips
+ * (6 - g % 6) % 6 lines to reach its first entry. */
+int dx_text_lines_dev(dx_ctx *ctx, const uint8_t *d_text, size_t n, int64_t skip,
+                      int64_t *nlines, int64_t *skip_off);
 
 /* The whole tool on one GPU: scan, make coding, 0x55aa key + coding header, encode.
  * Replaces dexqv.c:59-147. */
