@@ -627,12 +627,14 @@ static int dexta_impl(dx_ctx *ctx, int kind, const uint8_t *d_text, size_t n,
       if (rc != DX_OK) return rc;
       DX_CUDA(ctx,cudaMemcpyAsync(res,d_flags + 1,16,cudaMemcpyDeviceToHost,ctx->stream));
       DX_CUDA(ctx,cudaStreamSynchronize(ctx->stream));
+      if (res[0] == 2) return dx_fail(ctx,DX_E_TOOLONG,"%s line is too long (> 99998 chars)",kind == DX_FASTA ? "Fasta" : "Arrow");
       if (res[0]) { *redo = true; return DX_OK; }
       if (res[3])                                   // entries off the lattice (or narrower than 16)
         { if ((rc = dxk_fa_pack2(ctx,kind,d_text,ent,0,d_out + hbytes,d_flags + 1,
                                  (unsigned long long *) (d_flags + 6),1)) != DX_OK) return rc;
           DX_CUDA(ctx,cudaMemcpyAsync(res,d_flags + 1,4,cudaMemcpyDeviceToHost,ctx->stream));
           DX_CUDA(ctx,cudaStreamSynchronize(ctx->stream));
+          if (res[0] == 2) return dx_fail(ctx,DX_E_TOOLONG,"%s line is too long (> 99998 chars)",kind == DX_FASTA ? "Fasta" : "Arrow");
           if (res[0]) { *redo = true; return DX_OK; }
         }
     }
@@ -1419,7 +1421,20 @@ static int64_t lpt_order(const dx_ctx *ctx, const std::vector<CandInfo> &info, s
 struct QvWalkUser
 { const uint8_t *d_in; size_t n; const QvPlan *plan;
   std::vector<int64_t> side;           // 6 stream offsets per slow-path entry
+  int fieldbytes;                      // 12: int32 beg/end/qv; 6: the old layout's uint16 (undexqv.c:162-180)
+  int flip;                            // fields (and stream words) in the other byte order
 };
+
+// field k (0 beg, 1 end, 2 qv) of an entry header in either layout and byte order (undexqv.c:135-180)
+static int32_t qv_field(const uint8_t *f, int k, int fieldbytes, int flip)
+{ if (fieldbytes == 12)
+    { const uint8_t *p = f + 4*k;
+      return flip ? (int32_t) ((uint32_t) p[3] | ((uint32_t) p[2] << 8) | ((uint32_t) p[1] << 16) | ((uint32_t) p[0] << 24))
+                  : le32(p);
+    }
+  const uint8_t *p = f + 2*k;
+  return flip ? (int32_t) ((uint32_t) p[1] | ((uint32_t) p[0] << 8)) : (int32_t) ((uint32_t) p[0] | ((uint32_t) p[1] << 8));
+}
 
 // walk `count` entries whose first stream byte / length are on the device
 static int qv_walk(dx_ctx *ctx, const uint8_t *d_in, size_t n, const QvPlan &plan,
@@ -1437,17 +1452,18 @@ static int qv_walk_one(dx_ctx *ctx, void *user, int64_t q, int64_t *end, int64_t
 { QvWalkUser *u = (QvWalkUser *) user;
   int rc;
   std::vector<uint8_t> f;
-  if ((rc = peek(ctx,u->d_in,u->n,(size_t) q,12,f)) != DX_OK) return rc;
+  const int fb = u->fieldbytes;
+  if ((rc = peek(ctx,u->d_in,u->n,(size_t) q,(size_t) fb,f)) != DX_OK) return rc;
   *slot = (int64_t) (u->side.size() / 6);
-  if (f.size() < 12) { *end = -1; return DX_OK; }
-  const int32_t rlen = le32(f.data()+4) - le32(f.data());
+  if ((int) f.size() < fb) { *end = -1; return DX_OK; }
+  const int32_t rlen = qv_field(f.data(),1,fb,u->flip) - qv_field(f.data(),0,fb,u->flip);
   if (rlen < 0 || rlen >= (1 << 24)) { *end = -1; return DX_OK; }
   int64_t *d_start = (int64_t *) dx_arena_get(ctx,8);
   int32_t *d_rlen  = (int32_t *) dx_arena_get(ctx,4);
   int64_t *d_soff  = (int64_t *) dx_arena_get(ctx,48);
   int32_t *d_stat  = (int32_t *) dx_arena_get(ctx,4);
   if (!d_start || !d_rlen || !d_soff || !d_stat) return DX_E_NOMEM;
-  const int64_t start = q + 12;
+  const int64_t start = q + fb;
   if ((rc = upload(ctx,d_start,&start,1)) != DX_OK) return rc;
   if ((rc = upload(ctx,d_rlen,&rlen,1)) != DX_OK) return rc;
   if ((rc = qv_walk(ctx,u->d_in,u->n,*u->plan,d_start,d_rlen,1,d_soff,d_stat)) != DX_OK) return rc;
@@ -1466,16 +1482,24 @@ static int plan_undexqv(dx_ctx *ctx, const uint8_t *d_in, size_t n, const int64_
   if ((rc = peek(ctx,d_in,n,0,2 + 16384 + 100000,head)) != DX_OK) return rc;
   if (head.size() < 2) return dx_fail(ctx,DX_E_TRUNC,"System error, read failed!");
   uint16_t key; memcpy(&key,head.data(),2);
-  if (!(key == 0x55aa || key == 0xaa55))
-    return dx_fail(ctx,DX_E_KEY,"old-format .dexqv (16-bit entry fields, undexqv.c:107-110) is not supported");
+  // new layout: 0x55aa (either byte order) in front of the coding header; old layout: the file starts
+  // with the coding header itself (key 0x33cc) and beg/end/qv are uint16 (undexqv.c:103-110)
+  const bool newv = (key == 0x55aa || key == 0xaa55);
+  if (!newv && !(key == 0x33cc || key == 0xcc33))
+    return dx_fail(ctx,DX_E_KEY,"not a .dexqv file (endian key 0x%04x)",(unsigned) key);
+  const size_t keylen = newv ? 2 : 0;
   std::vector<char> prefix(100001);
   size_t used = 0;
-  if ((rc = dx_qv_read_coding(head.data()+2,head.size()-2,&plan.coding,prefix.data(),
+  if ((rc = dx_qv_read_coding(head.data()+keylen,head.size()-keylen,&plan.coding,prefix.data(),
                               (int) prefix.size(),&used)) != DX_OK)
     return dx_fail(ctx,rc,"Could not read the coding header (Read_QVcoding)");
-  if (plan.coding.flip)
-    return dx_fail(ctx,DX_E_KEY,"foreign-endian .dexqv is not supported");
-  const size_t first = 2 + used;
+  // A file of the other byte order (every stream word flipped, QV.c:553-568) or of the old layout is
+  // rare: it takes the sequential kernels, which flip words as they read them, and finds its
+  // entries by walking them one after the other.  Slow (a launch per entry), but the reference's bytes.
+  const bool legacy = (plan.coding.flip != 0) || !newv;
+  const int fieldbytes = newv ? 12 : 6;
+  if (legacy) { h_entry_off = NULL; nentries = 0; }
+  const size_t first = keylen + used;
   DxPhases ph(ctx);
   plan.plen = (int) strlen(prefix.data());
   plan.d_soff = NULL; plan.d_start = NULL; plan.d_rlen = NULL; plan.d_tab = NULL;
@@ -1485,7 +1509,7 @@ static int plan_undexqv(dx_ctx *ctx, const uint8_t *d_in, size_t n, const int64_
     // codes than the sub-tables take) is decoded by the sequential kernels of dx_qv_decode.cu
     QvDecTables4 *h4 = (QvDecTables4 *) malloc(sizeof(QvDecTables4));
     if (h4 == NULL) return DX_E_NOMEM;
-    plan.v2 = (ctx->route[DXR_DECODER] != 1) && build_dec_tables4(&plan.coding,h4);
+    plan.v2 = (ctx->route[DXR_DECODER] != 1) && !legacy && build_dec_tables4(&plan.coding,h4);
     plan.d_tab4 = NULL;
     if (plan.v2)
       { plan.d_tab4 = (QvDecTables4 *) dx_arena_get(ctx,sizeof(QvDecTables4));
@@ -1557,7 +1581,8 @@ static int plan_undexqv(dx_ctx *ctx, const uint8_t *d_in, size_t n, const int64_
   else
     { int64_t *d_q = NULL, nc = 0;
       ph.mark("tables");
-      if ((rc = dxk_index_positions(ctx,DX_PRED_QVCAND,d_in,n,first + 1,&d_q,&nc)) != DX_OK) return rc;
+      if (!legacy &&
+          (rc = dxk_index_positions(ctx,DX_PRED_QVCAND,d_in,n,first + 1,&d_q,&nc)) != DX_OK) return rc;
       ph.mark("index");
       const size_t N = (size_t) nc;
       int64_t  *d_fs    = (int64_t *) dx_arena_get(ctx,N*8);
@@ -1657,9 +1682,9 @@ static int plan_undexqv(dx_ctx *ctx, const uint8_t *d_in, size_t n, const int64_
       ph.mark("decode+download");
       std::vector<int64_t> end(N);
       for (size_t i = 0; i < N; i++) end[i] = stat[i] ? -1 : soff[6*i+5];
-      QvWalkUser user = { d_in, n, &plan, {} };
+      QvWalkUser user = { d_in, n, &plan, {}, fieldbytes, plan.coding.flip };
       std::vector<ChainEntry> chain;
-      if ((rc = resolve_chain(ctx,d_in,n,first,12,q,end,info,qv_walk_one,&user,chain)) != DX_OK)
+      if ((rc = resolve_chain(ctx,d_in,n,first,fieldbytes,q,end,info,qv_walk_one,&user,chain)) != DX_OK)
         return rc;
       ph.mark("chain");
       const size_t M = chain.size();
@@ -1683,8 +1708,10 @@ static int plan_undexqv(dx_ctx *ctx, const uint8_t *d_in, size_t n, const int64_
                                              : &user.side[6*(size_t) (-2 - c.cand)];
           memcpy(&so[6*i],src,48);
           hdrs[i].well = c.well + well_in;
-          hdrs[i].beg = le32(c.field); hdrs[i].end = le32(c.field+4); hdrs[i].qv = le32(c.field+8);
-          st[i] = c.q + 12;
+          hdrs[i].beg = qv_field(c.field,0,fieldbytes,plan.coding.flip);
+          hdrs[i].end = qv_field(c.field,1,fieldbytes,plan.coding.flip);
+          hdrs[i].qv  = qv_field(c.field,2,fieldbytes,plan.coding.flip);
+          st[i] = c.q + fieldbytes;
           rl[i] = hdrs[i].end - hdrs[i].beg;
         }
       plan.ix_fs = st;
@@ -2047,6 +2074,67 @@ extern "C" int dx_undexqv_dev(dx_ctx *ctx, const uint8_t *d_in, size_t n, int up
         }
     }
   *out_len = plan.text_len;
+  return DX_OK;
+}
+
+// Batched Load_QVentry (DB.c:2575-2621): the streams of entry i start at d_in[h_stream_off[i]] and
+// hold h_rlen[i] positions; its five lines, each followed by a newline, go to
+// d_out[off[i] .. off[i] + 5*(rlen+1)) with off = exclusive prefix sum (returned in h_out_off).
+extern "C" int dx_qv_load_entries_dev(dx_ctx *ctx, const uint8_t *d_in, size_t n, const dx_qv_coding *coding,
+                                      const int64_t *h_stream_off, const int32_t *h_rlen, int64_t nentries,
+                                      int upper, uint8_t *d_out, size_t cap, int64_t *h_out_off,
+                                      int64_t *h_end_off)
+{ if (ctx == NULL || coding == NULL || nentries < 0 || (nentries > 0 && (!h_stream_off || !h_rlen))) return DX_E_ARG;
+  int rc;
+  if ((rc = check_buf(ctx,d_in,"image")) != DX_OK) return rc;
+  if (coding->flip) return dx_fail(ctx,DX_E_KEY,"dx_qv_load_entries_dev: foreign-endian codings are not supported");
+  cudaSetDevice(ctx->device);
+  dx_arena_reset(ctx);
+  const size_t N = (size_t) nentries;
+  std::vector<int64_t> toff(N + 1,0);
+  for (size_t i = 0; i < N; i++)
+    { if (h_rlen[i] < 0 || h_rlen[i] >= (1 << 24) || h_stream_off[i] < 0 || (size_t) h_stream_off[i] > n)
+        return dx_fail(ctx,DX_E_ARG,"dx_qv_load_entries_dev: entry %zu out of range",i);
+      toff[i+1] = toff[i] + 5*((int64_t) h_rlen[i] + 1);
+    }
+  if (h_out_off) memcpy(h_out_off,toff.data(),(N + 1)*8);
+  if (N == 0) return DX_OK;
+  if ((size_t) toff[N] > cap)
+    return dx_fail(ctx,DX_E_CAP,"output needs %lld bytes, buffer has %zu",(long long) toff[N],cap);
+  QvDecTables4 *h4 = (QvDecTables4 *) malloc(sizeof(QvDecTables4));
+  if (h4 == NULL) return DX_E_NOMEM;
+  if (!build_dec_tables4(coding,h4))
+    { free(h4);
+      return dx_fail(ctx,DX_E_CODING,"dx_qv_load_entries_dev: the coding has more long codes than the decode tables hold");
+    }
+  QvDecTables4 *d_tab4 = (QvDecTables4 *) dx_arena_get(ctx,sizeof(QvDecTables4));
+  rc = d_tab4 ? upload(ctx,d_tab4,h4,1) : DX_E_NOMEM;
+  free(h4);
+  if (rc != DX_OK) return rc;
+  int64_t *d_start = (int64_t *) dx_arena_get(ctx,N*8);
+  int32_t *d_rlen  = (int32_t *) dx_arena_get(ctx,N*4);
+  int64_t *d_toff  = (int64_t *) dx_arena_get(ctx,(N+1)*8);
+  int64_t *d_soff  = (int64_t *) dx_arena_get(ctx,N*48);
+  int32_t *d_stat  = (int32_t *) dx_arena_get(ctx,N*4);
+  int32_t *d_order = (int32_t *) dx_arena_get(ctx,N*4);
+  if (!d_start || !d_rlen || !d_toff || !d_soff || !d_stat || !d_order) return DX_E_NOMEM;
+  std::vector<int32_t> order(N);
+  const int64_t n_coop = ticket_plan(ctx,h_rlen,N,order.data());
+  if ((rc = upload(ctx,d_start,h_stream_off,N)) != DX_OK) return rc;
+  if ((rc = upload(ctx,d_rlen,h_rlen,N)) != DX_OK) return rc;
+  if ((rc = upload(ctx,d_toff,toff.data(),N + 1)) != DX_OK) return rc;
+  if ((rc = upload(ctx,d_order,order.data(),N)) != DX_OK) return rc;
+  if ((rc = dxk_qv_decode6x(ctx,d_in,n,d_tab4,coding->delchar,coding->subchar,upper,2,(int64_t) N,d_start,d_rlen,
+                            NULL,NULL,0,d_out,d_soff,d_stat,NULL,d_order,d_toff,n_coop)) != DX_OK) return rc;
+  std::vector<int32_t> stat;
+  if ((rc = download(ctx,d_stat,N,stat)) != DX_OK) return rc;
+  for (size_t i = 0; i < N; i++)
+    if (stat[i]) return dx_fail(ctx,DX_E_TRUNC,"Could not read more bits (Decode), entry %zu",i + 1);
+  if (h_end_off != NULL)
+    { std::vector<int64_t> so;
+      if ((rc = download(ctx,d_soff,N*6,so)) != DX_OK) return rc;
+      for (size_t i = 0; i < N; i++) h_end_off[i] = so[6*i + 5];
+    }
   return DX_OK;
 }
 

@@ -99,8 +99,9 @@ struct Shim
   int64_t next = 0;
   // decoder side
   std::vector<uint8_t> dimg;            // key + coding header + entries
-  int64_t dpos0 = 0;                    // file offset of dimg[2]
-  bool decoded = false;
+  int64_t dpos0 = 0;                    // file offset of dimg[dkey]
+  int     dkey = 2;                     // key bytes put in front of the captured image (0: old layout)
+  bool decoded = false, undecodable = false;
   std::vector<uint8_t> dtext;
   std::vector<dx_index_row> index;
   // line reader (QV.c:733-798)
@@ -452,20 +453,24 @@ void Write_QVcoding(FILE *output, QVcoding *coding)
 QVcoding *Read_QVcoding(FILE *input)
 { static QVcoding coding;
   S.dpos0 = (int64_t) ftello(input);
-  S.dimg.assign(2,0);
-  S.dimg[0] = 0xaa; S.dimg[1] = 0x55;                      // the key the caller has already read
+  // undexqv.c:103-110: a caller that found no 0x55aa key rewinds -- position 0 means the OLD layout
+  // (the file begins with the coding header, entry fields are uint16); anywhere else the key the
+  // caller has already consumed is put back in front of the image
+  S.dkey = (S.dpos0 == 0) ? 0 : 2;
+  S.dimg.assign((size_t) S.dkey,0);
+  if (S.dkey) { S.dimg[0] = 0xaa; S.dimg[1] = 0x55; }
   { char buf[1 << 16]; size_t k;
     while ((k = fread(buf,1,sizeof(buf),input)) > 0) S.dimg.insert(S.dimg.end(),buf,buf + k);
   }
   dx_qv_coding cd;
   std::vector<char> prefix(100001);
   size_t used = 0;
-  if (dx_qv_read_coding(S.dimg.data() + 2,S.dimg.size() - 2,&cd,prefix.data(),(int) prefix.size(),&used) != DX_OK)
+  if (dx_qv_read_coding(S.dimg.data() + S.dkey,S.dimg.size() - (size_t) S.dkey,&cd,prefix.data(),(int) prefix.size(),&used) != DX_OK)
     { DXC_MSG("%s: Could not read the coding scheme (Read_QVcoding)\n",Prog_Name); DXC_EXIT(2,NULL); }
   DXC_TRY { publish(&coding,&cd); } DXC_CATCH(NULL)
   coding.prefix = strdup(prefix.data());
   fseeko(input,(off_t) (S.dpos0 + (int64_t) used),SEEK_SET);
-  S.decoded = false;
+  S.decoded = false; S.undecodable = false;
   return &coding;
 }
 
@@ -499,40 +504,77 @@ void Compress_Next_QVentry1(int rlen, char *del, char *tag, char *ins, char *mrg
   DXC_CATCH_VOID
 }
 
+// Two ways to serve the call, both leave the FILE* exactly where the reference would (QV.c:1428-1481):
+//   * the file Read_QVcoding captured is a .dexqv (undexqv.c's loop): the whole image is decoded once,
+//     every call hands out the entry whose streams start at the current position;
+//   * anything else -- a Dazzler .qvs (bare streams, several codings in one file, DB.c:2450-2507) read
+//     after fseeko(coff) (DB.c:2598-2599), or a position the index does not know: the bytes that follow
+//     the position are decoded as ONE entry with the coding the caller passes (dx_qv_load_entries_dev).
+static int one_entry(FILE *input, char **entry, QVcoding *coding, int rlen)
+{ dx_ctx *c = gpu();
+  const off_t pos = ftello(input);
+  // worst case: every symbol escaped (16-bit code + 8-bit literal) in four streams, plus the tags
+  const size_t want = (size_t) rlen*13 + 256;
+  std::vector<uint8_t> buf(want);
+  const size_t got = fread(buf.data(),1,want,input);
+  need(&S.d_a,&S.cap_a,got + 64);
+  const size_t outn = 5*((size_t) rlen + 1);
+  need(&S.d_b,&S.cap_b,outn + 64);
+  if (got) dx_h2d(c,S.d_a,buf.data(),got);
+  int64_t so = 0, eo = 0; int32_t rl = rlen;
+  if (dx_qv_load_entries_dev(c,S.d_a,got,dxc(coding),&so,&rl,1,0,S.d_b,S.cap_b,NULL,&eo) != DX_OK)
+    { DXC_MSG("%s: Could not read more bits (Decode)\n",Prog_Name ? Prog_Name : "dexcompat"); return 1; }
+  std::vector<uint8_t> lines(outn);
+  dx_d2h(c,lines.data(),S.d_b,outn);
+  if (dx_sync(c) != DX_OK) fatal("GPU error");
+  for (int e = 0; e < 5; e++)
+    memcpy(entry[e],lines.data() + (size_t) e*((size_t) rlen + 1),(size_t) rlen);
+  fseeko(input,pos + (off_t) eo,SEEK_SET);
+  return 0;
+}
+
 int Uncompress_Next_QVentry(FILE *input, char **entry, QVcoding *coding, int rlen)
-{ (void) coding;
-  if (!S.decoded)
+{ if (!S.decoded && !S.undecodable && S.dimg.size() > 2)
     DXC_TRY
     { dx_ctx *c = gpu();
       need(&S.d_a,&S.cap_a,S.dimg.size());
       dx_h2d(c,S.d_a,S.dimg.data(),S.dimg.size());
       size_t want = 0, m = 0;
-      if (dx_undexqv_size_dev(c,S.d_a,S.dimg.size(),&want) != DX_OK) fatal("Uncompress_Next_QVentry");
-      need(&S.d_b,&S.cap_b,want);
-      dx_keep_index(c,1);
-      if (dx_undexqv_dev(c,S.d_a,S.dimg.size(),0,S.d_b,S.cap_b,&m,NULL,0,0) != DX_OK) fatal("Uncompress_Next_QVentry");
-      int64_t cnt = 0;
-      dx_last_index(c,NULL,0,&cnt);
-      S.index.resize((size_t) cnt);
-      dx_last_index(c,S.index.data(),cnt,&cnt);
-      S.dtext.resize(m);
-      if (m) dx_d2h(c,S.dtext.data(),S.d_b,m);
-      dx_sync(c);
-      if (cnt == 0 && m > 0) fatal("no entry index for this file (general decode path)");
-      S.decoded = true;
+      S.undecodable = true;                                  // until the whole image proves to be a .dexqv
+      if (dx_undexqv_size_dev(c,S.d_a,S.dimg.size(),&want) == DX_OK)
+        { need(&S.d_b,&S.cap_b,want);
+          dx_keep_index(c,1);
+          const int rc = dx_undexqv_dev(c,S.d_a,S.dimg.size(),0,S.d_b,S.cap_b,&m,NULL,0,0);
+          int64_t cnt = 0;
+          if (rc == DX_OK) dx_last_index(c,NULL,0,&cnt);
+          if (rc == DX_OK && (cnt > 0 || m == 0))
+            { S.index.resize((size_t) cnt);
+              dx_last_index(c,S.index.data(),cnt,&cnt);
+              S.dtext.resize(m);
+              if (m) dx_d2h(c,S.dtext.data(),S.d_b,m);
+              dx_sync(c);
+              S.decoded = true; S.undecodable = false;
+            }
+          dx_keep_index(c,0);
+        }
     }
     DXC_CATCH(1)
-  // which entry starts at the current file position
-  const int64_t img = (int64_t) ftello(input) - S.dpos0 + 2;
-  size_t lo = 0, hi = S.index.size();
-  while (lo < hi) { const size_t mid = (lo + hi)/2; if (S.index[mid].stream_off < img) lo = mid + 1; else hi = mid; }
-  if (lo >= S.index.size() || S.index[lo].stream_off != img || S.index[lo].rlen != rlen)
-    { DXC_MSG("%s: Could not read entry (Uncompress_Next_QVentry)\n",Prog_Name); return 1; }
-  const dx_index_row &r = S.index[lo];
-  for (int e = 0; e < 5; e++)
-    memcpy(entry[e],S.dtext.data() + r.text_off + (int64_t) e*(rlen + 1),(size_t) rlen);
-  fseeko(input,(off_t) (S.dpos0 - 2 + r.end_off),SEEK_SET);
-  return 0;
+  if (S.decoded)
+    { // which entry starts at the current file position
+      const int64_t img = (int64_t) ftello(input) - S.dpos0 + S.dkey;
+      size_t lo = 0, hi = S.index.size();
+      while (lo < hi) { const size_t mid = (lo + hi)/2; if (S.index[mid].stream_off < img) lo = mid + 1; else hi = mid; }
+      if (lo < S.index.size() && S.index[lo].stream_off == img && S.index[lo].rlen == rlen)
+        { const dx_index_row &r = S.index[lo];
+          for (int e = 0; e < 5; e++)
+            memcpy(entry[e],S.dtext.data() + r.text_off + (int64_t) e*(rlen + 1),(size_t) rlen);
+          fseeko(input,(off_t) (S.dpos0 - S.dkey + r.end_off),SEEK_SET);
+          return 0;
+        }
+    }
+  int rc = 1;
+  DXC_TRY { rc = one_entry(input,entry,coding,rlen); } DXC_CATCH(1)
+  return rc;
 }
 
 }  // extern "C"

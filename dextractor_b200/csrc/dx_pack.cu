@@ -132,12 +132,29 @@ k_fa_measure(int kind, const uint8_t *text, int64_t n, const int64_t *hdr, FaEnt
         }
       const int64_t W = (first_nl < 0) ? region : first_nl;        // first line length
       uint32_t nl_count = 0, off_lattice = 0;
+      int64_t last_nl = -1;                                         // region offset of the last newline so far
+      bool toolong = false;                                         // a line of more than kLineLimit characters
       for (int64_t c0 = 0; c0 < nchunk; c0 += 32)
         { const int64_t c = c0 + lane;
+          uint32_t m0 = 0;
           if (c < nchunk)
             { const int64_t p0 = c*16 - skew;
               const int lo = (int) max((int64_t) 0,-p0), hi = (int) min((int64_t) 16,region - p0);
-              uint32_t m = dx_eq_mask16(dx_ldg16(base + c*16),'\n') & dx_range16(lo,hi);
+              m0 = dx_eq_mask16(dx_ldg16(base + c*16),'\n') & dx_range16(lo,hi);
+            }
+          // dexta.c:168-172: no line may have more than MAX_BUFFER-2 characters.  Inside a round of
+          // 512 bytes no gap can; what can is the gap back to the last newline of an earlier round.
+          { const uint32_t any = __ballot_sync(DX_FULL,m0 != 0);
+            if (any)
+              { const int f = __ffs(any) - 1, l = 31 - __clz(any);
+                const int64_t first = (c0 + f)*16 - skew + (__ffs(__shfl_sync(DX_FULL,m0,f)) - 1);
+                if (first - last_nl - 1 > kLineLimit) toolong = true;
+                last_nl = (c0 + l)*16 - skew + (31 - __clz(__shfl_sync(DX_FULL,m0,l)));
+              }
+          }
+          if (c < nchunk)
+            { const int64_t p0 = c*16 - skew;
+              uint32_t m = m0;
               nl_count += __popc(m);
               while (m)
                 { const int i = __ffs(m) - 1; m &= m - 1;
@@ -150,7 +167,7 @@ k_fa_measure(int kind, const uint8_t *text, int64_t n, const int64_t *hdr, FaEnt
       off_lattice = dx_warp_sum(off_lattice);
       if (region > 0 && text[stop-1] != '\n') flag |= 4;            // last line unterminated
       if (off_lattice) flag |= 2;
-      if (W > kLineLimit) flag |= 4;
+      if (W > kLineLimit || toolong || region - last_nl - 1 > kLineLimit) flag |= 4;
       const int64_t rlen = region - nl_count;
       if (rlen >= (int64_t) 1 << 30) flag |= 4;
       // regular = every line but the last has exactly W symbols and the last has 1..W

@@ -202,6 +202,8 @@ k_fa_pack2(Pack2Args a)
       LineWalk lw; lw.set(seq,(int32_t) a.ent.region[e]);
       WarpBits wb; wb.init(stage,pay,kP2Stage);
       bool bad = false;
+      int32_t last_nl = -1;                                          // region offset of the last newline
+      bool toolong = false;                                          // a line of more than kLineLimit characters
       uint4 nxt = (lane < lw.nchunk) ? dx_ldg16(lw.base + (int64_t) lane*16) : make_uint4(0,0,0,0);
 #pragma unroll 1
       for (int32_t c0 = 0; c0 < lw.nchunk; c0 += 32)
@@ -211,6 +213,19 @@ k_fa_pack2(Pack2Args a)
           const uint32_t valid = lw.valid(c);
           uint32_t nl = 0;
           if (valid && any_newline(v)) nl = dx_eq_mask16(v,'\n') & valid;
+          // dexta.c:168-172: every line the reference reads has at most MAX_BUFFER-2 characters.  Gaps
+          // inside a round are shorter than 512; what can be too long is the gap to the last newline
+          // of an earlier round.
+          { const uint32_t any = __ballot_sync(DX_FULL,nl != 0);
+            if (any)
+              { const int f = __ffs(any) - 1, l = 31 - __clz(any);
+                const int32_t mine_first = c*16 - lw.skew + (__ffs(nl) - 1);
+                const int32_t mine_last  = c*16 - lw.skew + (31 - __clz(nl));
+                const int32_t first = __shfl_sync(DX_FULL,mine_first,f);
+                if (first - last_nl - 1 > kLineLimit) toolong = true;
+                last_nl = __shfl_sync(DX_FULL,mine_last,l);
+              }
+          }
           const uint32_t keep = valid & ~nl;
           const uint32_t cnt = __popc(keep);
           const uint32_t x = (codes4<KIND>(v.x) << 24) | (codes4<KIND>(v.y) << 16) |
@@ -248,8 +263,10 @@ k_fa_pack2(Pack2Args a)
         }
       __syncwarp();
       const uint32_t kept = wb.total() >> 1;
-      if (bad || kept != (uint32_t) rlen)
-        { if (lane == 0) atomicExch(a.err,1); }                     // the measured count was wrong: redo
+      if (toolong || (int32_t) a.ent.region[e] - last_nl - 1 > kLineLimit)
+        { if (lane == 0) atomicMax(a.err,2); }                      // a line the reference refuses
+      else if (bad || kept != (uint32_t) rlen)
+        { if (lane == 0) atomicMax(a.err,1); }                      // the measured count was wrong: redo
       else
         { if (lane == 0 && wb.cbits) stage[wb.nst] = wb.carry;
           __syncwarp();

@@ -26,7 +26,7 @@ SYMBOLS = [
     "dx_qv_scan_dev", "dx_qv_make_coding", "dx_qv_write_coding", "dx_qv_read_coding",
     "dx_qv_encode_dev", "dx_dexqv_dev", "dx_dexqv_host", "dx_undexqv_dev", "dx_undexqv_host",
     "dx_undexqv_size_dev", "dx_keep_index", "dx_last_index", "dx_qv_forget", "dx_qv_last_well",
-    "dx_text_lines_dev",
+    "dx_text_lines_dev", "dx_qv_load_entries_dev",
 ]
 
 
@@ -133,6 +133,7 @@ def load_library():
         "dx_undexqv_size_dev": (C.c_int, [vp, vp, sz, szp]),
         "dx_keep_index": (C.c_int, [vp, C.c_int]),
         "dx_qv_forget": (C.c_int, [vp]),
+        "dx_qv_load_entries_dev": (C.c_int, [vp, vp, sz, C.POINTER(Coding), vp, vp, i64, C.c_int, vp, sz, vp, vp]),
         "dx_qv_last_well": (C.c_int, [vp, C.POINTER(i32)]),
         "dx_text_lines_dev": (C.c_int, [vp, vp, sz, i64, C.POINTER(i64), C.POINTER(i64)]),
         "dx_last_index": (C.c_int, [vp, vp, i64, C.POINTER(i64)]),
@@ -348,6 +349,18 @@ class Context:
             self._check(self.L.dx_undexqv_dev(self.h, d_in, n, int(upper), d_out, cap, C.byref(m),
                                               None, 0, well_in))
         return m.value
+
+    def qv_load_entries_dev(self, d_in, n, coding: Coding, stream_off, rlen, upper, d_out, cap):
+        """-> (out offsets [nentries+1], end offsets [nentries])"""
+        _wait_for_torch()
+        so = np.ascontiguousarray(stream_off, dtype=np.int64)
+        rl = np.ascontiguousarray(rlen, dtype=np.int32)
+        oo = np.zeros(len(so) + 1, dtype=np.int64)
+        eo = np.zeros(len(so), dtype=np.int64)
+        self._check(self.L.dx_qv_load_entries_dev(self.h, d_in, n, C.byref(coding), so.ctypes.data,
+                                                  rl.ctypes.data, len(so), int(upper), d_out, cap,
+                                                  oo.ctypes.data, eo.ctypes.data))
+        return oo, eo
 
     def qv_forget(self):
         self._check(self.L.dx_qv_forget(self.h))

@@ -226,6 +226,17 @@ int dx_undexqv_host(dx_ctx *ctx, const uint8_t *h_in, size_t n, int upper,
 /* size of the .quiva text dx_undexqv_* would produce for this file */
 int dx_undexqv_size_dev(dx_ctx *ctx, const uint8_t *d_in, size_t n, size_t *out_len);
 
+/* Batched Load_QVentry (DB.c:2575-2621, and Load_All... style loaders built on it): the caller knows
+ * where every entry's streams start (DAZZ_READ.coff of a Dazzler .qvs, which stores bare streams;
+ * or the byte behind beg/end/qv of a .dexqv entry) and how long it is.  Entry i's five lines (del,
+ * tag, ins, mrg, sub), each followed by '\n', go to d_out[off[i] ...), off = exclusive prefix sum of
+ * 5*(rlen+1), returned in h_out_off[0..nentries] if not NULL; h_end_off[i], if not NULL, receives the
+ * first image byte behind entry i (the file position Uncompress_Next_QVentry leaves, QV.c:1428-1481). */
+int dx_qv_load_entries_dev(dx_ctx *ctx, const uint8_t *d_in, size_t n, const dx_qv_coding *coding,
+                           const int64_t *h_stream_off, const int32_t *h_rlen, int64_t nentries,
+                           int upper, uint8_t *d_out, size_t cap, int64_t *h_out_off,
+                           int64_t *h_end_off);
+
 /* Where the entries of the last dx_undexqv_dev call were: for callers that keep the reference's
  * per-entry view of a file (the QV.h shim, a Dazzler .idx writer: DAZZ_READ.coff, dex2DB.c:617-621).
  * Off by default; dx_keep_index(ctx,1) makes every following dx_undexqv_dev record one row per

@@ -116,6 +116,10 @@ def main():
     want = orc.ref_tool("undexqv", native)[0]
     manifest = {"input_sha256": sha(text), "decoded_sha256": sha(want), "decoded_len": len(want),
                 "decoded_equals_input": want == text, "files": {}}
+    # (seeded numpy draws are not bit-reproducible across CPUs -- SIMD log/exp -- so the native file is
+    #  stored too: the expected text of every variant is what the oracle decodes from it)
+    with open(os.path.join(HERE, "legacy_native.dexqv"), "wb") as f:
+        f.write(native)
     manifest["native_sha256"] = sha(native)
     for flip, old in ((True, False), (False, True), (True, True)):
         b = build(text, flip, old)

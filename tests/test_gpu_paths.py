@@ -320,3 +320,27 @@ def test_lane_decoder_on_a_truncated_image_fails_cleanly(routed, orc):
     for cut in (len(enc) - 1, len(enc) - 40, len(enc) // 2):
         with pytest.raises(dx.DexError):
             ctx.undexqv(enc[:cut])
+
+
+def test_fasta_line_too_long_after_the_first_line(ctx, orc):
+    """dexta.c:168-172 refuses any line of more than MAX_BUFFER-2 = 99998 characters, not only the
+    first one of an entry; a line of exactly 99998 is fine."""
+    rng = np.random.default_rng(3)
+    acgt = np.frombuffer(b"acgt", dtype=np.uint8)
+
+    def seq(n):
+        return acgt[rng.integers(0, 4, size=n)].tobytes()
+
+    def text(long_len):
+        return (b">mv/1/0_100 RQ=0.851\n" + seq(60) + b"\n" + seq(40) + b"\n" +
+                b">mv/5/0_%d RQ=0.800\n" % (70 + long_len + 10) + seq(70) + b"\n" + seq(long_len) + b"\n" +
+                seq(10) + b"\n" + b">mv/9/0_80 RQ=0.700\n" + seq(80) + b"\n")
+
+    ok = text(99998)
+    assert ctx.dexta(ok) == orc.dexta(ok)
+    with pytest.raises(dx.DexError) as e:
+        ctx.dexta(text(99999))
+    assert e.value.code == -6                            # DX_E_TOOLONG
+    with pytest.raises(orc.OracleError) as e2:
+        orc.dexta(text(99999))
+    assert e2.value.code == -6
