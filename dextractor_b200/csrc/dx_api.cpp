@@ -236,6 +236,9 @@ extern "C" void dx_close(dx_ctx *ctx)
       for (cudaEvent_t e : ((DxProf *) ctx->prof)->pool) cudaEventDestroy(e);
       delete (DxProf *) ctx->prof;
     }
+  for (int i = 0; i < ctx->npev; i++) cudaEventDestroy(ctx->pev[i]);
+  if (ctx->cs_in)  cudaStreamDestroy(ctx->cs_in);
+  if (ctx->cs_out) cudaStreamDestroy(ctx->cs_out);
   cudaStreamDestroy(ctx->stream);
   free(ctx);
 }
@@ -247,7 +250,7 @@ extern "C" void       *dx_stream(dx_ctx *ctx) { return ctx ? (void *) ctx->strea
 extern "C" int dx_route(dx_ctx *ctx, const char *name, int64_t value)
 { static const char *names[DXR_COUNT] = { "no_fast", "no_spec", "exact_index", "exact_pack", "pack2", "two_pass",
                                           "chain_scan", "decoder", "lane_max_rlen", "lane_min_entries", "debug",
-                                          "serial_io" };
+                                          "serial_io", "pipe_chunk" };
   if (ctx == NULL || name == NULL) return DX_E_ARG;
   if (strcmp(name,"default") == 0)
     { const int64_t dbg = ctx->route[DXR_DEBUG];
@@ -2209,10 +2212,215 @@ extern "C" int dx_dexqv_host(dx_ctx *ctx, const uint8_t *h_text, size_t n, int l
   return stage_out(ctx,h_out,*out_len);
 }
 
+// ------------------------------------------------------------------------------------------------
+//  dx_undexqv_host as a pipeline: the image goes to the device in chunks (copy stream cs_in), every
+//  chunk is a WINDOW whose entries are found, decoded, verified and assembled as soon as it and its
+//  successor have arrived (an entry may run over the boundary), and a window's text leaves for the
+//  host (copy stream cs_out) while the next window is decoded: PCIe is busy in both directions and
+//  the kernels hide behind the copies.  Same kernels and the same chain rule as undexqv_fast; the
+//  chain just carries its position, well number and text offset from window to window.  Anything
+//  unusual (legacy layout, a missed entry, tables that do not fit) -> *handled = false after the
+//  copies have drained, and the caller runs the plain path on the complete image.
+// ------------------------------------------------------------------------------------------------
+static int pipe_setup(dx_ctx *ctx, int nev)
+{ if (ctx->cs_in == NULL)  DX_CUDA(ctx,cudaStreamCreateWithFlags(&ctx->cs_in,cudaStreamNonBlocking));
+  if (ctx->cs_out == NULL) DX_CUDA(ctx,cudaStreamCreateWithFlags(&ctx->cs_out,cudaStreamNonBlocking));
+  while (ctx->npev < nev)
+    { DX_CUDA(ctx,cudaEventCreateWithFlags(&ctx->pev[ctx->npev],cudaEventDisableTiming));
+      ctx->npev++;
+    }
+  return DX_OK;
+}
+
+static int undexqv_pipe(dx_ctx *ctx, const uint8_t *h_in, size_t n, int upper, uint8_t *h_out, size_t cap,
+                        size_t *out_len, bool *handled)
+{ int rc;
+  *handled = false;
+  const size_t kMinChunk = ctx->route[DXR_PIPE_CHUNK] > 0 ? (size_t) ctx->route[DXR_PIPE_CHUNK] : (size_t) 32 << 20;
+  if (n < 2*kMinChunk || kMinChunk < 16384 || ctx->route[DXR_SERIAL_IO] || ctx->route[DXR_DECODER] == 1 || ctx->route[DXR_NO_SPEC] ||
+      ctx->route[DXR_NO_FAST] || ctx->keep_index) return DX_OK;
+  uint16_t key; memcpy(&key,h_in,2);
+  if (key != 0x55aa) return DX_OK;
+  dx_qv_coding coding;
+  std::vector<char> prefix(100001);
+  size_t used = 0;
+  if (dx_qv_read_coding(h_in+2,n-2 < 300000 ? n-2 : 300000,&coding,prefix.data(),(int) prefix.size(),&used) != DX_OK ||
+      coding.flip) return DX_OK;
+  const size_t first = 2 + used;
+  const int plen = (int) strlen(prefix.data());
+  // every window's decode launch lasts about as long as its longest entry (~2 ms with 60 000-position
+  // entries), whatever else it holds: windows must stay large enough for the launch to hide behind the
+  // text copy of the window before it
+  int K = (int) (n / kMinChunk);
+  if (K > 10) K = 10;                                     // measured on 2 GB: 4 windows 47 ms, 8-12 windows 42-44 ms, 16 45 ms, serial 54 ms
+  const size_t chunk = round_up((n + (size_t) K - 1) / (size_t) K,(size_t) 4096);
+  K = (int) ((n + chunk - 1) / chunk);
+  cudaSetDevice(ctx->device);
+  if ((rc = pipe_setup(ctx,2*K + 2)) != DX_OK) return rc;
+  if ((rc = ensure_io(ctx,&ctx->io_in,&ctx->io_in_cap,n)) != DX_OK) return rc;
+  if ((rc = ensure_io(ctx,&ctx->io_out,&ctx->io_out_cap,cap)) != DX_OK) return rc;
+  dx_arena_reset(ctx);
+  const uint8_t *d_in = ctx->io_in;
+  uint8_t *d_out = ctx->io_out;
+  // all chunks on their way; event k = chunk k has arrived
+  for (int k = 0; k < K; k++)
+    { const size_t a = (size_t) k*chunk, b = (a + chunk < n) ? a + chunk : n;
+      DX_CUDA(ctx,cudaMemcpyAsync(ctx->io_in + a,h_in + a,b - a,cudaMemcpyHostToDevice,ctx->cs_in));
+      DX_CUDA(ctx,cudaEventRecord(ctx->pev[k],ctx->cs_in));
+    }
+  auto drain = [&]() { cudaStreamSynchronize(ctx->cs_in); cudaStreamSynchronize(ctx->cs_out);
+                       cudaStreamSynchronize(ctx->stream); };
+
+  QvDecTables4 *h4 = (QvDecTables4 *) dx_hpin_get(ctx,sizeof(QvDecTables4));
+  QvDecTables4 *d_tab4 = (QvDecTables4 *) dx_arena_get(ctx,sizeof(QvDecTables4));
+  char *d_prefix = (char *) dx_arena_get(ctx,(size_t) plen + 1);
+  char *h_prefix = (char *) dx_hpin_get(ctx,(size_t) plen + 1);
+  int32_t *d_flag = (int32_t *) dx_arena_get(ctx,16);
+  if (!h4 || !d_tab4 || !d_prefix || !h_prefix || !d_flag) { drain(); return DX_E_NOMEM; }
+  if (!build_dec_tables4(&coding,h4)) { drain(); return DX_OK; }
+  memcpy(h_prefix,prefix.data(),(size_t) plen + 1);
+  if ((rc = dxk_fetch(ctx,d_tab4,h4,sizeof(QvDecTables4))) != DX_OK) { drain(); return rc; }
+  if ((rc = dxk_fetch(ctx,d_prefix,h_prefix,(size_t) plen + 1)) != DX_OK) { drain(); return rc; }
+  DX_CUDA(ctx,cudaMemsetAsync(d_flag,0,16,ctx->stream));
+  int minbits = 0;
+  for (int k = 2; k <= 3; k++)
+    { int mn = 32;
+      for (int x = 0; x < 256; x++)
+        if (coding.tab[k].lens[x] > 0 && coding.tab[k].lens[x] < mn) mn = coding.tab[k].lens[x];
+      minbits += (mn == 32) ? 0 : mn;
+    }
+  struct Tail { int64_t total; int32_t flag; int32_t pad; };
+  Tail *h_tail = (Tail *) dx_hpin_get(ctx,sizeof(Tail));
+  if (h_tail == NULL) { drain(); return DX_E_NOMEM; }
+
+  int64_t cur = (int64_t) first;           // image offset of the next entry (chain position)
+  int32_t well = 0;
+  size_t  tbase = 0;                       // text bytes of the windows before this one
+  const size_t kBack = 4096;               // bytes before a window's first candidate the kernels may look at
+  for (int k = 0; k < K; k++)
+    { const size_t wa = (size_t) k*chunk, wb = (wa + chunk < n) ? wa + chunk : n;      // candidates of [wa, wb)
+      const size_t avail = ((size_t) (k + 2)*chunk < n) ? (size_t) (k + 2)*chunk : n;  // bytes on the device
+      DX_CUDA(ctx,cudaStreamWaitEvent(ctx->stream,ctx->pev[(k + 1 < K) ? k + 1 : k],0));
+      const size_t base = (k == 0) ? 0 : wa - kBack;                   // the window's own origin
+      const size_t wfirst = (k == 0) ? first : kBack;
+      const uint8_t *w_in = d_in + base;
+      const size_t w_n = avail - base;
+      const size_t scan_n = ((wb + 64 < avail) ? wb + 64 : avail) - base;
+      int64_t *d_q = NULL, nc = 0;
+      if ((rc = dxk_index_positions(ctx,DX_PRED_QVCAND,w_in,scan_n,wfirst + (k == 0 ? 1 : 0),&d_q,&nc)) != DX_OK)
+        { drain(); return rc; }
+      const size_t N = (size_t) nc;
+      if (N == 0)
+        { if (cur < (int64_t) wb) { drain(); return DX_OK; }          // entries here, but no candidate
+          continue;
+        }
+      QvPlanArrays pa;
+      pa.fs   = (int64_t *)  dx_arena_get(ctx,N*8);  pa.rlen = (int32_t *)  dx_arena_get(ctx,N*4);
+      pa.delta= (uint32_t *) dx_arena_get(ctx,N*4);  pa.beg  = (int32_t *)  dx_arena_get(ctx,N*4);
+      pa.end  = (int32_t *)  dx_arena_get(ctx,N*4);  pa.qv   = (int32_t *)  dx_arena_get(ctx,N*4);
+      uint32_t *d_tlen  = (uint32_t *) dx_arena_get(ctx,N*4);
+      int64_t  *d_limit = (int64_t *)  dx_arena_get(ctx,N*8);
+      int32_t  *d_ffrun = (int32_t *)  dx_arena_get(ctx,N*4);
+      uint8_t  *d_last  = (uint8_t *)  dx_arena_get(ctx,N);
+      int64_t  *d_toff  = (int64_t *)  dx_arena_get(ctx,(N+1)*8);
+      int64_t  *d_soff  = (int64_t *)  dx_arena_get(ctx,N*48);
+      int32_t  *d_stat  = (int32_t *)  dx_arena_get(ctx,N*4);
+      int32_t  *d_order = (int32_t *)  dx_arena_get(ctx,N*4);
+      int64_t *h_q     = (int64_t *) dx_hpin_get(ctx,N*8);
+      int32_t *h_ffrun = (int32_t *) dx_hpin_get(ctx,N*4);
+      uint8_t *h_last  = (uint8_t *) dx_hpin_get(ctx,N);
+      int32_t *h_rlen  = (int32_t *) dx_hpin_get(ctx,N*4);
+      int32_t *h_order = (int32_t *) dx_hpin_get(ctx,N*4);
+      int64_t *h_soff  = (int64_t *) dx_hpin_get(ctx,N*48);
+      int32_t *h_stat  = (int32_t *) dx_hpin_get(ctx,N*4);
+      int32_t *h_cand  = (int32_t *) dx_hpin_get(ctx,N*4);
+      int32_t *h_well  = (int32_t *) dx_hpin_get(ctx,N*4);
+      if (!pa.fs || !pa.rlen || !pa.delta || !pa.beg || !pa.end || !pa.qv || !d_tlen || !d_limit || !d_ffrun ||
+          !d_last || !d_toff || !d_soff || !d_stat || !d_order || !h_q || !h_ffrun || !h_last || !h_rlen ||
+          !h_order || !h_soff || !h_stat || !h_cand || !h_well) { drain(); return DX_E_NOMEM; }
+      if ((rc = dxk_qv_cand_prep(ctx,w_in,w_n,wfirst,d_q,nc,4,minbits,pa,d_tlen,d_limit,d_ffrun,d_last)) != DX_OK ||
+          (rc = dxk_scan_u32(ctx,d_tlen,nc,d_toff)) != DX_OK) { drain(); return rc; }
+      if ((rc = dxk_fetch(ctx,h_q,d_q,N*8)) != DX_OK) { drain(); return rc; }
+      if ((rc = dxk_fetch(ctx,h_ffrun,d_ffrun,N*4)) != DX_OK) { drain(); return rc; }
+      if ((rc = dxk_fetch(ctx,h_last,d_last,N)) != DX_OK) { drain(); return rc; }
+      if ((rc = dxk_fetch(ctx,h_rlen,pa.rlen,N*4)) != DX_OK) { drain(); return rc; }
+      if ((rc = dxk_fetch(ctx,&h_tail->total,d_toff+N,8)) != DX_OK) { drain(); return rc; }
+      DX_CUDA(ctx,cudaStreamSynchronize(ctx->stream));
+      const int64_t n_coop = ticket_plan(ctx,h_rlen,N,h_order);
+      if ((rc = dxk_fetch(ctx,d_order,h_order,N*4)) != DX_OK) { drain(); return rc; }
+      const size_t tmp_n = (size_t) h_tail->total;
+      uint8_t *d_tmp = (uint8_t *) dx_arena_get(ctx,tmp_n + 64);
+      if (d_tmp == NULL) { drain(); return DX_E_NOMEM; }
+      if ((rc = dxk_qv_decode6x(ctx,w_in,w_n,d_tab4,coding.delchar,coding.subchar,upper,2,nc,pa.fs,pa.rlen,NULL,NULL,0,
+                                d_tmp,d_soff,d_stat,d_limit,d_order,d_toff,n_coop)) != DX_OK) { drain(); return rc; }
+      if ((rc = dxk_fetch(ctx,h_soff,d_soff,N*48)) != DX_OK) { drain(); return rc; }
+      if ((rc = dxk_fetch(ctx,h_stat,d_stat,N*4)) != DX_OK) { drain(); return rc; }
+      DX_CUDA(ctx,cudaStreamSynchronize(ctx->stream));
+      // the chain (see resolve_chain), in window coordinates; it stops at the window's end
+      size_t M = 0;
+      { size_t i = 0;
+        const int64_t stop = (k + 1 < K) ? (int64_t) (wb - base) : (int64_t) (n - base);
+        int64_t c = cur - (int64_t) base;
+        while (c < stop)
+          { while (i < N && h_q[i] - 1 < c) i++;
+            while (i < N && h_last[i] == 0xff && h_q[i] - 1 - c <= h_ffrun[i]) i++;
+            if (i >= N || h_stat[i] != 0) { drain(); return DX_OK; }
+            const int64_t gap = h_q[i] - 1 - c;
+            if (gap > h_ffrun[i] || h_last[i] == 0xff) { drain(); return DX_OK; }
+            const int64_t end = h_soff[6*i + 5];
+            if (end > (int64_t) w_n || end <= c) { drain(); return DX_OK; }
+            well += 255 * (int32_t) gap + h_last[i];
+            h_cand[M] = (int32_t) i; h_well[M] = well; M++;
+            c = end;
+            i++;
+          }
+        cur = c + (int64_t) base;
+      }
+      if (M == 0) continue;
+      int32_t *d_cand = (int32_t *) dx_arena_get(ctx,M*4 + 4);
+      int32_t *d_wells = (int32_t *) dx_arena_get(ctx,M*4 + 4);
+      int32_t *d_well = (int32_t *) dx_arena_get(ctx,M*4 + 4);
+      uint32_t *d_len = (uint32_t *) dx_arena_get(ctx,M*4 + 4);
+      int64_t *d_opre = (int64_t *) dx_arena_get(ctx,(M+1)*8);
+      int64_t *d_src  = (int64_t *) dx_arena_get(ctx,M*8 + 8);
+      QvDecEntry *d_ent = (QvDecEntry *) dx_arena_get(ctx,(M+1)*sizeof(QvDecEntry));
+      if (!d_cand || !d_wells || !d_well || !d_len || !d_opre || !d_src || !d_ent) { drain(); return DX_E_NOMEM; }
+      if ((rc = dxk_fetch(ctx,d_cand,h_cand,M*4)) != DX_OK) { drain(); return rc; }
+      if ((rc = dxk_fetch(ctx,d_wells,h_well,M*4)) != DX_OK) { drain(); return rc; }
+      if ((rc = dxk_qv_text_len(ctx,(int64_t) M,d_cand,pa,NULL,d_wells,0,plen,d_len,d_well,d_flag)) != DX_OK ||
+          (rc = dxk_scan_u32(ctx,d_len,(int64_t) M,d_opre)) != DX_OK ||
+          (rc = dxk_qv_build_ent(ctx,(int64_t) M,d_cand,pa,d_well,d_opre,d_len,d_toff,d_ent,d_src,NULL,NULL)) != DX_OK)
+        { drain(); return rc; }
+      if ((rc = dxk_fetch(ctx,&h_tail->total,d_opre+M,8)) != DX_OK) { drain(); return rc; }
+      if ((rc = dxk_fetch(ctx,&h_tail->flag,d_flag,4)) != DX_OK) { drain(); return rc; }
+      DX_CUDA(ctx,cudaStreamSynchronize(ctx->stream));
+      if (h_tail->flag) { drain(); return dx_fail(ctx,DX_E_FORMAT,"unusable read length in an entry header"); }
+      const size_t wtext = (size_t) h_tail->total;
+      if (tbase + wtext > cap)
+        { drain(); return dx_fail(ctx,DX_E_CAP,"output needs more than %zu bytes",cap); }
+      if ((rc = dxk_qv_assemble(ctx,d_tmp,tmp_n,d_ent,d_src,(int64_t) M,d_prefix,plen,d_out + tbase)) != DX_OK)
+        { drain(); return rc; }
+      // this window's text leaves while the next window is decoded
+      DX_CUDA(ctx,cudaEventRecord(ctx->pev[K + k],ctx->stream));
+      DX_CUDA(ctx,cudaStreamWaitEvent(ctx->cs_out,ctx->pev[K + k],0));
+      DX_CUDA(ctx,cudaMemcpyAsync(h_out + tbase,d_out + tbase,wtext,cudaMemcpyDeviceToHost,ctx->cs_out));
+      tbase += wtext;
+    }
+  drain();
+  if (cur != (int64_t) n) return DX_OK;                              // (the plain path reports what is wrong)
+  *out_len = tbase;
+  *handled = true;
+  return DX_OK;
+}
+
 extern "C" int dx_undexqv_host(dx_ctx *ctx, const uint8_t *h_in, size_t n, int upper,
                                uint8_t *h_out, size_t cap, size_t *out_len)
 { if (ctx == NULL || h_in == NULL || h_out == NULL || out_len == NULL) return DX_E_ARG;
   int rc;
+  { bool handled = false;
+    if ((rc = undexqv_pipe(ctx,h_in,n,upper,h_out,cap,out_len,&handled)) != DX_OK) return rc;
+    if (handled) return DX_OK;
+  }
   if ((rc = stage_in(ctx,h_in,n)) != DX_OK) return rc;
   if ((rc = ensure_io(ctx,&ctx->io_out,&ctx->io_out_cap,cap)) != DX_OK) return rc;
   if ((rc = dx_undexqv_dev(ctx,ctx->io_in,n,upper,ctx->io_out,cap,out_len,NULL,0,0)) != DX_OK) return rc;

@@ -367,6 +367,37 @@ __global__ void k_qv_entries(const uint8_t *text, const int64_t *nl, int64_t nen
   if (!ok) atomicAdd(err+2,1ull);
 }
 
+}  // namespace
+
+// Small results for the host WITHOUT the copy engine: a kernel stores them into pinned host memory
+// (device-accessible under UVA).  A cudaMemcpy D2H of a few bytes queues on the device-to-host copy
+// engine BEHIND whatever large copy is in flight there -- in the pipelined dx_undexqv_host that
+// serialised every window's planning with the text copy of the window before it.
+__global__ void k_fetch(uint8_t *dst, const uint8_t *src, size_t n)
+{ const size_t i0 = (size_t) blockIdx.x * blockDim.x + threadIdx.x, step = (size_t) gridDim.x * blockDim.x;
+  if ((((uintptr_t) dst | (uintptr_t) src) & 15) == 0)
+    { const size_t nv = n >> 4;
+      for (size_t i = i0; i < nv; i += step)
+        reinterpret_cast<uint4 *>(dst)[i] = reinterpret_cast<const uint4 *>(src)[i];
+      for (size_t i = (nv << 4) + i0; i < n; i += step) dst[i] = src[i];
+    }
+  else
+    for (size_t i = i0; i < n; i += step) dst[i] = src[i];
+}
+
+int dxk_fetch(dx_ctx *ctx, void *h_pinned, const void *d_src, size_t bytes)
+{ if (bytes == 0) return DX_OK;
+  size_t blocks = (bytes/16 + 255) / 256;
+  if (blocks < 1) blocks = 1;
+  if (blocks > 1024) blocks = 1024;
+  k_fetch<<<(unsigned) blocks,256,0,ctx->stream>>>((uint8_t *) h_pinned,(const uint8_t *) d_src,bytes);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return dx_cuda_fail(ctx,e,"k_fetch");
+  return DX_OK;
+}
+
+namespace {
+
 template <int PRED>
 int index_positions_exact(dx_ctx *ctx, const uint8_t *buf, size_t n, size_t first,
                           int64_t **d_pos, int64_t *count)
@@ -472,10 +503,15 @@ int index_positions(dx_ctx *ctx, const uint8_t *buf, size_t n, size_t first,
   { const int rc = launch_scan(ctx,d_cnt,ntiles,d_pre,"k_tile_scan");
     if (rc != DX_OK) return rc;
   }
-  struct { int64_t total; int32_t over; int32_t pad; } h;
-  DX_CUDA(ctx,cudaMemcpyAsync(&h.total,d_pre+ntiles,8,cudaMemcpyDeviceToHost,ctx->stream));
-  DX_CUDA(ctx,cudaMemcpyAsync(&h.over,d_over,4,cudaMemcpyDeviceToHost,ctx->stream));
+  struct Res { int64_t total; int32_t over; int32_t pad; };
+  Res *hp = (Res *) dx_hpin_get(ctx,sizeof(Res));
+  if (hp == NULL) return DX_E_NOMEM;
+  { int rc;
+    if ((rc = dxk_fetch(ctx,&hp->total,d_pre+ntiles,8)) != DX_OK) return rc;
+    if ((rc = dxk_fetch(ctx,&hp->over,d_over,4)) != DX_OK) return rc;
+  }
   DX_CUDA(ctx,cudaStreamSynchronize(ctx->stream));
+  const Res h = *hp;
   if (h.over) return index_positions_exact<PRED>(ctx,buf,n,first,d_pos,count);
   *count = h.total;
   if (h.total == 0) return DX_OK;

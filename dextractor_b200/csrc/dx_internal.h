@@ -82,7 +82,9 @@ enum { DXR_NO_FAST = 0, DXR_NO_SPEC, DXR_EXACT_INDEX, DXR_EXACT_PACK, DXR_PACK2,
                                // 5 warp per entry only, 6 lane per entry only
        DXR_LANE_MAX_RLEN,      // > 0: entries longer than this go to the warp-per-entry kernel
        DXR_LANE_MIN_ENTRIES,   // > 0: fewer lane-sized entries than this -> warp per entry for all
-       DXR_DEBUG, DXR_SERIAL_IO, DXR_COUNT };
+       DXR_DEBUG, DXR_SERIAL_IO,
+       DXR_PIPE_CHUNK,         // > 0: window size of the pipelined *_host calls in bytes (tests: small files)
+       DXR_COUNT };
 
 struct dx_ctx
 { int          device;
@@ -101,6 +103,10 @@ struct dx_ctx
   // device staging for the *_host entry points (grown on demand, kept)
   uint8_t     *io_in;   size_t io_in_cap;
   uint8_t     *io_out;  size_t io_out_cap;
+  // copy streams and events of the pipelined *_host entry points (created on first use)
+  cudaStream_t cs_in, cs_out;
+  cudaEvent_t  pev[40];
+  int          npev;
 
   // per-kernel CUDA-event timing (dx_profile): (name, start, stop) per launch
   int          prof_on;
@@ -139,6 +145,9 @@ void dx_prof_end(dx_ctx *ctx, const char *what);
     if (e__ != cudaSuccess) return dx_cuda_fail(ctx, e__, what); } while (0)
 
 // ---- kernels' host launchers (defined in the .cu files) ---------------------------------------
+
+// dx_frame.cu : a few bytes device -> PINNED host memory by a kernel (not by the copy engine), async
+int dxk_fetch(dx_ctx *ctx, void *h_pinned, const void *d_src, size_t bytes);
 
 // dx_frame.cu : positions of bytes satisfying a predicate, in order
 enum { DX_PRED_NEWLINE = 0, DX_PRED_FASTA_HDR = 1, DX_PRED_QVCAND = 2, DX_PRED_ARCAND = 3 };

@@ -68,7 +68,8 @@ uint64_t dx_launch_count(dx_ctx *ctx, int reset);
  * route is 0 = the product's choice).  Names: "no_fast", "no_spec" (host-planned undex* paths),
  * "exact_index", "exact_pack", "pack2", "two_pass", "chain_scan", "decoder" (1 sequential kernels,
  * 5 warp-per-entry kernel only, 6 lane-per-entry kernel only), "lane_max_rlen", "lane_min_entries",
- * "serial_io" (the *_host calls copy, compute, copy without overlap), "debug"; "default" resets all.
+ * "serial_io" (the *_host calls copy, compute, copy without overlap), "pipe_chunk" (window bytes of
+ * the pipelined dx_undexqv_host, so that small files take it too), "debug"; "default" resets all.
  * No reference counterpart; nothing in the library reads the environment inside a call. */
 int dx_route(dx_ctx *ctx, const char *name, int64_t value);
 

@@ -344,3 +344,23 @@ def test_fasta_line_too_long_after_the_first_line(ctx, orc):
     with pytest.raises(orc.OracleError) as e2:
         orc.dexta(text(99999))
     assert e2.value.code == -6
+
+
+@pytest.mark.parametrize("chunk", [65536, 262144, 1 << 20])
+def test_pipelined_host_decode_on_small_windows(routed, orc, chunk):
+    """dx_undexqv_host as a pipeline of windows (chunked copies in, window-wise discovery / decode /
+    assemble, chunked copies out): forced onto a few-MB file by a small window size.  Entries run over
+    window boundaries; a window smaller than an entry sends the call to the plain path."""
+    ctx = routed
+    rng = np.random.default_rng(17)
+    lengths = [int(x) for x in synth.lengths_for_bytes(rng, 6_000_000, 5.0)] + [300, 61000, 5, 12000]
+    text = synth.make_quiva(17, lengths, max_well_delta=700)
+    enc = orc.dexqv(text)
+    want = orc.undexqv(enc)
+    ctx.route("pipe_chunk", chunk)
+    for upper in (False, True):
+        got = ctx.undexqv(enc, upper=upper, cap=len(want) + 4096)
+        exp = want if not upper else orc.undexqv(enc, upper=True)
+        assert got == exp, (upper, first_diff(got, exp))
+    ctx.route("serial_io", 1)
+    assert ctx.undexqv(enc, cap=len(want) + 4096) == want
