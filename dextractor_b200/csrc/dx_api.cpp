@@ -250,7 +250,7 @@ extern "C" void       *dx_stream(dx_ctx *ctx) { return ctx ? (void *) ctx->strea
 extern "C" int dx_route(dx_ctx *ctx, const char *name, int64_t value)
 { static const char *names[DXR_COUNT] = { "no_fast", "no_spec", "exact_index", "exact_pack", "pack2", "two_pass",
                                           "chain_scan", "decoder", "lane_max_rlen", "lane_min_entries", "debug",
-                                          "serial_io", "pipe_chunk" };
+                                          "serial_io", "pipe_chunk", "no_direct" };
   if (ctx == NULL || name == NULL) return DX_E_ARG;
   if (strcmp(name,"default") == 0)
     { const int64_t dbg = ctx->route[DXR_DEBUG];
@@ -1907,6 +1907,22 @@ static int undexqv_fast(dx_ctx *ctx, const uint8_t *d_in, size_t n, int upper, u
     return DX_E_NOMEM;
   if ((rc = dxk_qv_cand_prep(ctx,d_in,n,first,d_q,nc,4,minbits,pa,d_tlen,d_limit,d_ffrun,d_last)) != DX_OK) return rc;
   if ((rc = dxk_scan_u32(ctx,d_tlen,nc,d_toff)) != DX_OK) return rc;
+  // The layout of the text IF every candidate is an entry and follows its predecessor directly (true of
+  // nearly every file: a false candidate needs 13 bytes of stream data that look like an entry header):
+  // wells and text offsets are then prefix sums over the candidates, and the decoder can write headers
+  // and lines straight into place.  The chain below still decides; when it disagrees the lines are
+  // decoded again into a scratch image and moved (k_qv_assemble), as if nothing had been assumed.
+  int64_t *d_wpre = (int64_t *) dx_arena_get(ctx,(N+1)*8);
+  int64_t *d_opre = (int64_t *) dx_arena_get(ctx,(N+1)*8);
+  uint32_t *d_len = (uint32_t *) dx_arena_get(ctx,N*4 + 4);
+  int32_t *d_well = (int32_t *) dx_arena_get(ctx,N*4 + 4);
+  QvDecEntry *d_ent = (QvDecEntry *) dx_arena_get(ctx,(N+1)*sizeof(QvDecEntry));
+  int32_t *d_flag2 = d_flag + 2;                        // unusable length in some candidate
+  if (!d_wpre || !d_opre || !d_len || !d_well || !d_ent) return DX_E_NOMEM;
+  if ((rc = dxk_scan_u32(ctx,pa.delta,nc,d_wpre)) != DX_OK) return rc;
+  if ((rc = dxk_qv_text_len(ctx,nc,NULL,pa,d_wpre,NULL,well_in,plen,d_len,d_well,d_flag2)) != DX_OK) return rc;
+  if ((rc = dxk_scan_u32(ctx,d_len,nc,d_opre)) != DX_OK) return rc;
+  if ((rc = dxk_qv_build_ent(ctx,nc,NULL,pa,d_well,d_opre,d_len,NULL,d_ent,NULL,NULL,NULL)) != DX_OK) return rc;
   int64_t *h_q     = (int64_t *) dx_hpin_get(ctx,N*8);
   int32_t *h_ffrun = (int32_t *) dx_hpin_get(ctx,N*4);
   uint8_t *h_last  = (uint8_t *) dx_hpin_get(ctx,N);
@@ -1916,21 +1932,37 @@ static int undexqv_fast(dx_ctx *ctx, const uint8_t *d_in, size_t n, int upper, u
   int32_t *h_stat  = (int32_t *) dx_hpin_get(ctx,N*4);
   int32_t *h_cand  = (int32_t *) dx_hpin_get(ctx,N*4);
   int32_t *h_well  = (int32_t *) dx_hpin_get(ctx,N*4);
-  if (!h_q || !h_ffrun || !h_last || !h_rlen || !h_order || !h_soff || !h_stat || !h_cand || !h_well) return DX_E_NOMEM;
+  int64_t *h_tot   = (int64_t *) dx_hpin_get(ctx,16);
+  if (!h_q || !h_ffrun || !h_last || !h_rlen || !h_order || !h_soff || !h_stat || !h_cand || !h_well || !h_tot)
+    return DX_E_NOMEM;
   DX_CUDA(ctx,cudaMemcpyAsync(h_q,d_q,N*8,cudaMemcpyDeviceToHost,ctx->stream));
   DX_CUDA(ctx,cudaMemcpyAsync(h_ffrun,d_ffrun,N*4,cudaMemcpyDeviceToHost,ctx->stream));
   DX_CUDA(ctx,cudaMemcpyAsync(h_last,d_last,N,cudaMemcpyDeviceToHost,ctx->stream));
   DX_CUDA(ctx,cudaMemcpyAsync(h_rlen,pa.rlen,N*4,cudaMemcpyDeviceToHost,ctx->stream));
   DX_CUDA(ctx,cudaMemcpyAsync(&h_tail->total,d_toff+N,8,cudaMemcpyDeviceToHost,ctx->stream));
+  DX_CUDA(ctx,cudaMemcpyAsync(h_tot,d_opre+N,8,cudaMemcpyDeviceToHost,ctx->stream));
+  DX_CUDA(ctx,cudaMemcpyAsync(&h_tail->flag,d_flag2,4,cudaMemcpyDeviceToHost,ctx->stream));
   DX_CUDA(ctx,cudaStreamSynchronize(ctx->stream));
   ph.mark("prep");
   const int64_t n_coop = ticket_plan(ctx,h_rlen,N,h_order);
   DX_CUDA(ctx,cudaMemcpyAsync(d_order,h_order,N*4,cudaMemcpyHostToDevice,ctx->stream));
   const size_t tmp_n = (size_t) h_tail->total;
-  uint8_t *d_tmp = (uint8_t *) dx_arena_get(ctx,tmp_n + 64);
-  if (d_tmp == NULL) return DX_E_NOMEM;
-  if ((rc = dxk_qv_decode6x(ctx,d_in,n,d_tab4,coding.delchar,coding.subchar,upper,2,nc,pa.fs,pa.rlen,NULL,NULL,0,
-                            d_tmp,d_soff,d_stat,d_limit,d_order,d_toff,n_coop)) != DX_OK) return rc;
+  const int64_t direct_total = h_tot[0];
+  bool direct = !ctx->route[DXR_NO_DIRECT] && n_coop == (int64_t) N && h_tail->flag == 0 &&
+                direct_total >= 0 && (size_t) direct_total <= cap;
+  uint8_t *d_tmp = NULL;
+  auto spec_decode = [&]() -> int
+    { d_tmp = (uint8_t *) dx_arena_get(ctx,tmp_n + 64);
+      if (d_tmp == NULL) return DX_E_NOMEM;
+      return dxk_qv_decode6x(ctx,d_in,n,d_tab4,coding.delchar,coding.subchar,upper,2,nc,pa.fs,pa.rlen,NULL,NULL,0,
+                             d_tmp,d_soff,d_stat,d_limit,d_order,d_toff,n_coop);
+    };
+  if (direct)
+    rc = dxk_qv_decode6x(ctx,d_in,n,d_tab4,coding.delchar,coding.subchar,upper,3,nc,pa.fs,pa.rlen,d_ent,d_prefix,plen,
+                         d_out,d_soff,d_stat,d_limit,d_order,NULL,n_coop);
+  else
+    rc = spec_decode();
+  if (rc != DX_OK) return rc;
   DX_CUDA(ctx,cudaMemcpyAsync(h_soff,d_soff,N*48,cudaMemcpyDeviceToHost,ctx->stream));
   DX_CUDA(ctx,cudaMemcpyAsync(h_stat,d_stat,N*4,cudaMemcpyDeviceToHost,ctx->stream));
   DX_CUDA(ctx,cudaStreamSynchronize(ctx->stream));
@@ -1939,6 +1971,7 @@ static int undexqv_fast(dx_ctx *ctx, const uint8_t *d_in, size_t n, int upper, u
   // the chain (see resolve_chain): a candidate is the next entry iff the bytes between the end of
   // the previous entry and its fields are 0xff ... 0xff, d with d != 0xff
   size_t M = 0;
+  bool as_assumed = true;                 // every candidate an entry, every delta the one cand_prep assumed
   { int64_t cur = (int64_t) first;
     int32_t well = well_in;
     size_t i = 0;
@@ -1950,37 +1983,47 @@ static int undexqv_fast(dx_ctx *ctx, const uint8_t *d_in, size_t n, int upper, u
         if (gap > h_ffrun[i] || h_last[i] == 0xff) return DX_OK;
         const int64_t end = h_soff[6*i + 5];
         if (end > (int64_t) n || end <= cur) return DX_OK;
+        if (i != M || gap != h_ffrun[i]) as_assumed = false;
         well += 255 * (int32_t) gap + h_last[i];
         h_cand[M] = (int32_t) i; h_well[M] = well; M++;
         cur = end;
         i++;
       }
+    if (M != N) as_assumed = false;
   }
   ph.mark("chain");
-  int32_t *d_cand = (int32_t *) dx_arena_get(ctx,M*4 + 4);
-  int32_t *d_wells = (int32_t *) dx_arena_get(ctx,M*4 + 4);
-  int32_t *d_well = (int32_t *) dx_arena_get(ctx,M*4 + 4);
-  uint32_t *d_len = (uint32_t *) dx_arena_get(ctx,M*4 + 4);
-  int64_t *d_opre = (int64_t *) dx_arena_get(ctx,(M+1)*8);
-  int64_t *d_src  = (int64_t *) dx_arena_get(ctx,M*8 + 8);
-  QvDecEntry *d_ent = (QvDecEntry *) dx_arena_get(ctx,(M+1)*sizeof(QvDecEntry));
-  if (!d_cand || !d_wells || !d_well || !d_len || !d_opre || !d_src || !d_ent) return DX_E_NOMEM;
-  if (M > 0)
-    { DX_CUDA(ctx,cudaMemcpyAsync(d_cand,h_cand,M*4,cudaMemcpyHostToDevice,ctx->stream));
-      DX_CUDA(ctx,cudaMemcpyAsync(d_wells,h_well,M*4,cudaMemcpyHostToDevice,ctx->stream));
+  if (direct && as_assumed)
+    h_tail->total = direct_total;
+  else
+    { if (direct)
+        { // the assumption did not hold: the same candidates once more, lines only, into the scratch image
+          // (soff / status do not depend on where the text goes)
+          if (ctx->route[DXR_DEBUG])
+            fprintf(stderr,"[dexb200 debug] undexqv: %zu candidates, %zu entries: not as assumed, decoding again\n",N,M);
+          if ((rc = spec_decode()) != DX_OK) return rc;
+          direct = false;
+        }
+      int32_t *d_cand = (int32_t *) dx_arena_get(ctx,M*4 + 4);
+      int32_t *d_wells = (int32_t *) dx_arena_get(ctx,M*4 + 4);
+      int64_t *d_src  = (int64_t *) dx_arena_get(ctx,M*8 + 8);
+      if (!d_cand || !d_wells || !d_src) return DX_E_NOMEM;
+      if (M > 0)
+        { DX_CUDA(ctx,cudaMemcpyAsync(d_cand,h_cand,M*4,cudaMemcpyHostToDevice,ctx->stream));
+          DX_CUDA(ctx,cudaMemcpyAsync(d_wells,h_well,M*4,cudaMemcpyHostToDevice,ctx->stream));
+        }
+      if ((rc = dxk_qv_text_len(ctx,(int64_t) M,d_cand,pa,NULL,d_wells,0,plen,d_len,d_well,d_flag)) != DX_OK) return rc;
+      if ((rc = dxk_scan_u32(ctx,d_len,(int64_t) M,d_opre)) != DX_OK) return rc;
+      if ((rc = dxk_qv_build_ent(ctx,(int64_t) M,d_cand,pa,d_well,d_opre,d_len,d_toff,d_ent,d_src,NULL,NULL)) != DX_OK) return rc;
+      DX_CUDA(ctx,cudaMemcpyAsync(&h_tail->total,d_opre+M,8,cudaMemcpyDeviceToHost,ctx->stream));
+      DX_CUDA(ctx,cudaMemcpyAsync(&h_tail->flag,d_flag,4,cudaMemcpyDeviceToHost,ctx->stream));
+      DX_CUDA(ctx,cudaStreamSynchronize(ctx->stream));
+      if (h_tail->flag) return dx_fail(ctx,DX_E_FORMAT,"unusable read length in an entry header");
+      if ((size_t) h_tail->total > cap)
+        return dx_fail(ctx,DX_E_CAP,"output needs %lld bytes, buffer has %zu",(long long) h_tail->total,cap);
+      if ((rc = dxk_qv_assemble(ctx,d_tmp,tmp_n,d_ent,d_src,(int64_t) M,d_prefix,plen,d_out)) != DX_OK) return rc;
+      DX_CUDA(ctx,cudaStreamSynchronize(ctx->stream));
+      ph.mark("assemble");
     }
-  if ((rc = dxk_qv_text_len(ctx,(int64_t) M,d_cand,pa,NULL,d_wells,0,plen,d_len,d_well,d_flag)) != DX_OK) return rc;
-  if ((rc = dxk_scan_u32(ctx,d_len,(int64_t) M,d_opre)) != DX_OK) return rc;
-  if ((rc = dxk_qv_build_ent(ctx,(int64_t) M,d_cand,pa,d_well,d_opre,d_len,d_toff,d_ent,d_src,NULL,NULL)) != DX_OK) return rc;
-  DX_CUDA(ctx,cudaMemcpyAsync(&h_tail->total,d_opre+M,8,cudaMemcpyDeviceToHost,ctx->stream));
-  DX_CUDA(ctx,cudaMemcpyAsync(&h_tail->flag,d_flag,4,cudaMemcpyDeviceToHost,ctx->stream));
-  DX_CUDA(ctx,cudaStreamSynchronize(ctx->stream));
-  if (h_tail->flag) return dx_fail(ctx,DX_E_FORMAT,"unusable read length in an entry header");
-  if ((size_t) h_tail->total > cap)
-    return dx_fail(ctx,DX_E_CAP,"output needs %lld bytes, buffer has %zu",(long long) h_tail->total,cap);
-  if ((rc = dxk_qv_assemble(ctx,d_tmp,tmp_n,d_ent,d_src,(int64_t) M,d_prefix,plen,d_out)) != DX_OK) return rc;
-  DX_CUDA(ctx,cudaStreamSynchronize(ctx->stream));
-  ph.mark("assemble");
   ph.report("undexqv (entries discovered)");
   if (ctx->keep_index)
     { std::vector<dx_index_row> &ix = *(std::vector<dx_index_row> *) ctx->last_index;

@@ -84,6 +84,7 @@ enum { DXR_NO_FAST = 0, DXR_NO_SPEC, DXR_EXACT_INDEX, DXR_EXACT_PACK, DXR_PACK2,
        DXR_LANE_MIN_ENTRIES,   // > 0: fewer lane-sized entries than this -> warp per entry for all
        DXR_DEBUG, DXR_SERIAL_IO,
        DXR_PIPE_CHUNK,         // > 0: window size of the pipelined *_host calls in bytes (tests: small files)
+       DXR_NO_DIRECT,          // discovered entries: always decode into the scratch image, then assemble
        DXR_COUNT };
 
 struct dx_ctx

@@ -52,7 +52,8 @@ struct Dec5Args
   int64_t        n;
   const QvDecTables4 *tab;
   int32_t        delchar, subchar, upper, write;   // write: 0 walk, 1 text + header, 2 lines only
-                                                   //        (speculative, per-entry status)
+                                                   //        (speculative, per-entry status), 3 text +
+                                                   //        header in place AND per-entry status
   int64_t        count;
   const int64_t *start;        // first stream byte of each entry (after beg/end/qv)
   const int32_t *rlen;
@@ -547,7 +548,7 @@ k_qv_decode5(Dec5Args a)
       else if (a.write)
         { const QvDecEntry en = a.ent[e];
           line = a.out + en.text_off;
-          if (lane == 0 && a.write == 1)
+          if (lane == 0 && (a.write & 1))
             { uint8_t *h = a.out + en.out_off;          // "%s/%d/%d_%d RQ=0.%d\n" (undexqv.c:182)
               int hl = 0;
               for (int k = 0; k < a.plen; k++) h[hl++] = (uint8_t) a.prefix[k];
@@ -707,6 +708,6 @@ int dxk_qv_decode5x(dx_ctx *ctx, const uint8_t *d_in, size_t n, const QvDecTable
   int64_t grid = (count + kWarps - 1) / kWarps;
   if (grid > ctx->sm_count) grid = ctx->sm_count;
   DX_PROF_BEGIN(ctx); k_qv_decode5<<<(unsigned) grid,kThreads,smem,ctx->stream>>>(a);
-  DX_LAUNCHED(ctx,write == 1 ? "k_qv_decode5" : write == 2 ? "k_qv_decode5_spec" : "k_qv_walk5");
+  DX_LAUNCHED(ctx,write == 1 ? "k_qv_decode5" : write >= 2 ? "k_qv_decode5_spec" : "k_qv_walk5");
   return DX_OK;
 }

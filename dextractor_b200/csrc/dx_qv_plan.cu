@@ -58,13 +58,16 @@ __global__ void k_qv_cand_prep(const uint8_t *in, int64_t n, int64_t first, cons
   tlen[i] = (uint32_t) (5*(rl + 1));
   // context
   const int64_t p = qi - 1;
-  if (p < first) { ffrun[i] = -1; last[i] = 0; }
+  if (p < first) { ffrun[i] = -1; last[i] = 0; pa.delta[i] = 0; }
   else
     { last[i] = in[p];
       int32_t r = 0;
       int64_t k = p - 1;
       while (k >= first && in[k] == 0xff && r < (1 << 20)) { r++; k--; }
       ffrun[i] = r;
+      // the well delta IF every candidate is an entry and no stream ends in a 0xff byte (the usual
+      // case: the text can then be decoded straight into place, see undexqv_fast)
+      pa.delta[i] = (uint32_t) (255*r) + in[p];
     }
   // limit: the fields of the span-th candidate after this one, counting only candidates at least
   // 64 bytes after the previously counted one

@@ -69,7 +69,9 @@ uint64_t dx_launch_count(dx_ctx *ctx, int reset);
  * "exact_index", "exact_pack", "pack2", "two_pass", "chain_scan", "decoder" (1 sequential kernels,
  * 5 warp-per-entry kernel only, 6 lane-per-entry kernel only), "lane_max_rlen", "lane_min_entries",
  * "serial_io" (the *_host calls copy, compute, copy without overlap), "pipe_chunk" (window bytes of
- * the pipelined dx_undexqv_host, so that small files take it too), "debug"; "default" resets all.
+ * the pipelined dx_undexqv_host, so that small files take it too), "no_direct" (dx_undexqv_dev with
+ * discovered entries decodes into a scratch image and moves the lines, instead of straight into
+ * place), "debug"; "default" resets all.
  * No reference counterpart; nothing in the library reads the environment inside a call. */
 int dx_route(dx_ctx *ctx, const char *name, int64_t value);
 

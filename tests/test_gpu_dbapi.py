@@ -196,6 +196,7 @@ def test_batched_load_of_a_qvs(libs, tmp_path):
             for k, v in route.items():
                 ctx.route(k, v)
             out.zero_()
+            torch.cuda.synchronize()    # torch fills on its own stream, the library runs on another
             oo, eo = ctx.qv_load_entries_dev(img.data_ptr(), len(data), cd, coff, lengths, False,
                                              out.data_ptr(), out.numel())
             text = out[: oo[-1]].cpu().numpy().tobytes()

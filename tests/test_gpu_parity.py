@@ -196,6 +196,7 @@ def test_batched_reads(ctx, orc):
     d_so, d_len = torch.from_numpy(src_off).cuda(), torch.from_numpy(lens).cuda()
     d_do = torch.from_numpy(dst_off).cuda()
     d_dst = torch.zeros(int(clen.sum()), dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()        # torch fills on its own stream, the library runs on another
     ctx.compress_reads_dev(dx.FASTA, d_src.data_ptr(), d_so.data_ptr(), d_len.data_ptr(),
                            len(lens), d_dst.data_ptr(), d_do.data_ptr())
     ctx.sync()
@@ -207,6 +208,7 @@ def test_batched_reads(ctx, orc):
         orc.lib().orc_compress_read(len(r), buf)
         assert packed[dst_off[i]: dst_off[i] + clen[i]] == buf.raw[: clen[i]], i
     d_back = torch.zeros(len(src), dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
     ctx.uncompress_reads_dev(dx.FASTA, False, d_dst.data_ptr(), d_do.data_ptr(), d_len.data_ptr(),
                              len(lens), d_back.data_ptr(), d_so.data_ptr())
     ctx.sync()

@@ -39,6 +39,7 @@ ROUTES = [
     {"decoder": 6},                                      # lane-per-entry decoder for every entry
     {"lane_max_rlen": 3000},                             # both parallel decoders in one call
     {"decoder": 6, "no_fast": 1},                        # lane-per-entry decoder behind the host-planned path
+    {"no_direct": 1},                                    # discovered entries via the scratch image + k_qv_assemble
 ]
 
 

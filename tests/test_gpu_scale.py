@@ -56,6 +56,7 @@ def test_quiva_1gb_against_the_reference_tools(ctx, orc):
     # the REFERENCE's image decoded on the GPU: entries discovered, then entries known
     img = torch.from_numpy(np.frombuffer(want, dtype=np.uint8).copy()).to(dev)
     back = torch.zeros(U + 4096, dtype=torch.uint8, device=dev)
+    torch.cuda.synchronize()            # torch fills on its own stream, the library runs on another
     m = ctx.undexqv_dev(img.data_ptr(), len(want), False, back.data_ptr(), back.numel())
     assert m == U and bool(torch.equal(back[:U], text_t)), "GPU undexqv (discovered) differs at 1 GB"
     ctx.keep_index(True)
@@ -70,6 +71,7 @@ def test_quiva_1gb_against_the_reference_tools(ctx, orc):
     for i, r in enumerate(rows):
         offs[i + 1] = r[1]
     back.zero_()
+    torch.cuda.synchronize()
     m = ctx.undexqv_dev(img.data_ptr(), len(want), False, back.data_ptr(), back.numel(), entry_off=offs)
     assert m == U and bool(torch.equal(back[:U], text_t)), "GPU undexqv (offsets known) differs at 1 GB"
     # and the reference's own decoder on the GPU's image gives the text back
@@ -94,6 +96,7 @@ def test_fasta_arrow_1gb_against_the_reference_tools(ctx, orc, arrow):
     ref_text = _ref(orc, dec_tool, want)                         # (arrow: SN= digits pass through a float)
     img = torch.from_numpy(np.frombuffer(want, dtype=np.uint8).copy()).to(dev)
     un = torch.zeros(U + 4096, dtype=torch.uint8, device=dev)
+    torch.cuda.synchronize()
     k = ctx.undexta_dev(kind, img.data_ptr(), len(want), 80, False, un.data_ptr(), un.numel())
     assert k == len(ref_text) and sha(un[:k].cpu().numpy().tobytes()) == sha(ref_text), \
         f"GPU {dec_tool} differs from the reference's at 1 GB"
@@ -123,9 +126,11 @@ def test_quiva_8gb_shard_round_trip(ctx):
     n = len(hdr) + body
     assert n > 2 ** 31 and offs[-1] == body
     back = torch.zeros(U + 4096, dtype=torch.uint8, device=dev)
+    torch.cuda.synchronize()            # torch fills on its own stream, the library runs on another
     m = ctx.undexqv_dev(enc.data_ptr(), n, False, back.data_ptr(), back.numel(), entry_off=offs + len(hdr))
     assert m == U and bool(torch.equal(back[:U], text_t)), "8 GB round trip (offsets known) differs"
     back.zero_()
+    torch.cuda.synchronize()
     m = ctx.undexqv_dev(enc.data_ptr(), n, False, back.data_ptr(), back.numel())
     assert m == U and bool(torch.equal(back[:U], text_t)), "8 GB round trip (offsets discovered) differs"
     # a checksum of the image that a sharded run must reproduce: first and last MB + length
