@@ -48,10 +48,16 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks during the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks during the timed region (B200_PROFILING.md recipe).  The process is started
+    BEFORE the warm-up steps: NVML initialisation takes ~50 ms of driver time during which kernel
+    launches stall, as long as the whole timed region of a default run -- started at the timed region
+    it returned no sample and doubled the measured step.  Rows carry their arrival time; the ones
+    inside the timed region are reported, or (region shorter than the sampling period) the ones
+    since the start of the warm-up, i.e. under the same load."""
 
     def __init__(self, index):
         self.rows, self.proc, self.index = [], None, index
+        self.t0 = self.t1 = None
 
     def start(self):
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -59,7 +65,7 @@ class ClockSampler:
              "clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -67,16 +73,29 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
+
+    def begin(self):
+        self.t0 = time.time()
+
+    def end(self):
+        self.t1 = time.time()
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        if self.t1 is None:
+            self.t1 = time.time()
+        time.sleep(0.12)
         self.proc.terminate()
+        rows = [r for t, r in self.rows if self.t0 is not None and self.t0 <= t <= self.t1 + 0.05]
+        window = "timed region"
+        if not rows:
+            rows = [r for t, r in self.rows if t <= self.t1 + 0.05]
+            window = "warm-up + timed region (the timed region is shorter than the sampling period)"
         sm, mx, reasons = [], 0, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for r in rows:
             try:
                 sm.append(float(r[0])); mx = max(mx, float(r[1]))
                 for k, nm in enumerate(names):
@@ -86,7 +105,7 @@ class ClockSampler:
                 pass
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "window": window, "reasons": sorted(reasons)}
 
 
 def workload_config(args):
@@ -444,6 +463,7 @@ def run_ours(args, env=None, out=print):
         sh.encode()
         sh.decode_discover()
 
+    sampler = env.clock_sampler(); sampler.start()
     for _ in range(args.warmup):
         full_step()
     ok = sh.round_trip_ok()                        # property at full size: decode(encode(x)) == x
@@ -456,13 +476,14 @@ def run_ours(args, env=None, out=print):
     comm.barrier(); env.sync()
     ctx.launch_count(reset=True)
     ctx.profile(True); ctx.profile_report()
-    sampler = env.clock_sampler(); sampler.start()
 
     def k_steps():
         for _ in range(args.steps):
             full_step()
 
+    sampler.begin()
     ms = env.timed_ms(k_steps)
+    sampler.end()
     comm.barrier()
     clocks = sampler.stop()
     launches = ctx.launch_count()

@@ -1907,20 +1907,23 @@ static int undexqv_fast(dx_ctx *ctx, const uint8_t *d_in, size_t n, int upper, u
     return DX_E_NOMEM;
   if ((rc = dxk_qv_cand_prep(ctx,d_in,n,first,d_q,nc,4,minbits,pa,d_tlen,d_limit,d_ffrun,d_last)) != DX_OK) return rc;
   if ((rc = dxk_scan_u32(ctx,d_tlen,nc,d_toff)) != DX_OK) return rc;
-  // The layout of the text IF every candidate is an entry and follows its predecessor directly (true of
-  // nearly every file: a false candidate needs 13 bytes of stream data that look like an entry header):
-  // wells and text offsets are then prefix sums over the candidates, and the decoder can write headers
-  // and lines straight into place.  The chain below still decides; when it disagrees the lines are
-  // decoded again into a scratch image and moved (k_qv_assemble), as if nothing had been assumed.
+  // The layout of the text IF the entries are exactly the candidates that are not within 13 bytes of a
+  // later one (fields that overlap: k_qv_direct_prep) and every well delta is below 255 (no 0xff
+  // delta bytes; true of real data, where consecutive wells are a few holes apart): wells and text
+  // offsets are then prefix sums over the candidates, and the decoder can write headers and lines
+  // straight into place.  The chain below still decides; when it disagrees the lines are decoded
+  // again into a scratch image and moved (k_qv_assemble), as if nothing had been assumed.
   int64_t *d_wpre = (int64_t *) dx_arena_get(ctx,(N+1)*8);
   int64_t *d_opre = (int64_t *) dx_arena_get(ctx,(N+1)*8);
   uint32_t *d_len = (uint32_t *) dx_arena_get(ctx,N*4 + 4);
   int32_t *d_well = (int32_t *) dx_arena_get(ctx,N*4 + 4);
   QvDecEntry *d_ent = (QvDecEntry *) dx_arena_get(ctx,(N+1)*sizeof(QvDecEntry));
+  int32_t *d_rlen_d = (int32_t *) dx_arena_get(ctx,N*4 + 4);   // rlen, -1 for candidates outside that layout
   int32_t *d_flag2 = d_flag + 2;                        // unusable length in some candidate
-  if (!d_wpre || !d_opre || !d_len || !d_well || !d_ent) return DX_E_NOMEM;
+  if (!d_wpre || !d_opre || !d_len || !d_well || !d_ent || !d_rlen_d) return DX_E_NOMEM;
+  if ((rc = dxk_qv_direct_prep(ctx,d_q,nc,pa,d_rlen_d)) != DX_OK) return rc;
   if ((rc = dxk_scan_u32(ctx,pa.delta,nc,d_wpre)) != DX_OK) return rc;
-  if ((rc = dxk_qv_text_len(ctx,nc,NULL,pa,d_wpre,NULL,well_in,plen,d_len,d_well,d_flag2)) != DX_OK) return rc;
+  if ((rc = dxk_qv_text_len(ctx,nc,NULL,pa,d_wpre,NULL,well_in,plen,d_len,d_well,d_flag2,d_rlen_d)) != DX_OK) return rc;
   if ((rc = dxk_scan_u32(ctx,d_len,nc,d_opre)) != DX_OK) return rc;
   if ((rc = dxk_qv_build_ent(ctx,nc,NULL,pa,d_well,d_opre,d_len,NULL,d_ent,NULL,NULL,NULL)) != DX_OK) return rc;
   int64_t *h_q     = (int64_t *) dx_hpin_get(ctx,N*8);
@@ -1958,7 +1961,7 @@ static int undexqv_fast(dx_ctx *ctx, const uint8_t *d_in, size_t n, int upper, u
                              d_tmp,d_soff,d_stat,d_limit,d_order,d_toff,n_coop);
     };
   if (direct)
-    rc = dxk_qv_decode6x(ctx,d_in,n,d_tab4,coding.delchar,coding.subchar,upper,3,nc,pa.fs,pa.rlen,d_ent,d_prefix,plen,
+    rc = dxk_qv_decode6x(ctx,d_in,n,d_tab4,coding.delchar,coding.subchar,upper,3,nc,pa.fs,d_rlen_d,d_ent,d_prefix,plen,
                          d_out,d_soff,d_stat,d_limit,d_order,NULL,n_coop);
   else
     rc = spec_decode();
@@ -1970,8 +1973,10 @@ static int undexqv_fast(dx_ctx *ctx, const uint8_t *d_in, size_t n, int upper, u
 
   // the chain (see resolve_chain): a candidate is the next entry iff the bytes between the end of
   // the previous entry and its fields are 0xff ... 0xff, d with d != 0xff
-  size_t M = 0;
-  bool as_assumed = true;                 // every candidate an entry, every delta the one cand_prep assumed
+  size_t M = 0, kept = 0;
+  bool as_assumed = true;                 // the entries are the candidates of the assumed layout, with its deltas
+  auto in_layout = [&](size_t i) -> bool { return !(i + 1 < N && h_q[i+1] - h_q[i] < 13); };
+  for (size_t i = 0; i < N; i++) kept += in_layout(i);
   { int64_t cur = (int64_t) first;
     int32_t well = well_in;
     size_t i = 0;
@@ -1983,23 +1988,27 @@ static int undexqv_fast(dx_ctx *ctx, const uint8_t *d_in, size_t n, int upper, u
         if (gap > h_ffrun[i] || h_last[i] == 0xff) return DX_OK;
         const int64_t end = h_soff[6*i + 5];
         if (end > (int64_t) n || end <= cur) return DX_OK;
-        if (i != M || gap != h_ffrun[i]) as_assumed = false;
+        if (!in_layout(i) || gap != 0) as_assumed = false;
         well += 255 * (int32_t) gap + h_last[i];
         h_cand[M] = (int32_t) i; h_well[M] = well; M++;
         cur = end;
         i++;
       }
-    if (M != N) as_assumed = false;
+    if (M != kept) as_assumed = false;
   }
   ph.mark("chain");
   if (direct && as_assumed)
-    h_tail->total = direct_total;
+    { h_tail->total = direct_total;
+      if (ctx->route[DXR_DEBUG])
+        fprintf(stderr,"[dexb200 debug] undexqv: %zu candidates, %zu entries, decoded in place\n",N,M);
+    }
   else
     { if (direct)
         { // the assumption did not hold: the same candidates once more, lines only, into the scratch image
           // (soff / status do not depend on where the text goes)
           if (ctx->route[DXR_DEBUG])
-            fprintf(stderr,"[dexb200 debug] undexqv: %zu candidates, %zu entries: not as assumed, decoding again\n",N,M);
+            fprintf(stderr,"[dexb200 debug] undexqv: %zu candidates (%zu in the assumed layout), %zu entries: "
+                           "not as assumed, decoding again\n",N,kept,M);
           if ((rc = spec_decode()) != DX_OK) return rc;
           direct = false;
         }
@@ -2028,12 +2037,13 @@ static int undexqv_fast(dx_ctx *ctx, const uint8_t *d_in, size_t n, int upper, u
   if (ctx->keep_index)
     { std::vector<dx_index_row> &ix = *(std::vector<dx_index_row> *) ctx->last_index;
       std::vector<QvDecEntry> he;
-      if ((rc = download(ctx,d_ent,M,he)) != DX_OK) return rc;
+      if ((rc = download(ctx,d_ent,direct ? N : M,he)) != DX_OK) return rc;     // direct: one row per candidate
       ix.resize(M);
       for (size_t m = 0; m < M; m++)
         { const size_t c = (size_t) h_cand[m];
+          const QvDecEntry &d = he[direct ? c : m];
           ix[m].stream_off = h_q[c] + 12; ix[m].end_off = h_soff[6*c + 5];
-          ix[m].text_off = he[m].text_off; ix[m].rlen = he[m].end - he[m].beg; ix[m].well = he[m].well;
+          ix[m].text_off = d.text_off; ix[m].rlen = d.end - d.beg; ix[m].well = d.well;
         }
     }
   *out_len = (size_t) h_tail->total;

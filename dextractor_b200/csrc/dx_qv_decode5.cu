@@ -543,6 +543,10 @@ k_qv_decode5(Dec5Args a)
       int64_t at = a.start[e];
       int64_t o[6];
       uint8_t *line = NULL;
+      if (L < 0)                                             // ruled out by the planner: nothing is written
+        { if (lane == 0 && a.write != 1) a.status[e] = 1;
+          continue;
+        }
       if (a.write == 2 && a.ent == NULL)
         line = a.out + a.toff[e];
       else if (a.write)
@@ -565,10 +569,6 @@ k_qv_decode5(Dec5Args a)
       uint32_t bad = 0;
       StreamOut r;
       for (int k = 0; k < 6; k++) o[k] = at;
-      if (L < 0)                                             // ruled out by the host
-        { if (lane == 0 && a.write != 1) a.status[e] = 1;
-          continue;
-        }
 
       // a candidate that turns out not to be an entry (speculative modes) is dropped at the first sign
       do

@@ -65,9 +65,11 @@ __global__ void k_qv_cand_prep(const uint8_t *in, int64_t n, int64_t first, cons
       int64_t k = p - 1;
       while (k >= first && in[k] == 0xff && r < (1 << 20)) { r++; k--; }
       ffrun[i] = r;
-      // the well delta IF every candidate is an entry and no stream ends in a 0xff byte (the usual
-      // case: the text can then be decoded straight into place, see undexqv_fast)
-      pa.delta[i] = (uint32_t) (255*r) + in[p];
+      // the well delta IF this is an entry less than 255 wells after its predecessor (0xff bytes in
+      // front of the terminator then belong to the previous stream, whose last byte is the top of a
+      // code word and 0xff for one entry in 200): the usual case, in which the text can be decoded
+      // straight into place, see undexqv_fast
+      pa.delta[i] = in[p];
     }
   // limit: the fields of the span-th candidate after this one, counting only candidates at least
   // 64 bytes after the previously counted one
@@ -88,17 +90,30 @@ __global__ void k_qv_cand_prep(const uint8_t *in, int64_t n, int64_t first, cons
 // the field arrays; well[m] = well_in + wpre[m+1] when wells come from a scan of the deltas
 __global__ void k_qv_text_len(int64_t count, const int32_t *cand, QvPlanArrays pa, const int64_t *wpre,
                               const int32_t *wells, int32_t well_in, int plen, uint32_t *len,
-                              int32_t *well_out, int32_t *flag)
+                              int32_t *well_out, int32_t *flag, const int32_t *sel)
 { const int64_t m = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
   if (m >= count) return;
   const int64_t c = cand ? cand[m] : m;
   const int32_t well = wells ? wells[m] : (int32_t) (well_in + wpre[m+1]);
+  if (sel != NULL && sel[c] < 0) { len[m] = 0; well_out[m] = well; return; }     // not part of the layout
   const int32_t beg = pa.beg[c], en = pa.end[c], qv = pa.qv[c];
   const int64_t rl = (int64_t) en - beg;
   if (rl < 0 || rl >= (1 << 24)) { atomicExch(flag,2); len[m] = 0; well_out[m] = well; return; }
   const uint32_t hl = (uint32_t) plen + 1u + ndig(well) + 1u + ndig(beg) + 1u + ndig(en) + 6u + ndig(qv) + 1u;
   len[m] = hl + (uint32_t) (5*(rl + 1));
   well_out[m] = well;
+}
+
+// The layout of the text if every candidate is an entry (undexqv_fast): of candidates whose fields
+// overlap (closer than 13 bytes -- an entry before a short read has a look-alike one byte earlier,
+// whose fields are the true ones shifted by 8 bits) only the last can be that entry; the others
+// leave the layout: no text, no well delta, not decoded.
+__global__ void k_qv_direct_prep(const int64_t *q, int64_t count, QvPlanArrays pa, int32_t *rlen_d)
+{ const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const bool dropped = (i + 1 < count && q[i+1] - q[i] < 13);
+  rlen_d[i] = dropped ? -1 : pa.rlen[i];
+  if (dropped) pa.delta[i] = 0;
 }
 
 __global__ void k_qv_build_ent(int64_t count, const int32_t *cand, QvPlanArrays pa, const int32_t *well,
@@ -140,12 +155,20 @@ int dxk_qv_cand_prep(dx_ctx *ctx, const uint8_t *d_in, size_t n, size_t first, c
 
 int dxk_qv_text_len(dx_ctx *ctx, int64_t count, const int32_t *d_cand, QvPlanArrays pa, const int64_t *d_wpre,
                     const int32_t *d_wells, int32_t well_in, int plen, uint32_t *d_len, int32_t *d_well_out,
-                    int32_t *d_flag)
+                    int32_t *d_flag, const int32_t *d_sel)
 { if (count == 0) return DX_OK;
   DX_PROF_BEGIN(ctx);
   k_qv_text_len<<<(unsigned) ((count+255)/256),256,0,ctx->stream>>>(count,d_cand,pa,d_wpre,d_wells,well_in,plen,d_len,
-                                                                   d_well_out,d_flag);
+                                                                   d_well_out,d_flag,d_sel);
   DX_LAUNCHED(ctx,"k_qv_text_len");
+  return DX_OK;
+}
+
+int dxk_qv_direct_prep(dx_ctx *ctx, const int64_t *d_q, int64_t count, QvPlanArrays pa, int32_t *d_rlen_d)
+{ if (count == 0) return DX_OK;
+  DX_PROF_BEGIN(ctx);
+  k_qv_direct_prep<<<(unsigned) ((count+255)/256),256,0,ctx->stream>>>(d_q,count,pa,d_rlen_d);
+  DX_LAUNCHED(ctx,"k_qv_direct_prep");
   return DX_OK;
 }
 

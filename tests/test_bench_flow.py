@@ -146,6 +146,8 @@ class FakeEnv:
     def clock_sampler(self):
         class S:
             def start(self): pass
+            def begin(self): pass
+            def end(self): pass
             def stop(self): return {"sm_mhz": 1.0, "sm_max_mhz": 1.0, "reasons": []}
         return S()
 

@@ -77,9 +77,15 @@ def _reads(seed, lengths):
 
 def _write_block(L, f, reads, lossy=0):
     """one coding + its entries, dex2DB order; -> coff of every read"""
+    def mutable(r):
+        # the reference packs the tags (and, lossy, edits the QVs) IN PLACE (QV.c:1343-1379): hand it
+        # copies -- a Python bytes object is immutable, and a one-character line is the interpreter's
+        # shared object for that character
+        return [C.create_string_buffer(x, len(x) + 8) for x in r]
+
     L.QVcoding_Scan1(0, None, None, None, None, None)
     for r in reads:
-        L.QVcoding_Scan1(len(r[0]), *r)
+        L.QVcoding_Scan1(len(r[0]), *mutable(r))
     cd = L.Create_QVcoding(lossy)
     assert cd
     cd.contents.prefix = L.Strdup(b".qvs", b"Allocating header prefix")
@@ -87,7 +93,7 @@ def _write_block(L, f, reads, lossy=0):
     coff = []
     for r in reads:
         coff.append(libc.ftello(f))
-        L.Compress_Next_QVentry1(len(r[0]), *r, f, cd, lossy)
+        L.Compress_Next_QVentry1(len(r[0]), *mutable(r), f, cd, lossy)
     return coff
 
 

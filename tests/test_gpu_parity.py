@@ -214,3 +214,37 @@ def test_batched_reads(ctx, orc):
     ctx.sync()
     back = d_back.cpu().numpy().tobytes()
     assert back == src.lower().replace(b"n", b"a")
+
+
+def test_batched_arrows(ctx, orc):
+    """The same batch form for pulse widths, as Load_All_Arrows uses the codec (DB.c:1556-1614):
+    Number_Arrow + Compress_Read one way, Uncompress_Read + Letter_Arrow the other."""
+    import ctypes as C
+    import torch
+    rng = np.random.default_rng(4)
+    lens = np.array([1, 2, 3, 4, 5, 7, 8, 9, 31, 32, 33, 255, 256, 257, 1000, 4097, 30001], dtype=np.int32)
+    reads = [rng.choice(np.frombuffer(b"1234", dtype=np.uint8), size=int(n)).tobytes() for n in lens]
+    src = b"".join(reads)
+    src_off = np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.int64)
+    clen = (lens + 3) // 4
+    dst_off = np.concatenate([[0], np.cumsum(clen)[:-1]]).astype(np.int64)
+    d_src = torch.frombuffer(bytearray(src), dtype=torch.uint8).cuda()
+    d_so, d_len = torch.from_numpy(src_off).cuda(), torch.from_numpy(lens).cuda()
+    d_do = torch.from_numpy(dst_off).cuda()
+    d_dst = torch.zeros(int(clen.sum()), dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    ctx.compress_reads_dev(dx.ARROW, d_src.data_ptr(), d_so.data_ptr(), d_len.data_ptr(),
+                           len(lens), d_dst.data_ptr(), d_do.data_ptr())
+    ctx.sync()
+    packed = d_dst.cpu().numpy().tobytes()
+    for i, r in enumerate(reads):
+        buf = C.create_string_buffer(r, len(r) + 8)
+        orc.lib().orc_number_arrow(buf)
+        orc.lib().orc_compress_read(len(r), buf)
+        assert packed[dst_off[i]: dst_off[i] + clen[i]] == buf.raw[: clen[i]], i
+    d_back = torch.zeros(len(src), dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    ctx.uncompress_reads_dev(dx.ARROW, False, d_dst.data_ptr(), d_do.data_ptr(), d_len.data_ptr(),
+                             len(lens), d_back.data_ptr(), d_so.data_ptr())
+    ctx.sync()
+    assert d_back.cpu().numpy().tobytes() == src
