@@ -250,7 +250,7 @@ extern "C" void       *dx_stream(dx_ctx *ctx) { return ctx ? (void *) ctx->strea
 extern "C" int dx_route(dx_ctx *ctx, const char *name, int64_t value)
 { static const char *names[DXR_COUNT] = { "no_fast", "no_spec", "exact_index", "exact_pack", "pack2", "two_pass",
                                           "chain_scan", "decoder", "lane_max_rlen", "lane_min_entries", "debug",
-                                          "serial_io", "pipe_chunk", "no_direct" };
+                                          "serial_io", "pipe_chunk", "no_direct", "hist_mode" };
   if (ctx == NULL || name == NULL) return DX_E_ARG;
   if (strcmp(name,"default") == 0)
     { const int64_t dbg = ctx->route[DXR_DEBUG];
@@ -1798,10 +1798,8 @@ static int undexqv_fast(dx_ctx *ctx, const uint8_t *d_in, size_t n, int upper, u
         DX_CUDA(ctx,cudaMemcpyAsync(d_tab4,h4,sizeof(QvDecTables4),cudaMemcpyHostToDevice,ctx->stream));
       return DX_OK;
     };
-  if (h_entry_off == NULL)
-    { if ((rc = make_tables()) != DX_OK) return rc;
-      if (!tables_ok) return DX_OK;
-    }
+  // ... and while the candidate index runs when there is none
+  struct Deferred { decltype(make_tables) *fn; int rc; } deferred = { &make_tables, DX_OK };
   char *h_prefix = (char *) dx_hpin_get(ctx,(size_t) plen + 1);
   if (h_prefix == NULL) return DX_E_NOMEM;
   memcpy(h_prefix,prefix.data(),(size_t) plen + 1);
@@ -1883,7 +1881,16 @@ static int undexqv_fast(dx_ctx *ctx, const uint8_t *d_in, size_t n, int upper, u
 
   // ---- entry starts unknown: candidates, speculative decode, verified chain --------------------------
   int64_t *d_q = NULL, nc = 0;
-  if ((rc = dxk_index_positions(ctx,DX_PRED_QVCAND,d_in,n,first + 1,&d_q,&nc)) != DX_OK) return rc;
+  ctx->overlap_arg = &deferred;
+  ctx->overlap_fn = [](void *p) { Deferred *d = (Deferred *) p; d->rc = (*d->fn)(); };
+  rc = dxk_index_positions(ctx,DX_PRED_QVCAND,d_in,n,first + 1,&d_q,&nc);
+  if (ctx->overlap_fn != NULL)                          // the index took a route without the hook
+    { ctx->overlap_fn = NULL;
+      deferred.rc = make_tables();
+    }
+  if (rc != DX_OK) return rc;
+  if (deferred.rc != DX_OK) return deferred.rc;
+  if (!tables_ok) return DX_OK;
   ph.mark("index");
   const size_t N = (size_t) nc;
   if (N == 0) return DX_OK;                             // empty or all entries missed: general path

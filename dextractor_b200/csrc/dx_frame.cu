@@ -510,6 +510,11 @@ int index_positions(dx_ctx *ctx, const uint8_t *buf, size_t n, size_t first,
     if ((rc = dxk_fetch(ctx,&hp->total,d_pre+ntiles,8)) != DX_OK) return rc;
     if ((rc = dxk_fetch(ctx,&hp->over,d_over,4)) != DX_OK) return rc;
   }
+  if (ctx->overlap_fn != NULL)                  // the caller's host work, hidden behind the index pass
+    { void (*fn)(void *) = ctx->overlap_fn;
+      ctx->overlap_fn = NULL;
+      fn(ctx->overlap_arg);
+    }
   DX_CUDA(ctx,cudaStreamSynchronize(ctx->stream));
   const Res h = *hp;
   if (h.over) return index_positions_exact<PRED>(ctx,buf,n,first,d_pos,count);

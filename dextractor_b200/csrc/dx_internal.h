@@ -85,6 +85,7 @@ enum { DXR_NO_FAST = 0, DXR_NO_SPEC, DXR_EXACT_INDEX, DXR_EXACT_PACK, DXR_PACK2,
        DXR_DEBUG, DXR_SERIAL_IO,
        DXR_PIPE_CHUNK,         // > 0: window size of the pipelined *_host calls in bytes (tests: small files)
        DXR_NO_DIRECT,          // discovered entries: always decode into the scratch image, then assemble
+       DXR_HIST_MODE,          // k_qv_hist_run: 0 shared atomics, 1 match.any groups, 2 / 3 one of each, 4 no queue
        DXR_COUNT };
 
 struct dx_ctx
@@ -106,6 +107,9 @@ struct dx_ctx
   uint8_t     *io_out;  size_t io_out_cap;
   // copy streams and events of the pipelined *_host entry points (created on first use)
   cudaStream_t cs_in, cs_out;
+  // host work to do while the next position index runs on the device (called once, before its sync)
+  void       (*overlap_fn)(void *);
+  void        *overlap_arg;
   cudaEvent_t  pev[40];
   int          npev;
 

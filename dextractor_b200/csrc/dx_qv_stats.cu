@@ -122,6 +122,7 @@ struct HistArgs
   int64_t        efirst[4];        // first entry whose runs are counted
   unsigned long long *ticket;
   unsigned long long *ghist;       // [6][256]
+  int32_t        mode;             // k_qv_hist_run: how a batch is counted (warp_count2), route hist_mode
 };
 
 constexpr int kHistQueue = 544;    // a row adds <= 512 items to < 32 left over
@@ -272,14 +273,35 @@ k_qv_hist(HistArgs a)
 
 constexpr int kRunWarps   = 16;
 constexpr int kRunThreads = kRunWarps * 32;
+constexpr int kRunCtas    = 2;             // resident CTAs per SM (3 = 48 warps was measured: 1.19 ms against 1.01)
 constexpr int kRunWarpWords = 512 + kHistQueue;          // histogram (256 symbols + 256 run lengths), queue
 
-// the lanes < n of the warp add 1 to bin key[lane]; lanes with equal keys are grouped
-__device__ __forceinline__ void warp_count(uint32_t *hist, uint32_t key, uint32_t n, int lane)
-{ if ((uint32_t) lane < n)
+// the lanes < n of the warp add 1 to bin key[lane] (and, with `two`, to bin key2[lane]).
+//   mode 0: every lane issues a shared-memory atomic add, equal keys are serialised by the hardware
+//           (the default: 0.70 ms on the 2 GB bench file);
+//   mode 1: round 1's form -- lanes with equal keys are grouped by match.any and the group's first
+//           lane adds its size with a plain load / add / store (1.07 ms: the two match.any of a
+//           batch, not the adds, were what the warps waited for; three CTAs per SM made it slower);
+//   mode 2: match for the symbol, atomics for the run length (0.85 ms);  mode 3: the other way round
+//           (0.83 ms);  mode 4 does not come here: no queue, see the kernel (0.73 ms).
+// With atomics the kernel retires ~1.5 atomic lanes per clock and SM, the rate of the unit.
+__device__ __forceinline__ void warp_count2(uint32_t *hist, uint32_t key, uint32_t key2, bool two,
+                                            uint32_t n, int lane, int mode)
+{ const bool m1 = (mode == 1 || mode == 2), m2 = (mode == 1 || mode == 3);
+  if ((uint32_t) lane < n)
     { const uint32_t mask = (n >= 32u) ? DX_FULL : ((1u << n) - 1u);
-      const uint32_t peers = __match_any_sync(mask,key);
-      if ((uint32_t) lane == (uint32_t) (__ffs(peers) - 1)) hist[key] += (uint32_t) __popc(peers);
+      if (m1)
+        { const uint32_t peers = __match_any_sync(mask,key);
+          if ((uint32_t) lane == (uint32_t) (__ffs(peers) - 1)) hist[key] += (uint32_t) __popc(peers);
+        }
+      else atomicAdd(&hist[key],1u);
+      if (two)
+        { if (m2)
+            { const uint32_t peers2 = __match_any_sync(mask,key2);
+              if ((uint32_t) lane == (uint32_t) (__ffs(peers2) - 1)) hist[key2] += (uint32_t) __popc(peers2);
+            }
+          else atomicAdd(&hist[key2],1u);
+        }
     }
   __syncwarp();
 }
@@ -297,7 +319,7 @@ __device__ __noinline__ void run_warp_flush(const HistArgs &a, int s, uint32_t *
   __syncwarp();
 }
 
-__global__ void __launch_bounds__(kRunThreads,2)
+__global__ void __launch_bounds__(kRunThreads,kRunCtas)
 k_qv_hist_run(HistArgs a)
 { extern __shared__ __align__(16) uint8_t dx_hist_smem[];
   const int lane = threadIdx.x & 31;
@@ -339,6 +361,35 @@ k_qv_hist_run(HistArgs a)
 #pragma unroll 1
       for (int32_t c0 = 0; c0 < nchunk + 32; c0 += 32)            // one extra round drains the queue
         { const bool last = (c0 >= nchunk);
+          if (a.mode == 4)
+            { // no queue: every lane counts the items of its own chunk with shared-memory atomics; the
+              // run before a lane's first item ends at the last item of the nearest lane in front of
+              // it that has one (positions grow with the lane), or at the previous rounds' last item
+              if (last) break;
+              const int32_t c = c0 + lane;
+              const uint4 v = nxt;
+              nxt = nx2;
+              nx2 = (c + 64 < nchunk) ? dx_ldg16(base + (int64_t) (c + 64)*16) : make_uint4(0,0,0,0);
+              const int32_t p0 = c*16 - skew;
+              uint32_t m = 0;
+              if (c < nchunk)
+                m = dx_range16(max(0,-p0),min(16,rlen - p0)) & ~dx_eq_mask16(v,rc);
+              const int32_t mylast = m ? p0 + (31 - __clz(m)) : -1;
+              const uint32_t has = __ballot_sync(DX_FULL,m != 0u);
+              const uint32_t before = has & ((1u << lane) - 1u);
+              const int32_t fromlane = __shfl_sync(DX_FULL,mylast,before ? 31 - __clz(before) : 0);
+              int32_t pp = before ? fromlane : prevpos;
+              while (m)
+                { const int i = __ffs(m) - 1; m &= m - 1;
+                  const int32_t pos = p0 + i;
+                  atomicAdd(&hist[dx_byte_of(v,i)],1u);
+                  if (runs) atomicAdd(&hist[256 + min(pos - pp - 1,255)],1u);
+                  pp = pos;
+                }
+              const int32_t tail = __shfl_sync(DX_FULL,mylast,has ? 31 - __clz(has) : 0);
+              if (has) prevpos = tail;
+              continue;
+            }
           if (!last)
             { const int32_t c = c0 + lane;
               const uint4 v = nxt;
@@ -368,8 +419,7 @@ k_qv_hist_run(HistArgs a)
                   const int32_t pp = (lane == 0) ? prevpos : (int32_t) (queue[done + lane - 1] >> 8);
                   rl = (uint32_t) min((int32_t) (it >> 8) - pp - 1,255);
                 }
-              warp_count(hist,it & 0xffu,n,lane);
-              if (runs) warp_count(hist,256u + rl,n,lane);
+              warp_count2(hist,it & 0xffu,256u + rl,runs,n,lane,a.mode);
               prevpos = __shfl_sync(DX_FULL,(int32_t) (it >> 8),n-1);
               done += n;
             }
@@ -383,7 +433,7 @@ k_qv_hist_run(HistArgs a)
           __syncwarp();
         }
       if (runs && prevpos < rlen-1)                                // trailing run (QV.c:713-720)
-        { if (lane == 0) hist[256 + min(rlen-1-prevpos,255)] += 1u;
+        { if (lane == 0) atomicAdd(&hist[256 + min(rlen-1-prevpos,255)],1u);
           __syncwarp();
         }
     }
@@ -438,6 +488,7 @@ int dxk_qv_hist(dx_ctx *ctx, const uint8_t *d_text, QvEntries ent, const QvProbe
   plain.text = run.text = d_text; plain.ent = run.ent = ent;
   plain.ghist = run.ghist = d_hist;
   plain.ticket = d_hist + 6*256; run.ticket = d_hist + 6*256 + 1;
+  run.mode = (int32_t) ctx->route[DXR_HIST_MODE];
   for (int s = 0; s < 4; s++)
     { const int32_t rc = (s == 0) ? h_probe->delchar : (s == 3) ? h_probe->subchar : -1;
       HistArgs &h = (rc >= 0) ? run : plain;
@@ -457,7 +508,7 @@ int dxk_qv_hist(dx_ctx *ctx, const uint8_t *d_text, QvEntries ent, const QvProbe
     }
   if (run.ns > 0)
     { DX_PROF_BEGIN(ctx);
-      k_qv_hist_run<<<ctx->sm_count*2,kRunThreads,kRunWarps*kRunWarpWords*4,ctx->stream>>>(run);
+      k_qv_hist_run<<<ctx->sm_count*kRunCtas,kRunThreads,kRunWarps*kRunWarpWords*4,ctx->stream>>>(run);
       DX_LAUNCHED(ctx,"k_qv_hist_run");
     }
   DX_CUDA(ctx,cudaMemcpyAsync(h_hist,d_hist,6*256*8,cudaMemcpyDeviceToHost,ctx->stream));

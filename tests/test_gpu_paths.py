@@ -40,6 +40,8 @@ ROUTES = [
     {"lane_max_rlen": 3000},                             # both parallel decoders in one call
     {"decoder": 6, "no_fast": 1},                        # lane-per-entry decoder behind the host-planned path
     {"no_direct": 1},                                    # discovered entries via the scratch image + k_qv_assemble
+    {"hist_mode": 1},                                    # run-length histograms: match.any groups
+    {"hist_mode": 4},                                    # ... without the item queue
 ]
 
 
@@ -365,3 +367,28 @@ def test_pipelined_host_decode_on_small_windows(routed, orc, chunk):
         assert got == exp, (upper, first_diff(got, exp))
     ctx.route("serial_io", 1)
     assert ctx.undexqv(enc, cap=len(want) + 4096) == want
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2, 3, 4])
+def test_run_histogram_counting_modes(ctx, orc, mode):
+    """k_qv_hist_run counts a batch of (symbol, run length) items in five ways (route hist_mode):
+    every one must give Histogram_Seqs / Histogram_Runs' numbers (QV.c:702-724) on files of random
+    shape -- run densities 0 ... 0.995, runs beyond 255, run characters that appear late."""
+    import torch
+    from tests import fuzz
+    ctx.route("default")
+    ctx.route("hist_mode", mode)
+    try:
+        texts = [fuzz.fuzz_quiva(seed)[0] for seed in (0, 3, 5, 8, 13, 21)]
+        texts += [QUIVA[n] for n in ("long_runs", "late_n", "lognormal_40", "no_n_tags")]
+        for i, text in enumerate(texts):
+            t = torch.frombuffer(bytearray(text), dtype=torch.uint8).cuda()
+            st = ctx.qv_scan_dev(t.data_ptr(), len(text))
+            ref = orc.qv_scan(text)
+            assert (st.delchar, st.subchar, st.totchar) == (ref.delchar, ref.subchar, ref.totchar), i
+            for k, nm in enumerate(["del_", "ins", "mrg", "sub"]):
+                assert list(st.hist[k]) == list(getattr(ref, nm)), (i, nm)
+            assert [x + 1 for x in st.hist[4]] == list(ref.delrun), i
+            assert [x + 1 for x in st.hist[5]] == list(ref.subrun), i
+    finally:
+        ctx.route("default")
