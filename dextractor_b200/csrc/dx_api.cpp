@@ -44,6 +44,12 @@ int dx_fail(dx_ctx *ctx, int code, const char *fmt, ...)
   return code;
 }
 
+// the output buffer is too small: the size the call needs is kept for dx_needed_bytes
+int dx_fail_cap(dx_ctx *ctx, size_t need, size_t cap)
+{ ctx->need_bytes = need;
+  return dx_fail(ctx,DX_E_CAP,"output needs %zu bytes, buffer has %zu",need,cap);
+}
+
 int dx_cuda_fail(dx_ctx *ctx, cudaError_t e, const char *what)
 { return dx_fail(ctx,DX_E_CUDA,"CUDA error %d (%s) in %s",(int) e,cudaGetErrorString(e),what); }
 
@@ -245,6 +251,7 @@ extern "C" void dx_close(dx_ctx *ctx)
 
 extern "C" const char *dx_strerror(const dx_ctx *ctx) { return ctx ? ctx->err : "no context"; }
 extern "C" int64_t     dx_error_line(const dx_ctx *ctx) { return ctx ? ctx->err_line : 0; }
+extern "C" size_t      dx_needed_bytes(const dx_ctx *ctx) { return ctx ? ctx->need_bytes : 0; }
 extern "C" void       *dx_stream(dx_ctx *ctx) { return ctx ? (void *) ctx->stream : NULL; }
 
 extern "C" int dx_route(dx_ctx *ctx, const char *name, int64_t value)
@@ -607,7 +614,7 @@ static int dexta_impl(dx_ctx *ctx, int kind, const uint8_t *d_text, size_t n,
   int64_t body = 0;
   if ((rc = dxk_fa_offsets(ctx,kind,ent,0,&body)) != DX_OK) return rc;
   if (hbytes + (size_t) body > cap)
-    return dx_fail(ctx,DX_E_CAP,"output needs %zu bytes, buffer has %zu",hbytes + (size_t) body,cap);
+    return dx_fail_cap(ctx,(size_t) (hbytes + (size_t) body),cap);
 
   std::vector<uint8_t> fh(hbytes);
   const uint16_t key = 0x55aa;
@@ -856,7 +863,7 @@ static int undexta_fast(dx_ctx *ctx, int kind, const uint8_t *d_in, size_t n, in
   DX_CUDA(ctx,cudaStreamSynchronize(ctx->stream));
   const size_t total = (size_t) *h_total;
   if (d_out != NULL)
-    { if (total > cap) return dx_fail(ctx,DX_E_CAP,"output needs %zu bytes, buffer has %zu",total,cap);
+    { if (total > cap) return dx_fail_cap(ctx,(size_t) (total),cap);
       if (ctx->route[DXR_PACK2])
         rc = dxk_unpack2(ctx,kind,upper,width,d_in,n,d_ent,(int64_t) M,d_prefix,plen,d_out,d_ticket);
       else
@@ -886,7 +893,7 @@ extern "C" int dx_undexta_dev(dx_ctx *ctx, int kind, const uint8_t *d_in, size_t
   PkPlan plan;
   if ((rc = plan_undexta(ctx,kind,d_in,n,width,plan)) != DX_OK) return rc;
   if (plan.text_len > cap)
-    return dx_fail(ctx,DX_E_CAP,"output needs %zu bytes, buffer has %zu",plan.text_len,cap);
+    return dx_fail_cap(ctx,(size_t) (plan.text_len),cap);
   if (d_out == NULL && plan.text_len > 0) return dx_fail(ctx,DX_E_ARG,"output is NULL");
   const size_t N = plan.ent.size();
   PkDecEntry *d_ent = (PkDecEntry *) dx_arena_get(ctx,N*sizeof(PkDecEntry));
@@ -1853,7 +1860,7 @@ static int undexqv_fast(dx_ctx *ctx, const uint8_t *d_in, size_t n, int upper, u
       if (h_tail->flag == 1) return dx_fail(ctx,DX_E_TRUNC,"compressed image ends inside an entry header");
       if (h_tail->flag == 2) return dx_fail(ctx,DX_E_FORMAT,"unusable read length in an entry header");
       if ((size_t) h_tail->total > cap)
-        return dx_fail(ctx,DX_E_CAP,"output needs %lld bytes, buffer has %zu",(long long) h_tail->total,cap);
+        return dx_fail_cap(ctx,(size_t) (h_tail->total),cap);
       const int64_t n_coop = ticket_plan(ctx,h_rlen,N,h_order);
       DX_CUDA(ctx,cudaMemcpyAsync(d_order,h_order,N*4,cudaMemcpyHostToDevice,ctx->stream));
       if ((rc = dxk_qv_decode6x(ctx,d_in,n,d_tab4,coding.delchar,coding.subchar,upper,1,(int64_t) N,pa.fs,pa.rlen,
@@ -2035,7 +2042,7 @@ static int undexqv_fast(dx_ctx *ctx, const uint8_t *d_in, size_t n, int upper, u
       DX_CUDA(ctx,cudaStreamSynchronize(ctx->stream));
       if (h_tail->flag) return dx_fail(ctx,DX_E_FORMAT,"unusable read length in an entry header");
       if ((size_t) h_tail->total > cap)
-        return dx_fail(ctx,DX_E_CAP,"output needs %lld bytes, buffer has %zu",(long long) h_tail->total,cap);
+        return dx_fail_cap(ctx,(size_t) (h_tail->total),cap);
       if ((rc = dxk_qv_assemble(ctx,d_tmp,tmp_n,d_ent,d_src,(int64_t) M,d_prefix,plen,d_out)) != DX_OK) return rc;
       DX_CUDA(ctx,cudaStreamSynchronize(ctx->stream));
       ph.mark("assemble");
@@ -2077,7 +2084,7 @@ extern "C" int dx_undexqv_dev(dx_ctx *ctx, const uint8_t *d_in, size_t n, int up
   QvPlan plan;
   if ((rc = plan_undexqv(ctx,d_in,n,h_entry_off,nentries,well_in,true,upper,plan)) != DX_OK) return rc;
   if (plan.text_len > cap)
-    return dx_fail(ctx,DX_E_CAP,"output needs %zu bytes, buffer has %zu",plan.text_len,cap);
+    return dx_fail_cap(ctx,(size_t) (plan.text_len),cap);
   const size_t N = plan.ent.size();
   QvDecEntry *d_ent = (QvDecEntry *) dx_arena_get(ctx,N*sizeof(QvDecEntry));
   int32_t *d_stat = (int32_t *) dx_arena_get(ctx,4);
@@ -2163,7 +2170,7 @@ extern "C" int dx_qv_load_entries_dev(dx_ctx *ctx, const uint8_t *d_in, size_t n
   if (h_out_off) memcpy(h_out_off,toff.data(),(N + 1)*8);
   if (N == 0) return DX_OK;
   if ((size_t) toff[N] > cap)
-    return dx_fail(ctx,DX_E_CAP,"output needs %lld bytes, buffer has %zu",(long long) toff[N],cap);
+    return dx_fail_cap(ctx,(size_t) (toff[N]),cap);
   QvDecTables4 *h4 = (QvDecTables4 *) malloc(sizeof(QvDecTables4));
   if (h4 == NULL) return DX_E_NOMEM;
   if (!build_dec_tables4(coding,h4))

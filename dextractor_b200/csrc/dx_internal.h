@@ -106,6 +106,7 @@ struct dx_ctx
   uint8_t     *io_in;   size_t io_in_cap;
   uint8_t     *io_out;  size_t io_out_cap;
   // copy streams and events of the pipelined *_host entry points (created on first use)
+  size_t       need_bytes;      // output size asked for by the last DX_E_CAP failure (dx_needed_bytes)
   cudaStream_t cs_in, cs_out;
   // host work to do while the next position index runs on the device (called once, before its sync)
   void       (*overlap_fn)(void *);
@@ -135,6 +136,7 @@ struct dx_ctx
 
 int   dx_fail(dx_ctx *ctx, int code, const char *fmt, ...);
 int   dx_cuda_fail(dx_ctx *ctx, cudaError_t e, const char *what);
+int   dx_fail_cap(dx_ctx *ctx, size_t need, size_t cap);
 void  dx_arena_reset(dx_ctx *ctx);
 void *dx_arena_get(dx_ctx *ctx, size_t bytes);        // 256-byte aligned; NULL + error on failure
 int   dx_arena_reserve(dx_ctx *ctx, size_t bytes);    // make sure this much is available

@@ -566,7 +566,7 @@ int dxk_qv_encode(dx_ctx *ctx, const uint8_t *d_text, size_t text_n, QvEntries e
       DX_CUDA(ctx,cudaStreamSynchronize(ctx->stream));
       if (!ovf)
         { if ((size_t) total > cap)
-            return dx_fail(ctx,DX_E_CAP,"output needs %lld bytes, buffer has %zu",(long long) total,cap);
+            return dx_fail_cap(ctx,(size_t) (total),cap);
           CompactArgs c;
           c.scratch = d_scratch; c.scratch_end16 = d_scratch + sbytes - 16;
           c.ent = ent; c.bytes = d_bytes; c.off = d_off; c.lwell_in = lwell_in; c.out = d_out;
@@ -584,7 +584,7 @@ int dxk_qv_encode(dx_ctx *ctx, const uint8_t *d_text, size_t text_n, QvEntries e
       DX_CUDA(ctx,cudaMemcpyAsync(&lastw,ent.well+(n-1),4,cudaMemcpyDeviceToHost,ctx->stream));
       DX_CUDA(ctx,cudaStreamSynchronize(ctx->stream));
       if ((size_t) total > cap)
-        return dx_fail(ctx,DX_E_CAP,"output needs %lld bytes, buffer has %zu",(long long) total,cap);
+        return dx_fail_cap(ctx,(size_t) (total),cap);
       a.ticket = d_ticket + 1;
       DX_PROF_BEGIN(ctx); k_qv_code<1><<<grid,kEncThreads,smem1,ctx->stream>>>(a);
       DX_LAUNCHED(ctx,"k_qv_emit");

@@ -17,7 +17,7 @@ ERRNAMES = {-1: "FORMAT", -2: "CAP", -3: "TRUNC", -4: "KEY", -5: "LINELEN", -6: 
 
 # every symbol include/dexb200.h declares (checked by tests/test_abi.py)
 SYMBOLS = [
-    "dx_open", "dx_close", "dx_strerror", "dx_error_line", "dx_sync", "dx_stream",
+    "dx_open", "dx_close", "dx_strerror", "dx_error_line", "dx_needed_bytes", "dx_sync", "dx_stream",
     "dx_device_alloc", "dx_device_free", "dx_pinned_alloc", "dx_pinned_free", "dx_h2d", "dx_d2h", "dx_d2d",
     "dx_launch_count", "dx_profile", "dx_profile_report", "dx_route",
     "dx_dexta_dev", "dx_dexta_host", "dx_undexta_dev", "dx_undexta_host", "dx_undexta_size_host",
@@ -99,6 +99,7 @@ def load_library():
         "dx_close": (None, [vp]),
         "dx_strerror": (C.c_char_p, [vp]),
         "dx_error_line": (i64, [vp]),
+        "dx_needed_bytes": (C.c_size_t, [vp]),
         "dx_sync": (C.c_int, [vp]),
         "dx_stream": (vp, [vp]),
         "dx_device_alloc": (vp, [vp, sz]),
@@ -245,8 +246,13 @@ class Context:
         out = np.empty(len(text) // 2 + 4096, dtype=np.uint8)
         n = C.c_size_t(0)
         src = np.frombuffer(text, dtype=np.uint8)
-        self._check(self.L.dx_dexta_host(self.h, kind, src.ctypes.data, len(text),
-                                         out.ctypes.data, out.size, C.byref(n)))
+        rc = self.L.dx_dexta_host(self.h, kind, src.ctypes.data, len(text), out.ctypes.data, out.size,
+                                  C.byref(n))
+        if rc == -2 and self.L.dx_needed_bytes(self.h) > out.size:      # DX_E_CAP: go again with what it needs
+            out = np.empty(self.L.dx_needed_bytes(self.h) + 64, dtype=np.uint8)
+            rc = self.L.dx_dexta_host(self.h, kind, src.ctypes.data, len(text), out.ctypes.data, out.size,
+                                      C.byref(n))
+        self._check(rc)
         return out[: n.value].tobytes()
 
     def undexta(self, data: bytes, kind: int = FASTA, width: int = 80, upper: bool = False) -> bytes:

@@ -49,6 +49,10 @@ int         dx_open(int device, dx_ctx **ctx);
 void        dx_close(dx_ctx *ctx);
 const char *dx_strerror(const dx_ctx *ctx);     /* text of the last error on this context       */
 int64_t     dx_error_line(const dx_ctx *ctx);   /* 1-based input line of a text error, 0 if n/a */
+/* the output size the last call that returned DX_E_CAP needed (0 if it could not tell): allocate that
+ * much and call again -- an image has no useful a-priori bound, a single well gap of 2^31 holes is
+ * 8.4 MB of 0xff delta bytes (dexta.c:186-193) */
+size_t      dx_needed_bytes(const dx_ctx *ctx);
 int         dx_sync(dx_ctx *ctx);               /* wait for the context's stream                */
 void       *dx_stream(dx_ctx *ctx);             /* the cudaStream_t every _dev call runs on     */
 

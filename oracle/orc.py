@@ -94,7 +94,12 @@ def _run(fn, data: bytes, cap: int, *mid):
 
 
 def dexta(text: bytes, arrow: bool = False) -> bytes:
-    return _run(lib().orc_dexta, text, len(text) // 2 + 4096, int(arrow))
+    try:
+        return _run(lib().orc_dexta, text, len(text) // 2 + 4096, int(arrow))
+    except OracleError as e:                     # many tiny entries / huge well gaps: the image outgrows the text
+        if e.code != -2:
+            raise
+        return _run(lib().orc_dexta, text, 64 * len(text) + (1 << 24), int(arrow))
 
 
 def undexta(data: bytes, arrow: bool = False, width: int = 80, upper: bool = False) -> bytes:

@@ -91,3 +91,32 @@ def test_errors_are_reported_like_the_reference(tmp):
     _write(base + ".dexta", b"\x12\x34rubbish")
     p = subprocess.run([os.path.join(BIN, "undexta"), base], capture_output=True)
     assert p.returncode == 1 and b"endian key invalid" in p.stderr
+
+
+@pytest.mark.parametrize("tool,src,dst,arrow", [("dexta", ".fasta", ".dexta", False), ("dexar", ".arrow", ".dexar", True)])
+def test_many_tiny_entries_outgrow_the_first_buffer(orc, tmp, tool, src, dst, arrow):
+    """An image is 13 (17) header bytes per entry plus a quarter of the bases: 150 000 one-base entries
+    with well gaps give an image LARGER than the text.  The tool's first buffer (n/3 + 200 000) is
+    too small; it must ask the library what the call needs (dx_needed_bytes) and go again -- the
+    reference compresses such a file without complaint (dexta.c:139-205)."""
+    parts = []
+    well = 0
+    for i in range(150000):
+        well += 1 + (i % 7) * 300                        # up to seven 0xff delta bytes
+        if arrow:
+            parts.append(b">m/%d/0_1 SN=5.00,6.00,7.00,8.00\n%c\n" % (well, b"1234"[i % 4]))
+        else:
+            parts.append(b">m/%d/0_1 RQ=0.850\n%c\n" % (well, b"acgt"[i % 4]))
+    text = b"".join(parts)
+    want = orc.dexta(text, arrow=arrow)
+    assert len(want) > len(text) // 3 + 200000
+    base = os.path.join(tmp, "tiny")
+    _write(base + src, text)
+    run_tool(tool, base + src, "-k")
+    assert _read(base + dst) == want
+    import dextractor_b200 as dx                      # and the same through the host-buffer binding
+    ctx = dx.Context(0)
+    try:
+        assert ctx.dexta(text, kind=dx.ARROW if arrow else dx.FASTA) == want
+    finally:
+        ctx.close()
