@@ -232,6 +232,18 @@ class Comm:
         dist.all_gather_into_tensor(out, row)
         return out.view(self.world, -1)
 
+    def gather_rows(self, row):
+        """row: int64 numpy array on the host -> [world, len(row)] numpy array on every rank.  With one
+        rank there is nothing to exchange and nothing leaves the host; otherwise the rows go through
+        the communication device (NCCL all-gather on device buffers)."""
+        import numpy as np
+        import torch
+        if self.world == 1:
+            self.log.append(f"all_gather:{row.size}")
+            return np.asarray(row, dtype=np.int64).reshape(1, -1)
+        rows = self.all_gather_i64(torch.from_numpy(row).to(self.device))
+        return rows.cpu().numpy()
+
     def all_reduce(self, values, op="max", dtype=None):
         """list of numbers -> list reduced over the ranks"""
         import torch
@@ -396,10 +408,8 @@ def run_ours(args, env=None, out=print):
             """COLLECTIVE (one all-gather): dexqv = scan -> statistics exchange -> code construction
             -> file header + encode.  The image is [header][entries] from enc[0]."""
             st = ctx.qv_scan_dev(self.text.data_ptr(), self.U, self.carry)
-            import torch
-            row = torch.from_numpy(shards.pack_stats(st, self.last_well)).to(comm.device)
-            rows = comm.all_gather_i64(row)
-            tot, lwell_in = shards.merge_stats(rows.cpu().numpy(), rank, self.rc)
+            rows = comm.gather_rows(shards.pack_stats(st, self.last_well))
+            tot, lwell_in = shards.merge_stats(rows, rank, self.rc)
             cd = dxl.make_coding(tot, False)
             hdr = b"\xaa\x55" + dxl.write_coding(cd, self.prefix)
             hl = len(hdr)

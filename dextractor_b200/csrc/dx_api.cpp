@@ -1980,6 +1980,27 @@ static int undexqv_fast(dx_ctx *ctx, const uint8_t *d_in, size_t n, int upper, u
   else
     rc = spec_decode();
   if (rc != DX_OK) return rc;
+  if (direct && !ctx->keep_index)
+    { // the usual end of the call: the device checks that the decode confirmed the layout (the chain
+      // walk below as a predicate over independent candidates); the host reads two words
+      int32_t *d_chk = (int32_t *) dx_arena_get(ctx,8);
+      int32_t *h_chk = (int32_t *) dx_hpin_get(ctx,8);
+      if (!d_chk || !h_chk) return DX_E_NOMEM;
+      DX_CUDA(ctx,cudaMemsetAsync(d_chk,0,8,ctx->stream));
+      if ((rc = dxk_qv_chain_check(ctx,d_q,nc,d_rlen_d,d_stat,d_soff,d_last,first,n,d_chk)) != DX_OK) return rc;
+      DX_CUDA(ctx,cudaMemcpyAsync(h_chk,d_chk,8,cudaMemcpyDeviceToHost,ctx->stream));
+      DX_CUDA(ctx,cudaStreamSynchronize(ctx->stream));
+      ph.mark("decode");
+      if (h_chk[0] == 0)
+        { if (ctx->route[DXR_DEBUG])
+            fprintf(stderr,"[dexb200 debug] undexqv: %zu candidates, %d entries, decoded in place (checked on the device)\n",
+                    N,h_chk[1]);
+          ph.report("undexqv (entries discovered)");
+          *out_len = (size_t) direct_total;
+          *handled = true;
+          return DX_OK;
+        }
+    }
   DX_CUDA(ctx,cudaMemcpyAsync(h_soff,d_soff,N*48,cudaMemcpyDeviceToHost,ctx->stream));
   DX_CUDA(ctx,cudaMemcpyAsync(h_stat,d_stat,N*4,cudaMemcpyDeviceToHost,ctx->stream));
   DX_CUDA(ctx,cudaStreamSynchronize(ctx->stream));

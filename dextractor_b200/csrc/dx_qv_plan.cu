@@ -116,6 +116,30 @@ __global__ void k_qv_direct_prep(const int64_t *q, int64_t count, QvPlanArrays p
   if (dropped) pa.delta[i] = 0;
 }
 
+// ... and the check that the decode confirmed that layout (the host's chain walk, undexqv_fast, as a
+// predicate over independent candidates): the first kept candidate's terminator byte is the first
+// byte after the coding header, every kept candidate decoded cleanly, has a terminator below 0xff
+// and ends exactly where the terminator of the next kept candidate stands (no 0xff delta bytes),
+// the last one ends at the end of the image.  flag[0] = 1 on any violation; flag[1] += kept.
+__global__ void k_qv_chain_check(const int64_t *q, int64_t count, const int32_t *rlen_d, const int32_t *stat,
+                                 const int64_t *soff, const uint8_t *last, int64_t first, int64_t n, int32_t *flag)
+{ const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const bool kept = !(i + 1 < count && q[i+1] - q[i] < 13);
+  if (!kept) return;
+  atomicAdd(flag + 1,1);
+  bool ok = (rlen_d[i] >= 0 && stat[i] == 0 && last[i] != 0xff);
+  int64_t j = i + 1;                                    // next kept candidate
+  while (j < count && (j + 1 < count && q[j+1] - q[j] < 13)) j++;
+  const int64_t end = soff[6*i + 5];
+  ok = ok && (end == ((j < count) ? q[j] - 1 : n));
+  { int64_t k = i - 1;                                  // the first kept one? (only dropped ones in front:
+    while (k >= 0 && (q[k+1] - q[k] < 13)) k--;         //  the walk ends at once everywhere else)
+    if (k < 0) ok = ok && (q[i] - 1 == first);
+  }
+  if (!ok) atomicExch(flag,1);
+}
+
 __global__ void k_qv_build_ent(int64_t count, const int32_t *cand, QvPlanArrays pa, const int32_t *well,
                                const int64_t *opre, const uint32_t *len, const int64_t *toff,
                                QvDecEntry *ent, int64_t *src, int64_t *fs_out, int32_t *rlen_out)
@@ -180,5 +204,15 @@ int dxk_qv_build_ent(dx_ctx *ctx, int64_t count, const int32_t *d_cand, QvPlanAr
   k_qv_build_ent<<<(unsigned) ((count+255)/256),256,0,ctx->stream>>>(count,d_cand,pa,d_well,d_opre,d_len,d_toff,d_ent,
                                                                     d_src,d_fs_out,d_rlen_out);
   DX_LAUNCHED(ctx,"k_qv_build_ent");
+  return DX_OK;
+}
+
+int dxk_qv_chain_check(dx_ctx *ctx, const int64_t *d_q, int64_t count, const int32_t *d_rlen_d, const int32_t *d_stat,
+                       const int64_t *d_soff, const uint8_t *d_last, size_t first, size_t n, int32_t *d_flag)
+{ if (count == 0) return DX_OK;
+  DX_PROF_BEGIN(ctx);
+  k_qv_chain_check<<<(unsigned) ((count+255)/256),256,0,ctx->stream>>>(d_q,count,d_rlen_d,d_stat,d_soff,d_last,
+                                                                      (int64_t) first,(int64_t) n,d_flag);
+  DX_LAUNCHED(ctx,"k_qv_chain_check");
   return DX_OK;
 }
