@@ -433,11 +433,15 @@ struct CompactArgs
   int32_t         lwell_in;
   uint8_t        *out;
   unsigned long long *ticket;
+  const int32_t  *ovf;            // a stream outgrew its scratch room: nothing to move, the host takes the exact route
+  int64_t         cap;            // room at out: a larger image is an error the host reports, nothing is written
 };
 
 __global__ void __launch_bounds__(256)
 k_qv_compact(CompactArgs a)
 { const int lane = threadIdx.x & 31;
+  // launched before the host has seen the total (one round trip less): the same two tests here
+  if (*a.ovf != 0 || a.off[a.ent.n] > a.cap) return;
   const int64_t nunits = a.ent.n * 5;
   unsigned long long next = 0;
   if (lane == 0) next = atomicAdd(a.ticket,1ull);
@@ -559,21 +563,31 @@ int dxk_qv_encode(dx_ctx *ctx, const uint8_t *d_text, size_t text_n, QvEntries e
       DX_PROF_BEGIN(ctx); k_qv_code<2><<<grid,kEncThreads,smem1,ctx->stream>>>(b);
       DX_LAUNCHED(ctx,"k_qv_emit");
       if ((rc = entry_offsets()) != DX_OK) return rc;
-      int32_t ovf = 0;
-      DX_CUDA(ctx,cudaMemcpyAsync(&total,d_off+n,8,cudaMemcpyDeviceToHost,ctx->stream));
-      DX_CUDA(ctx,cudaMemcpyAsync(&lastw,ent.well+(n-1),4,cudaMemcpyDeviceToHost,ctx->stream));
-      DX_CUDA(ctx,cudaMemcpyAsync(&ovf,d_ovf,4,cudaMemcpyDeviceToHost,ctx->stream));
+      struct Res { int64_t total; int32_t lastw, ovf; };
+      Res *hr = (Res *) dx_hpin_get(ctx,sizeof(Res));
+      if (hr == NULL) return DX_E_NOMEM;
+      CompactArgs c;
+      c.scratch = d_scratch; c.scratch_end16 = d_scratch + sbytes - 16;
+      c.ent = ent; c.bytes = d_bytes; c.off = d_off; c.lwell_in = lwell_in; c.out = d_out;
+      c.ticket = d_ticket2 + 1; c.ovf = d_ovf; c.cap = (int64_t) cap;
+      DX_PROF_BEGIN(ctx); k_qv_compact<<<ctx->sm_count*8,256,0,ctx->stream>>>(c);
+      DX_LAUNCHED(ctx,"k_qv_compact");
+      DX_CUDA(ctx,cudaMemcpyAsync(&hr->total,d_off+n,8,cudaMemcpyDeviceToHost,ctx->stream));
+      DX_CUDA(ctx,cudaMemcpyAsync(&hr->lastw,ent.well+(n-1),4,cudaMemcpyDeviceToHost,ctx->stream));
+      DX_CUDA(ctx,cudaMemcpyAsync(&hr->ovf,d_ovf,4,cudaMemcpyDeviceToHost,ctx->stream));
+      if (h_entry_off != NULL && max_entries >= n)
+        DX_CUDA(ctx,cudaMemcpyAsync(h_entry_off,d_off,(size_t) (n+1)*8,cudaMemcpyDeviceToHost,ctx->stream));
       DX_CUDA(ctx,cudaStreamSynchronize(ctx->stream));
-      if (!ovf)
+      total = hr->total; lastw = hr->lastw;
+      if (!hr->ovf)
         { if ((size_t) total > cap)
             return dx_fail_cap(ctx,(size_t) (total),cap);
-          CompactArgs c;
-          c.scratch = d_scratch; c.scratch_end16 = d_scratch + sbytes - 16;
-          c.ent = ent; c.bytes = d_bytes; c.off = d_off; c.lwell_in = lwell_in; c.out = d_out;
-          c.ticket = d_ticket2 + 1;
-          DX_PROF_BEGIN(ctx); k_qv_compact<<<ctx->sm_count*8,256,0,ctx->stream>>>(c);
-          DX_LAUNCHED(ctx,"k_qv_compact");
           done = true;
+          if (h_entry_off != NULL && max_entries >= n)     // everything is on the host already
+            { *out_len = (size_t) total;
+              if (last_well) *last_well = lastw;
+              return DX_OK;
+            }
         }
     }
   if (!done)

@@ -233,7 +233,8 @@ def test_stream_that_outgrows_its_scratch_room(ctx, orc):
     ctx.profile(True); ctx.profile_report()
     assert ctx.dexqv(text) == enc
     prof = ctx.profile_report(); ctx.profile(False)
-    assert "k_qv_size" in prof and "k_qv_compact" not in prof, sorted(prof)
+    # (k_qv_compact is launched before the host has seen the overflow flag and returns at once)
+    assert "k_qv_size" in prof and prof["k_qv_emit"][0] == 2, sorted(prof)
     assert ctx.undexqv(enc) == text
 
 
