@@ -474,10 +474,20 @@ __device__ __noinline__ void write_tags(const Dec5Args &a, const uint8_t *del, c
       if (cnt > 0)
         { if (a.delchar < 0) m = (1u << cnt) - 1u;
           else
-            { uint32_t d[4] = { 0, 0, 0, 0 };
-              for (int k = 0; k < cnt; k++)
-                d[k >> 2] |= (uint32_t) __ldcg(del + p + k) << (8*(k & 3));
-              m = ~dx_eq_mask16(make_uint4(d[0],d[1],d[2],d[3]),(uint32_t) a.delchar) & ((1u << cnt) - 1u);
+            { // the lane's 16 bytes of the del line (any alignment) from five aligned words; only words
+              // that hold a byte of the line are read (the last of them ends at most three bytes
+              // behind it: the newline and the tag line are there)
+              const uintptr_t A = reinterpret_cast<uintptr_t>(del + p);
+              const uint32_t *al = reinterpret_cast<const uint32_t *>(A & ~(uintptr_t) 3);
+              const uint32_t *endw = reinterpret_cast<const uint32_t *>(
+                                       (reinterpret_cast<uintptr_t>(del + rlen) + 3) & ~(uintptr_t) 3);
+              const uint32_t sh = (uint32_t) (A & 3) * 8;
+              uint32_t x[5];
+#pragma unroll
+              for (int k = 0; k < 5; k++) x[k] = (al + k < endw) ? __ldcg(al + k) : 0u;
+              const uint4 d = make_uint4(__funnelshift_r(x[0],x[1],sh),__funnelshift_r(x[1],x[2],sh),
+                                         __funnelshift_r(x[2],x[3],sh),__funnelshift_r(x[3],x[4],sh));
+              m = ~dx_eq_mask16(d,(uint32_t) a.delchar) & ((1u << cnt) - 1u);
             }
         }
       const uint32_t c = __popc(m);
