@@ -1921,9 +1921,9 @@ static int undexqv_fast(dx_ctx *ctx, const uint8_t *d_in, size_t n, int upper, u
     return DX_E_NOMEM;
   if ((rc = dxk_qv_cand_prep(ctx,d_in,n,first,d_q,nc,4,minbits,pa,d_tlen,d_limit,d_ffrun,d_last)) != DX_OK) return rc;
   if ((rc = dxk_scan_u32(ctx,d_tlen,nc,d_toff)) != DX_OK) return rc;
-  // The layout of the text IF the entries are exactly the candidates that are not within 13 bytes of a
-  // later one (fields that overlap: k_qv_direct_prep) and every well delta is below 255 (no 0xff
-  // delta bytes; true of real data, where consecutive wells are a few holes apart): wells and text
+  // The layout of the text IF the entries are exactly the candidates k_qv_direct_prep keeps (not within
+  // 13 bytes of a later one, fields in the range of real headers) and every well delta but the first is below 255
+  // (no 0xff delta bytes; true of real data, where consecutive wells are a few holes apart): wells and text
   // offsets are then prefix sums over the candidates, and the decoder can write headers and lines
   // straight into place.  The chain below still decides; when it disagrees the lines are decoded
   // again into a scratch image and moved (k_qv_assemble), as if nothing had been assumed.
@@ -1934,8 +1934,9 @@ static int undexqv_fast(dx_ctx *ctx, const uint8_t *d_in, size_t n, int upper, u
   QvDecEntry *d_ent = (QvDecEntry *) dx_arena_get(ctx,(N+1)*sizeof(QvDecEntry));
   int32_t *d_rlen_d = (int32_t *) dx_arena_get(ctx,N*4 + 4);   // rlen, -1 for candidates outside that layout
   int32_t *d_flag2 = d_flag + 2;                        // unusable length in some candidate
-  if (!d_wpre || !d_opre || !d_len || !d_well || !d_ent || !d_rlen_d) return DX_E_NOMEM;
-  if ((rc = dxk_qv_direct_prep(ctx,d_q,nc,pa,d_rlen_d)) != DX_OK) return rc;
+  uint8_t *d_keep = (uint8_t *) dx_arena_get(ctx,N + 4);         // 1: part of that layout
+  if (!d_wpre || !d_opre || !d_len || !d_well || !d_ent || !d_rlen_d || !d_keep) return DX_E_NOMEM;
+  if ((rc = dxk_qv_direct_prep(ctx,d_q,nc,pa,d_rlen_d,d_keep)) != DX_OK) return rc;
   if ((rc = dxk_scan_u32(ctx,pa.delta,nc,d_wpre)) != DX_OK) return rc;
   if ((rc = dxk_qv_text_len(ctx,nc,NULL,pa,d_wpre,NULL,well_in,plen,d_len,d_well,d_flag2,d_rlen_d)) != DX_OK) return rc;
   if ((rc = dxk_scan_u32(ctx,d_len,nc,d_opre)) != DX_OK) return rc;
@@ -1950,8 +1951,10 @@ static int undexqv_fast(dx_ctx *ctx, const uint8_t *d_in, size_t n, int upper, u
   int32_t *h_cand  = (int32_t *) dx_hpin_get(ctx,N*4);
   int32_t *h_well  = (int32_t *) dx_hpin_get(ctx,N*4);
   int64_t *h_tot   = (int64_t *) dx_hpin_get(ctx,16);
-  if (!h_q || !h_ffrun || !h_last || !h_rlen || !h_order || !h_soff || !h_stat || !h_cand || !h_well || !h_tot)
+  uint8_t *h_keep  = (uint8_t *) dx_hpin_get(ctx,N);
+  if (!h_q || !h_ffrun || !h_last || !h_rlen || !h_order || !h_soff || !h_stat || !h_cand || !h_well || !h_tot || !h_keep)
     return DX_E_NOMEM;
+  DX_CUDA(ctx,cudaMemcpyAsync(h_keep,d_keep,N,cudaMemcpyDeviceToHost,ctx->stream));
   DX_CUDA(ctx,cudaMemcpyAsync(h_q,d_q,N*8,cudaMemcpyDeviceToHost,ctx->stream));
   DX_CUDA(ctx,cudaMemcpyAsync(h_ffrun,d_ffrun,N*4,cudaMemcpyDeviceToHost,ctx->stream));
   DX_CUDA(ctx,cudaMemcpyAsync(h_last,d_last,N,cudaMemcpyDeviceToHost,ctx->stream));
@@ -1987,7 +1990,7 @@ static int undexqv_fast(dx_ctx *ctx, const uint8_t *d_in, size_t n, int upper, u
       int32_t *h_chk = (int32_t *) dx_hpin_get(ctx,8);
       if (!d_chk || !h_chk) return DX_E_NOMEM;
       DX_CUDA(ctx,cudaMemsetAsync(d_chk,0,8,ctx->stream));
-      if ((rc = dxk_qv_chain_check(ctx,d_q,nc,d_rlen_d,d_stat,d_soff,d_last,first,n,d_chk)) != DX_OK) return rc;
+      if ((rc = dxk_qv_chain_check(ctx,d_q,nc,d_keep,d_rlen_d,d_stat,d_soff,d_last,d_ffrun,first,n,d_chk)) != DX_OK) return rc;
       DX_CUDA(ctx,cudaMemcpyAsync(h_chk,d_chk,8,cudaMemcpyDeviceToHost,ctx->stream));
       DX_CUDA(ctx,cudaStreamSynchronize(ctx->stream));
       ph.mark("decode");
@@ -2010,7 +2013,7 @@ static int undexqv_fast(dx_ctx *ctx, const uint8_t *d_in, size_t n, int upper, u
   // the previous entry and its fields are 0xff ... 0xff, d with d != 0xff
   size_t M = 0, kept = 0;
   bool as_assumed = true;                 // the entries are the candidates of the assumed layout, with its deltas
-  auto in_layout = [&](size_t i) -> bool { return !(i + 1 < N && h_q[i+1] - h_q[i] < 13); };
+  auto in_layout = [&](size_t i) -> bool { return h_keep[i] != 0; };
   for (size_t i = 0; i < N; i++) kept += in_layout(i);
   { int64_t cur = (int64_t) first;
     int32_t well = well_in;
@@ -2023,7 +2026,14 @@ static int undexqv_fast(dx_ctx *ctx, const uint8_t *d_in, size_t n, int upper, u
         if (gap > h_ffrun[i] || h_last[i] == 0xff) return DX_OK;
         const int64_t end = h_soff[6*i + 5];
         if (end > (int64_t) n || end <= cur) return DX_OK;
-        if (!in_layout(i) || gap != 0) as_assumed = false;
+        if (!in_layout(i) || (gap != 0 && !(M == 0 && gap == h_ffrun[i])))
+          { if (as_assumed && ctx->route[DXR_DEBUG])
+              fprintf(stderr,"[dexb200 debug] undexqv: entry %zu = candidate %zu at %lld is not as assumed: in layout %d, "
+                             "gap %lld, 0xff run %d, next candidate %lld bytes on, rlen %d\n",M,i,(long long) h_q[i],
+                      (int) in_layout(i),(long long) gap,h_ffrun[i],
+                      (long long) (i + 1 < N ? h_q[i+1] - h_q[i] : -1),h_rlen[i]);
+            as_assumed = false;
+          }
         well += 255 * (int32_t) gap + h_last[i];
         h_cand[M] = (int32_t) i; h_well[M] = well; M++;
         cur = end;

@@ -242,9 +242,11 @@ int dxk_qv_cand_prep(dx_ctx *ctx, const uint8_t *d_in, size_t n, size_t first, c
 int dxk_qv_text_len(dx_ctx *ctx, int64_t count, const int32_t *d_cand, QvPlanArrays pa, const int64_t *d_wpre,
                     const int32_t *d_wells, int32_t well_in, int plen, uint32_t *d_len, int32_t *d_well_out,
                     int32_t *d_flag, const int32_t *d_sel = NULL);
-int dxk_qv_direct_prep(dx_ctx *ctx, const int64_t *d_q, int64_t count, QvPlanArrays pa, int32_t *d_rlen_d);
-int dxk_qv_chain_check(dx_ctx *ctx, const int64_t *d_q, int64_t count, const int32_t *d_rlen_d, const int32_t *d_stat,
-                       const int64_t *d_soff, const uint8_t *d_last, size_t first, size_t n, int32_t *d_flag);
+int dxk_qv_direct_prep(dx_ctx *ctx, const int64_t *d_q, int64_t count, QvPlanArrays pa, int32_t *d_rlen_d,
+                       uint8_t *d_keep);
+int dxk_qv_chain_check(dx_ctx *ctx, const int64_t *d_q, int64_t count, const uint8_t *d_keep, const int32_t *d_rlen_d,
+                       const int32_t *d_stat, const int64_t *d_soff, const uint8_t *d_last, const int32_t *d_ffrun,
+                       size_t first, size_t n, int32_t *d_flag);
 int dxk_qv_build_ent(dx_ctx *ctx, int64_t count, const int32_t *d_cand, QvPlanArrays pa, const int32_t *d_well,
                      const int64_t *d_opre, const uint32_t *d_len, const int64_t *d_toff, QvDecEntry *d_ent,
                      int64_t *d_src, int64_t *d_fs_out, int32_t *d_rlen_out);

@@ -70,6 +70,9 @@ __global__ void k_qv_cand_prep(const uint8_t *in, int64_t n, int64_t first, cons
       // code word and 0xff for one entry in 200): the usual case, in which the text can be decoded
       // straight into place, see undexqv_fast
       pa.delta[i] = in[p];
+      // (the 0xff bytes in front of the FIRST entry of the image have no stream to belong to: a shard
+      //  of a larger file starts with the delta against its predecessor's last well, which can be large)
+      if (r > 0 && p - r == first) pa.delta[i] += 255u * (uint32_t) r;
     }
   // limit: the fields of the span-th candidate after this one, counting only candidates at least
   // 64 bytes after the previously counted one
@@ -104,38 +107,44 @@ __global__ void k_qv_text_len(int64_t count, const int32_t *cand, QvPlanArrays p
   well_out[m] = well;
 }
 
-// The layout of the text if every candidate is an entry (undexqv_fast): of candidates whose fields
-// overlap (closer than 13 bytes -- an entry before a short read has a look-alike one byte earlier,
-// whose fields are the true ones shifted by 8 bits) only the last can be that entry; the others
-// leave the layout: no text, no well delta, not decoded.
-__global__ void k_qv_direct_prep(const int64_t *q, int64_t count, QvPlanArrays pa, int32_t *rlen_d)
+// The layout of the text IF the entries are the candidates kept here (undexqv_fast).  Dropped:
+//   * of candidates whose fields overlap (closer than 13 bytes: the second subread of a well, delta
+//     0 behind zero padding, has look-alikes 4 and 8 bytes in front of it whose fields are the true
+//     ones shifted by one or two words) all but the last -- two entries can never be that close;
+//   * candidates outside what real headers hold (region score 0..1000, bax.c:347; a read starting
+//     within the first 16 M bases of its well): the index's filter is wide on purpose (beg < 2^27,
+//     qv < 2^16 -- about one hit per 2 GB file in the middle of stream data), this one is not.
+// A dropped candidate leaves the layout: no text, no well delta, not decoded.  A true entry dropped
+// here only sends the call down the scratch-image form.
+__global__ void k_qv_direct_prep(const int64_t *q, int64_t count, QvPlanArrays pa, int32_t *rlen_d, uint8_t *keep)
 { const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= count) return;
-  const bool dropped = (i + 1 < count && q[i+1] - q[i] < 13);
-  rlen_d[i] = dropped ? -1 : pa.rlen[i];
-  if (dropped) pa.delta[i] = 0;
+  const bool kept = !(i + 1 < count && q[i+1] - q[i] < 13) &&
+                    (uint32_t) pa.qv[i] <= 1000u && (uint32_t) pa.beg[i] < (1u << 24);
+  keep[i] = kept ? 1 : 0;
+  rlen_d[i] = kept ? pa.rlen[i] : -1;
+  if (!kept) pa.delta[i] = 0;
 }
 
 // ... and the check that the decode confirmed that layout (the host's chain walk, undexqv_fast, as a
 // predicate over independent candidates): the first kept candidate's terminator byte is the first
-// byte after the coding header, every kept candidate decoded cleanly, has a terminator below 0xff
+// byte after the coding header (or only 0xff bytes lie between), every kept candidate decoded cleanly, has a terminator below 0xff
 // and ends exactly where the terminator of the next kept candidate stands (no 0xff delta bytes),
 // the last one ends at the end of the image.  flag[0] = 1 on any violation; flag[1] += kept.
-__global__ void k_qv_chain_check(const int64_t *q, int64_t count, const int32_t *rlen_d, const int32_t *stat,
-                                 const int64_t *soff, const uint8_t *last, int64_t first, int64_t n, int32_t *flag)
+__global__ void k_qv_chain_check(const int64_t *q, int64_t count, const uint8_t *keep, const int32_t *rlen_d,
+                                 const int32_t *stat, const int64_t *soff, const uint8_t *last, const int32_t *ffrun,
+                                 int64_t first, int64_t n, int32_t *flag)
 { const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= count) return;
-  const bool kept = !(i + 1 < count && q[i+1] - q[i] < 13);
-  if (!kept) return;
+  if (i >= count || !keep[i]) return;
   atomicAdd(flag + 1,1);
   bool ok = (rlen_d[i] >= 0 && stat[i] == 0 && last[i] != 0xff);
   int64_t j = i + 1;                                    // next kept candidate
-  while (j < count && (j + 1 < count && q[j+1] - q[j] < 13)) j++;
+  while (j < count && !keep[j]) j++;
   const int64_t end = soff[6*i + 5];
   ok = ok && (end == ((j < count) ? q[j] - 1 : n));
   { int64_t k = i - 1;                                  // the first kept one? (only dropped ones in front:
-    while (k >= 0 && (q[k+1] - q[k] < 13)) k--;         //  the walk ends at once everywhere else)
-    if (k < 0) ok = ok && (q[i] - 1 == first);
+    while (k >= 0 && !keep[k]) k--;                     //  the walk ends at once everywhere else)
+    if (k < 0) ok = ok && (q[i] - 1 - first == 0 || q[i] - 1 - first == (int64_t) ffrun[i]);   // 0xff bytes only
   }
   if (!ok) atomicExch(flag,1);
 }
@@ -188,10 +197,11 @@ int dxk_qv_text_len(dx_ctx *ctx, int64_t count, const int32_t *d_cand, QvPlanArr
   return DX_OK;
 }
 
-int dxk_qv_direct_prep(dx_ctx *ctx, const int64_t *d_q, int64_t count, QvPlanArrays pa, int32_t *d_rlen_d)
+int dxk_qv_direct_prep(dx_ctx *ctx, const int64_t *d_q, int64_t count, QvPlanArrays pa, int32_t *d_rlen_d,
+                       uint8_t *d_keep)
 { if (count == 0) return DX_OK;
   DX_PROF_BEGIN(ctx);
-  k_qv_direct_prep<<<(unsigned) ((count+255)/256),256,0,ctx->stream>>>(d_q,count,pa,d_rlen_d);
+  k_qv_direct_prep<<<(unsigned) ((count+255)/256),256,0,ctx->stream>>>(d_q,count,pa,d_rlen_d,d_keep);
   DX_LAUNCHED(ctx,"k_qv_direct_prep");
   return DX_OK;
 }
@@ -207,11 +217,12 @@ int dxk_qv_build_ent(dx_ctx *ctx, int64_t count, const int32_t *d_cand, QvPlanAr
   return DX_OK;
 }
 
-int dxk_qv_chain_check(dx_ctx *ctx, const int64_t *d_q, int64_t count, const int32_t *d_rlen_d, const int32_t *d_stat,
-                       const int64_t *d_soff, const uint8_t *d_last, size_t first, size_t n, int32_t *d_flag)
+int dxk_qv_chain_check(dx_ctx *ctx, const int64_t *d_q, int64_t count, const uint8_t *d_keep, const int32_t *d_rlen_d,
+                       const int32_t *d_stat, const int64_t *d_soff, const uint8_t *d_last, const int32_t *d_ffrun,
+                       size_t first, size_t n, int32_t *d_flag)
 { if (count == 0) return DX_OK;
   DX_PROF_BEGIN(ctx);
-  k_qv_chain_check<<<(unsigned) ((count+255)/256),256,0,ctx->stream>>>(d_q,count,d_rlen_d,d_stat,d_soff,d_last,
+  k_qv_chain_check<<<(unsigned) ((count+255)/256),256,0,ctx->stream>>>(d_q,count,d_keep,d_rlen_d,d_stat,d_soff,d_last,d_ffrun,
                                                                       (int64_t) first,(int64_t) n,d_flag);
   DX_LAUNCHED(ctx,"k_qv_chain_check");
   return DX_OK;

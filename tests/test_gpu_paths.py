@@ -7,6 +7,7 @@ import numpy as np
 import pytest
 
 import dextractor_b200 as dx
+from dextractor_b200 import lib as dxl
 from dextractor_b200 import synth
 from tests import cases
 from tests.test_gpu_parity import first_diff
@@ -393,3 +394,41 @@ def test_run_histogram_counting_modes(ctx, orc, mode):
             assert [x + 1 for x in st.hist[5]] == list(ref.subrun), i
     finally:
         ctx.route("default")
+
+
+def test_a_shard_that_starts_far_behind_its_predecessor_decodes_in_place(ctx, orc):
+    """A shard's image starts with the delta of its first well against the predecessor's last well:
+    thousands of 0xff bytes when the wells are far apart (bench.py gives every rank its own well
+    range).  Those bytes can only be delta bytes -- there is no stream in front of them -- so the
+    in-place form of the discovered decode must take them in its stride: one decode launch, no
+    k_qv_assemble, and the text of the shard with the right well numbers."""
+    import torch
+    rng = np.random.default_rng(31)
+    lengths = [int(x) for x in rng.integers(300, 6000, size=120)]
+    text = synth.make_quiva(31, lengths)
+    # move every well up by 2 000 000: the first delta (against well_in = 7) is 7 843 x 0xff + one byte
+    lines = text.split(b"\n")
+    for e in range(len(lengths)):
+        f = lines[6 * e].split(b"/")
+        f[1] = str(int(f[1]) + 2_000_000).encode()
+        lines[6 * e] = b"/".join(f)
+    text = b"\n".join(lines)
+    t = torch.frombuffer(bytearray(text), dtype=torch.uint8).cuda()
+    st = ctx.qv_scan_dev(t.data_ptr(), len(text))
+    cd = dxl.make_coding(st, False)
+    hdr = b"\xaa\x55" + dxl.write_coding(cd, text[: text.index(b"/", 1)])
+    enc = torch.zeros(len(text) + 65536, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    ctx.h2d(enc.data_ptr(), hdr)
+    body, lastw, _ = ctx.qv_encode_dev(t.data_ptr(), len(text), cd, False, 7, enc.data_ptr() + len(hdr),
+                                       enc.numel() - len(hdr))
+    n = len(hdr) + body
+    img = enc[:n].cpu().numpy().tobytes()
+    assert img[len(hdr): len(hdr) + 7000] == b"\xff" * 7000
+    back = torch.zeros(len(text) + 64, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    ctx.profile(True); ctx.profile_report()
+    m = ctx.undexqv_dev(enc.data_ptr(), n, False, back.data_ptr(), back.numel(), well_in=7)
+    prof = ctx.profile_report(); ctx.profile(False)
+    assert back[:m].cpu().numpy().tobytes() == text
+    assert "k_qv_assemble" not in prof and prof["k_qv_decode5_spec"][0] == 1, sorted(prof)
