@@ -664,6 +664,12 @@ def run_ours(args, env=None, out=print):
             t_d = timed(dec2)
             sweep[name] = {"entries": int(ne), "bytes": int(Us), "dexqv_gbs": Us / (t_e * 1e-3) / GB,
                            "undexqv_discovered_gbs": Us / (t_d * 1e-3) / GB}
+            if not args.no_cpu:                      # the whole 0.5 GB image against the reference tool's
+                want, kind = env.reference_dexqv(env.host_bytes(tx))
+                same = (env.host_bytes(e2[: st2["n"]]) == want)
+                sweep[name].update(checker=kind, equal=bool(same))
+                assert same, f"length sweep {name}: the image differs from the {kind}'s"
+                del want
             del tx, e2, b2
             env.free_cached()
         extras["length_sweep"] = sweep

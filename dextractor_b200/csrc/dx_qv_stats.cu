@@ -284,7 +284,10 @@ constexpr int kRunWarpWords = 512 + kHistQueue;          // histogram (256 symbo
 //           batch, not the adds, were what the warps waited for; three CTAs per SM made it slower);
 //   mode 2: match for the symbol, atomics for the run length (0.85 ms);  mode 3: the other way round
 //           (0.83 ms);  mode 4 does not come here: no queue, see the kernel (0.73 ms).
-// With atomics the kernel retires ~1.5 atomic lanes per clock and SM, the rate of the unit.
+// With atomics the kernel retires ~1.5 atomic lanes per clock and SM, the rate of the unit.  Counting
+// the items the way k_qv_hist<plain> counts bytes -- 256 thread-private one-byte counters, no queue,
+// 768 threads -- was measured too: 1.09 ms (a load / add / store chain per item inside a loop whose
+// length differs from lane to lane); not kept.
 __device__ __forceinline__ void warp_count2(uint32_t *hist, uint32_t key, uint32_t key2, bool two,
                                             uint32_t n, int lane, int mode)
 { const bool m1 = (mode == 1 || mode == 2), m2 = (mode == 1 || mode == 3);

@@ -1,4 +1,4 @@
-"""The bench line the driver parses: checks the committed B200 lines (profiles/r01_bench_n*.json,
+"""The bench line the driver parses: checks the committed B200 lines (profiles/r0?_bench_n*.json,
 written by bench.py on the GPU box) against the contract -- keys, units, and the arithmetic that ties
 value, ms_per_step and the roofline object together."""
 import glob
@@ -8,7 +8,7 @@ import os
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LINES = sorted(glob.glob(os.path.join(ROOT, "profiles", "r01_bench_n[0-9].json")))
+LINES = sorted(glob.glob(os.path.join(ROOT, "profiles", "r0[0-9]_bench_n[0-9].json")))
 
 
 @pytest.mark.parametrize("path", LINES, ids=[os.path.basename(p) for p in LINES])
@@ -37,8 +37,17 @@ def test_committed_bench_line_follows_the_contract(path):
     if d["n_gpus"] == 1:
         c = d["cpu_baseline"]
         assert c["kind"] in ("reference", "port") and c["cores"] >= 1 and c["value"] > 0 and c["sample"]
+    if os.path.basename(path).startswith("r02"):
+        # round 2: the traffic figure names its source, the sharded path was checked against the reference
+        # tool before timing, and both arms print the same config object
+        assert r["traffic"] is None or r["traffic_source"]
+        assert d["extra"]["sharded_parity"]["equal"] is True and d["extra"]["sharded_parity"]["round_trip"] is True
+        ref = json.load(open(os.path.join(ROOT, "profiles", "r02_bench_reference_arm.json")))
+        if d["n_gpus"] == 1:
+            assert ref["config"] == d["config"] and ref["metric"] == d["metric"] and ref["unit"] == d["unit"]
 
 
-def test_reference_arm_line_is_committed():
-    d = json.load(open(os.path.join(ROOT, "profiles", "r01_bench_reference_arm.json")))
+@pytest.mark.parametrize("tag", ["r01", "r02"])
+def test_reference_arm_line_is_committed(tag):
+    d = json.load(open(os.path.join(ROOT, "profiles", f"{tag}_bench_reference_arm.json")))
     assert d["impl"] == "reference" and d["unit"] == "GB/s" and d["value"] > 0
