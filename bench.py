@@ -55,11 +55,16 @@ class ClockSampler:
     inside the timed region are reported, or (region shorter than the sampling period) the ones
     since the start of the warm-up, i.e. under the same load."""
 
-    def __init__(self, index):
-        self.rows, self.proc, self.index = [], None, index
+    def __init__(self, index, enabled=True):
+        # index: one GPU, or a comma-separated list (rank 0 of a multi-GPU run samples every GPU of the
+        # job with ONE nvidia-smi; a sampler per rank made eight NVML clients poll the driver at once
+        # and stretched the 8-GPU step by over a millisecond)
+        self.rows, self.proc, self.index, self.enabled = [], None, index, enabled
         self.t0 = self.t1 = None
 
     def start(self):
+        if not self.enabled:
+            return
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
@@ -82,6 +87,8 @@ class ClockSampler:
         self.t1 = time.time()
 
     def stop(self):
+        if not self.enabled:
+            return None
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         if self.t1 is None:
@@ -104,8 +111,9 @@ class ClockSampler:
             except Exception:
                 pass
         sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None,
-                "samples": len(sm), "window": window, "reasons": sorted(reasons)}
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_min_mhz": sm[0] if sm else None,
+                "sm_max_mhz": mx or None, "samples": len(sm), "gpus": self.index, "window": window,
+                "reasons": sorted(reasons)}
 
 
 def workload_config(args):
@@ -295,7 +303,7 @@ class CudaEnv:
         self.torch, self.dx = torch, dx
         torch.cuda.set_device(local)
         self.dev = torch.device("cuda", local)
-        self.local = local
+        self.local, self.world = local, world
         if world > 1:
             import torch.distributed as dist
             # stdout carries ONE JSON line: keep NCCL's own banner out of it
@@ -347,7 +355,10 @@ class CudaEnv:
         return a.elapsed_time(b)
 
     def clock_sampler(self):
-        return ClockSampler(self.local)
+        # one sampler per JOB: rank 0 watches every GPU of the job (ranks = local GPUs 0..N-1 on one node)
+        if self.world > 1:
+            return ClockSampler(",".join(str(i) for i in range(self.world)), enabled=(self.local == 0))
+        return ClockSampler(str(self.local))
 
     def reference_dexqv(self, text: bytes):
         """the checker (never timed here): the reference's dexqv, else the oracle port"""
