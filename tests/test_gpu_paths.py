@@ -432,3 +432,37 @@ def test_a_shard_that_starts_far_behind_its_predecessor_decodes_in_place(ctx, or
     prof = ctx.profile_report(); ctx.profile(False)
     assert back[:m].cpu().numpy().tobytes() == text
     assert "k_qv_assemble" not in prof and prof["k_qv_decode5_spec"][0] == 1, sorted(prof)
+
+
+def test_headers_outside_the_usual_range_still_decode(ctx, orc):
+    """The in-place form of the discovered decode lays the text out for candidates whose fields look
+    like real headers (region score <= 1000, start below 16 M).  Nothing in the format says so: an
+    entry with RQ=0.2000, one starting at base 20 000 000 and one with a six-digit score must come
+    out exactly as the reference writes them (the call takes the scratch-image form for this file)."""
+    rng = np.random.default_rng(41)
+    lengths = [int(x) for x in rng.integers(200, 5000, size=90)]
+    text = synth.make_quiva(41, lengths)
+    lines = text.split(b"\n")
+
+    def rewrite(e, beg=None, qv=None):
+        f = lines[6 * e].split(b"/")
+        span, rq = f[2].split(b" RQ=0.")
+        b0, e0 = (int(x) for x in span.split(b"_"))
+        if beg is not None:
+            e0, b0 = beg + (e0 - b0), beg
+        if qv is not None:
+            rq = str(qv).encode()
+        f[2] = b"%d_%d RQ=0.%s" % (b0, e0, rq)
+        lines[6 * e] = b"/".join(f)
+
+    rewrite(7, qv=2000)
+    rewrite(30, beg=20_000_000)
+    rewrite(55, qv=654321)
+    text = b"\n".join(lines)
+    enc = orc.dexqv(text)
+    assert ctx.dexqv(text) == enc
+    ctx.profile(True); ctx.profile_report()
+    back = ctx.undexqv(enc)
+    prof = ctx.profile_report(); ctx.profile(False)
+    assert back == orc.undexqv(enc) == text
+    assert "k_qv_assemble" in prof, sorted(prof)          # not in place: the layout did not hold
