@@ -257,7 +257,7 @@ extern "C" void       *dx_stream(dx_ctx *ctx) { return ctx ? (void *) ctx->strea
 extern "C" int dx_route(dx_ctx *ctx, const char *name, int64_t value)
 { static const char *names[DXR_COUNT] = { "no_fast", "no_spec", "exact_index", "exact_pack", "pack2", "two_pass",
                                           "chain_scan", "decoder", "lane_max_rlen", "lane_min_entries", "debug",
-                                          "serial_io", "pipe_chunk", "no_direct", "hist_mode" };
+                                          "serial_io", "pipe_chunk", "no_direct", "index_bulk", "hist_mode" };
   if (ctx == NULL || name == NULL) return DX_E_ARG;
   if (strcmp(name,"default") == 0)
     { const int64_t dbg = ctx->route[DXR_DEBUG];

@@ -467,6 +467,84 @@ k_pred_slots(const uint8_t *buf, size_t n, size_t first, uint32_t *tile_count, i
     }
 }
 
+// ---- the same pass with TMA bulk copies (an experiment, route "index_bulk") ----------------------
+// One elected thread per CTA moves whole 16 KB tiles global -> shared with cp.async.bulk and an
+// mbarrier (UBLKCP in the SASS), two tiles in flight, every thread then reads its four chunks from
+// shared memory.  This takes the LDG instructions and their address arithmetic off the 256 threads
+// and hands the data movement to the copy engine of the SM -- what the round-1 verdict asked to try.
+// Measured on the 2 GB text (profiles/r02_tma_experiment.txt): see there; the LDG form above already
+// runs at the measured HBM peak, which is the most a different way of fetching the same bytes can do.
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{ asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory"); }
+
+__device__ __forceinline__ void bulk_load(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{ asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{ asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\t"
+               "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+               "@!p bra WAIT_%=;\n\t}" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+template <int PRED>
+__global__ void __launch_bounds__(kTileThreads)
+k_pred_slots_bulk(const uint8_t *buf, size_t n, size_t first, int64_t ntiles, uint32_t *tile_count, int64_t *slots,
+                  int32_t *overflow)
+{ extern __shared__ __align__(128) uint8_t dx_bulk_smem[];           // 2 x 16 KB tiles
+  __shared__ uint64_t bar[2];
+  __shared__ uint32_t cnt;
+  if (threadIdx.x == 0)
+    { mbar_init(&bar[0],1); mbar_init(&bar[1],1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+  __syncthreads();
+  auto tile_bytes = [&](int64_t t) -> uint32_t
+    { const size_t base = (size_t) t * kTileBytes;
+      const size_t left = n - base;
+      return (uint32_t) (((left < (size_t) kTileBytes ? left : (size_t) kTileBytes) + 15) & ~(size_t) 15);
+    };
+  int64_t t = blockIdx.x;
+  if (threadIdx.x == 0 && t < ntiles) bulk_load(dx_bulk_smem,buf + (size_t) t*kTileBytes,tile_bytes(t),&bar[0]);
+  uint32_t phase[2] = { 0, 0 };
+  for (int it = 0; t < ntiles; t += gridDim.x, it++)
+    { const int b = it & 1;
+      const int64_t tn = t + gridDim.x;
+      if (threadIdx.x == 0)
+        { cnt = 0;
+          if (tn < ntiles)                                        // the other buffer was drained an iteration ago
+            bulk_load(dx_bulk_smem + (size_t) (b ^ 1)*kTileBytes,buf + (size_t) tn*kTileBytes,tile_bytes(tn),&bar[b ^ 1]);
+        }
+      mbar_wait(&bar[b],phase[b]); phase[b] ^= 1u;
+      __syncthreads();                                            // cnt = 0 is visible
+      const size_t base = (size_t) t * kTileBytes;
+      const uint4 *tile = reinterpret_cast<const uint4 *>(dx_bulk_smem + (size_t) b*kTileBytes);
+#pragma unroll
+      for (int j = 0; j < kTileChunks; j++)
+        { const size_t at = base + ((size_t) j * kTileThreads + threadIdx.x) * 16;
+          uint32_t hits = (at < n) ? chunk_hits<PRED>(buf,n,first,at,tile[j * kTileThreads + threadIdx.x]) : 0;
+          if (hits)
+            { uint32_t sidx = atomicAdd(&cnt,(uint32_t) __popc(hits));
+              while (hits)
+                { const int i = __ffs(hits) - 1;
+                  hits &= hits - 1;
+                  if (sidx < (uint32_t) kSlot) slots[(size_t) t * kSlot + sidx] = (int64_t) (at + i);
+                  sidx++;
+                }
+            }
+        }
+      __syncthreads();                                            // everybody is done with buffer b and with cnt
+      if (threadIdx.x == 0)
+        { tile_count[t] = cnt;
+          if (cnt > (uint32_t) kSlot) atomicExch(overflow,1);
+        }
+    }
+}
+
 __global__ void k_pred_gather(const uint32_t *tile_count, const int64_t *tile_prefix, const int64_t *slots,
                               int64_t ntiles, int64_t *pos)
 { const int64_t t = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
@@ -497,9 +575,20 @@ int index_positions(dx_ctx *ctx, const uint8_t *buf, size_t n, size_t first,
   if (d_cnt == NULL || d_pre == NULL || d_slot == NULL) return DX_E_NOMEM;
   int32_t *d_over = (int32_t *) (d_cnt + ntiles);
   DX_CUDA(ctx,cudaMemsetAsync(d_over,0,4,ctx->stream));
-  DX_PROF_BEGIN(ctx);
-  k_pred_slots<PRED><<<(unsigned) ntiles,kTileThreads,0,ctx->stream>>>(buf,n,first,d_cnt,d_slot,d_over);
-  DX_LAUNCHED(ctx,"k_pred_slots");
+  if (PRED == DX_PRED_NEWLINE && ctx->route[DXR_INDEX_BULK])
+    { const size_t smem = 2*(size_t) kTileBytes;
+      DX_CUDA(ctx,cudaFuncSetAttribute(k_pred_slots_bulk<PRED>,cudaFuncAttributeMaxDynamicSharedMemorySize,(int) smem));
+      int64_t grid = (int64_t) ctx->sm_count * (ctx->route[DXR_INDEX_BULK] > 1 ? ctx->route[DXR_INDEX_BULK] : 4);
+      if (grid > ntiles) grid = ntiles;
+      DX_PROF_BEGIN(ctx);
+      k_pred_slots_bulk<PRED><<<(unsigned) grid,kTileThreads,smem,ctx->stream>>>(buf,n,first,ntiles,d_cnt,d_slot,d_over);
+      DX_LAUNCHED(ctx,"k_pred_slots_bulk");
+    }
+  else
+    { DX_PROF_BEGIN(ctx);
+      k_pred_slots<PRED><<<(unsigned) ntiles,kTileThreads,0,ctx->stream>>>(buf,n,first,d_cnt,d_slot,d_over);
+      DX_LAUNCHED(ctx,"k_pred_slots");
+    }
   { const int rc = launch_scan(ctx,d_cnt,ntiles,d_pre,"k_tile_scan");
     if (rc != DX_OK) return rc;
   }

@@ -85,6 +85,7 @@ enum { DXR_NO_FAST = 0, DXR_NO_SPEC, DXR_EXACT_INDEX, DXR_EXACT_PACK, DXR_PACK2,
        DXR_DEBUG, DXR_SERIAL_IO,
        DXR_PIPE_CHUNK,         // > 0: window size of the pipelined *_host calls in bytes (tests: small files)
        DXR_NO_DIRECT,          // discovered entries: always decode into the scratch image, then assemble
+       DXR_INDEX_BULK,         // newline index with cp.async.bulk tiles (experiment); > 1: CTAs per SM
        DXR_HIST_MODE,          // k_qv_hist_run: 0 shared atomics, 1 match.any groups, 2 / 3 one of each, 4 no queue
        DXR_COUNT };
 

@@ -75,7 +75,8 @@ uint64_t dx_launch_count(dx_ctx *ctx, int reset);
  * "serial_io" (the *_host calls copy, compute, copy without overlap), "pipe_chunk" (window bytes of
  * the pipelined dx_undexqv_host, so that small files take it too), "no_direct" (dx_undexqv_dev with
  * discovered entries decodes into a scratch image and moves the lines, instead of straight into
- * place), "hist_mode" (how k_qv_hist_run counts a batch: 0 shared atomics, 1 match.any groups, 2 / 3
+ * place), "index_bulk" (the newline index fetches its tiles with cp.async.bulk + mbarrier instead of
+ * vector loads: an experiment, value = CTAs per SM), "hist_mode" (how k_qv_hist_run counts a batch: 0 shared atomics, 1 match.any groups, 2 / 3
  * one of each, 4 without the item queue), "debug"; "default" resets all.
  * No reference counterpart; nothing in the library reads the environment inside a call. */
 int dx_route(dx_ctx *ctx, const char *name, int64_t value);

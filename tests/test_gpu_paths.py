@@ -41,6 +41,7 @@ ROUTES = [
     {"lane_max_rlen": 3000},                             # both parallel decoders in one call
     {"decoder": 6, "no_fast": 1},                        # lane-per-entry decoder behind the host-planned path
     {"no_direct": 1},                                    # discovered entries via the scratch image + k_qv_assemble
+    {"index_bulk": 4},                                   # newline index through cp.async.bulk tiles (TMA experiment)
     {"hist_mode": 1},                                    # run-length histograms: match.any groups
     {"hist_mode": 4},                                    # ... without the item queue
 ]
