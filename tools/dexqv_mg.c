@@ -351,8 +351,10 @@ int main(int argc, char *argv[])
       if (o.verbose)
         { double tr = 0, ts = 0, tc = 0, tw = 0; int64_t ne = 0, ob = 0;
           for (k = 0; k < o.world; k++)
-            { if (R[k].t_read > tr) tr = R[k].t_read; if (R[k].t_scan > ts) ts = R[k].t_scan;
-              if (R[k].t_code > tc) tc = R[k].t_code; if (R[k].t_write > tw) tw = R[k].t_write;
+            { if (R[k].t_read > tr)  tr = R[k].t_read;
+              if (R[k].t_scan > ts)  ts = R[k].t_scan;
+              if (R[k].t_code > tc)  tc = R[k].t_code;
+              if (R[k].t_write > tw) tw = R[k].t_write;
               ne += R[k].nent; ob += R[k].obytes;
             }
           fprintf(stderr,"  %lld bytes, %lld entries -> %lld bytes; max over ranks: read+H2D %.3f s, "
