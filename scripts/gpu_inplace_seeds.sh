@@ -1,4 +1,6 @@
 #!/bin/bash
+# six 2 GB bench files of different seeds / well ranges: does the discovered-entry decode hold its assumed
+# layout (decoded in place) on each of them?  Prints the library's debug line per file.
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 DEXB200_DEBUG=1 timeout 600 python - <<'PY' 2>&1 | grep -v "host phases" | tail -30
