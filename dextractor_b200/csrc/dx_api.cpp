@@ -14,6 +14,7 @@
 #include <algorithm>
 #include <chrono>
 #include "dx_internal.h"
+#include "dx_chain.h"
 
 // wall-clock marks of the host phases of a call, printed with DEXB200_DEBUG set
 struct DxPhases
@@ -1994,7 +1995,7 @@ static int undexqv_fast(dx_ctx *ctx, const uint8_t *d_in, size_t n, int upper, u
       DX_CUDA(ctx,cudaMemcpyAsync(h_chk,d_chk,8,cudaMemcpyDeviceToHost,ctx->stream));
       DX_CUDA(ctx,cudaStreamSynchronize(ctx->stream));
       ph.mark("decode");
-      if (h_chk[0] == 0)
+      if (h_chk[0] == 0 && h_chk[1] > 0)             // (no kept candidate at all proves nothing)
         { if (ctx->route[DXR_DEBUG])
             fprintf(stderr,"[dexb200 debug] undexqv: %zu candidates, %d entries, decoded in place (checked on the device)\n",
                     N,h_chk[1]);
@@ -2009,37 +2010,15 @@ static int undexqv_fast(dx_ctx *ctx, const uint8_t *d_in, size_t n, int upper, u
   DX_CUDA(ctx,cudaStreamSynchronize(ctx->stream));
   ph.mark("decode");
 
-  // the chain (see resolve_chain): a candidate is the next entry iff the bytes between the end of
-  // the previous entry and its fields are 0xff ... 0xff, d with d != 0xff
+  // the chain (dx_chain.h): a candidate is the next entry iff the bytes between the end of the previous
+  // entry and its fields are 0xff ... 0xff, d with d != 0xff
   size_t M = 0, kept = 0;
   bool as_assumed = true;                 // the entries are the candidates of the assumed layout, with its deltas
-  auto in_layout = [&](size_t i) -> bool { return h_keep[i] != 0; };
-  for (size_t i = 0; i < N; i++) kept += in_layout(i);
-  { int64_t cur = (int64_t) first;
-    int32_t well = well_in;
-    size_t i = 0;
-    while (cur < (int64_t) n)
-      { while (i < N && h_q[i] - 1 < cur) i++;
-        while (i < N && h_last[i] == 0xff && h_q[i] - 1 - cur <= h_ffrun[i]) i++;
-        if (i >= N || h_stat[i] != 0) return DX_OK;                     // general path
-        const int64_t gap = h_q[i] - 1 - cur;
-        if (gap > h_ffrun[i] || h_last[i] == 0xff) return DX_OK;
-        const int64_t end = h_soff[6*i + 5];
-        if (end > (int64_t) n || end <= cur) return DX_OK;
-        if (!in_layout(i) || (gap != 0 && !(M == 0 && gap == h_ffrun[i])))
-          { if (as_assumed && ctx->route[DXR_DEBUG])
-              fprintf(stderr,"[dexb200 debug] undexqv: entry %zu = candidate %zu at %lld is not as assumed: in layout %d, "
-                             "gap %lld, 0xff run %d, next candidate %lld bytes on, rlen %d\n",M,i,(long long) h_q[i],
-                      (int) in_layout(i),(long long) gap,h_ffrun[i],
-                      (long long) (i + 1 < N ? h_q[i+1] - h_q[i] : -1),h_rlen[i]);
-            as_assumed = false;
-          }
-        well += 255 * (int32_t) gap + h_last[i];
-        h_cand[M] = (int32_t) i; h_well[M] = well; M++;
-        cur = end;
-        i++;
-      }
-    if (M != kept) as_assumed = false;
+  for (size_t i = 0; i < N; i++) kept += (h_keep[i] != 0);
+  { DxChainIn ci = { h_q, h_ffrun, h_last, h_stat, h_soff, h_keep, (int64_t) N, (int64_t) first, (int64_t) n };
+    int64_t m = 0;
+    if (!dx_chain_walk(ci,well_in,h_cand,h_well,&m,&as_assumed)) return DX_OK;          // general path
+    M = (size_t) m;
   }
   ph.mark("chain");
   if (direct && as_assumed)

@@ -8,6 +8,7 @@
 
 #include "dx_internal.h"
 #include "dx_common.cuh"
+#include "dx_chain.h"
 
 namespace {
 
@@ -137,16 +138,8 @@ __global__ void k_qv_chain_check(const int64_t *q, int64_t count, const uint8_t 
 { const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= count || !keep[i]) return;
   atomicAdd(flag + 1,1);
-  bool ok = (rlen_d[i] >= 0 && stat[i] == 0 && last[i] != 0xff);
-  int64_t j = i + 1;                                    // next kept candidate
-  while (j < count && !keep[j]) j++;
-  const int64_t end = soff[6*i + 5];
-  ok = ok && (end == ((j < count) ? q[j] - 1 : n));
-  { int64_t k = i - 1;                                  // the first kept one? (only dropped ones in front:
-    while (k >= 0 && !keep[k]) k--;                     //  the walk ends at once everywhere else)
-    if (k < 0) ok = ok && (q[i] - 1 - first == 0 || q[i] - 1 - first == (int64_t) ffrun[i]);   // 0xff bytes only
-  }
-  if (!ok) atomicExch(flag,1);
+  const DxChainIn c = { q, ffrun, last, stat, soff, keep, count, first, n };
+  if (!dx_chain_check_one(c,rlen_d,i)) atomicExch(flag,1);
 }
 
 __global__ void k_qv_build_ent(int64_t count, const int32_t *cand, QvPlanArrays pa, const int32_t *well,

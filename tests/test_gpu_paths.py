@@ -467,3 +467,20 @@ def test_headers_outside_the_usual_range_still_decode(ctx, orc):
     prof = ctx.profile_report(); ctx.profile(False)
     assert back == orc.undexqv(enc) == text
     assert "k_qv_assemble" in prof, sorted(prof)          # not in place: the layout did not hold
+
+
+def test_every_header_outside_the_usual_range(ctx, orc):
+    """... and a file in which NO entry is in that range (every score above 1000): the assumed layout is
+    empty, and an empty layout must not count as confirmed (found by tests/hostfuzz/fz_chain.cpp: "all
+    kept candidates pass" is vacuously true when nothing was kept)."""
+    rng = np.random.default_rng(43)
+    lengths = [int(x) for x in rng.integers(100, 3000, size=50)]
+    text = synth.make_quiva(43, lengths)
+    lines = text.split(b"\n")
+    for e in range(len(lengths)):
+        head, rq = lines[6 * e].split(b" RQ=0.")
+        lines[6 * e] = head + b" RQ=0." + str(1500 + e).encode()
+    text = b"\n".join(lines)
+    enc = orc.dexqv(text)
+    assert ctx.dexqv(text) == enc
+    assert ctx.undexqv(enc) == text

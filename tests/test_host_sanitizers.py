@@ -2,7 +2,12 @@
 compiled with AddressSanitizer + UndefinedBehaviorSanitizer and driven by two small C harnesses
 (tests/hostfuzz/): every truncation and 20 000 random corruptions of real headers on exactly-sized
 heap buffers, and 3 000 random statistics (ties, 2^62 counts, single-symbol streams) through
-make -> write -> read.  Any report from a sanitizer fails the test.  CPU only."""
+make -> write -> read.  Any report from a sanitizer fails the test.  CPU only.
+
+Also here: the entry-chain decision of csrc/dx_chain.h (which candidates of a .dexqv image are its
+entries), whose two forms -- the host's walk and the per-candidate predicate the device evaluates after
+an in-place decode -- are driven on 100 000 random images by tests/hostfuzz/fz_chain.cpp: the walk
+against the truth, the two forms against each other, the assumed wells against the walk's."""
 import os
 import shutil
 import subprocess
@@ -59,3 +64,19 @@ def test_code_construction_under_sanitizers(built):
     out = _run([str(built / "fz_make_coding")])
     coded, refused, trips = (int(x) for x in out.split() if x.isdigit())
     assert coded + refused == 3000 and trips == coded
+
+
+@pytest.mark.timeout(900)
+def test_entry_chain_walk_and_device_predicate_agree(tmp_path):
+    if shutil.which("g++") is None:
+        pytest.skip("no g++")
+    exe = tmp_path / "fz_chain"
+    r = subprocess.run(["g++", "-std=c++17", *SAN, "-I" + os.path.join(ROOT, "dextractor_b200", "csrc"),
+                        "-o", str(exe), os.path.join(ROOT, "tests", "hostfuzz", "fz_chain.cpp")],
+                       capture_output=True, text=True)
+    if r.returncode != 0:
+        pytest.skip("sanitizer build not possible here: " + r.stderr[-300:])
+    out = _run([str(exe), "100000"])
+    assert out.startswith("ok 100000 images"), out
+    walked, assumed, broken = [int(x) for x in out.replace(":", " ").split() if x.isdigit()][1:4]
+    assert walked > 80000 and assumed > 30000 and broken > 1000, out      # every branch was exercised
